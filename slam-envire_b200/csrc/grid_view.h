@@ -1,0 +1,233 @@
+// grid_view.h -- the model index that replaces libkdtree++ on the B200 path,
+// and the exact nearest-neighbour search over it.
+//
+// Replaces: FindPairsKDTree::findPairs -> kdtree.find_nearest(node, d_box)
+//           (reference icp/icp.hpp:242-252).
+//
+// Layout (all in HBM, built once per model by grid_build.cuh):
+//   pts[n]          model points sorted by level-0 cell key (x fastest), 32 B
+//                   each: fp64 x,y,z in the global frame + insertion index
+//   cell_start[c]   exclusive prefix of points per level-0 cell, ncell+1 entries
+//                   (so x-adjacent cells form one contiguous run of pts)
+//   mask[l][c]      l >= 1: one byte per level-l cell, bit (dx|dy<<1|dz<<2) set
+//                   when that child cell of level l-1 holds at least one point.
+//                   Level l cells have edge h*2^l; the top level is one cell.
+//
+// Search: exact Euclidean NN inside the inclusive ball d_box.  The uniform grid
+// is searched as "rings" of cells around the query, but rings are expanded
+// hierarchically: the start level is the one whose cell edge covers the current
+// upper bound U (previous iteration's pair, or d_box), so the ball touches at
+// most 2x2x2 cells of that level; those cells are then descended depth-first,
+// nearest child first, skipping empty space through the occupancy masks and
+// pruning every cell whose box is farther than the best distance so far.
+// Pruning is conservative (eps slack, ">" not ">=") so the answer is the
+// lexicographic minimum over (d^2, insertion index) of ALL model points: the
+// same point a kd-tree returns, with equidistant ties resolved to the lowest
+// insertion index.  Distances are evaluated exactly like libkdtree++ does:
+// sqrt((dx*dx + dy*dy) + dz*dz) in fp64 without FMA contraction.
+//
+// The functions are __host__ __device__ so tests/ can run the very same search
+// code on the CPU (tests/harness) against the oracle before it meets a GPU.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#ifdef __CUDACC__
+#define ICPB_HD __host__ __device__ __forceinline__
+#else
+#define ICPB_HD inline
+#endif
+
+#define ICPB_MAX_LEVELS 16
+#define ICPB_NONE 0xFFFFFFFFu
+#define ICPB_SEARCH_STACK 112
+
+struct
+#ifdef __CUDACC__
+    __align__(32)
+#else
+    __attribute__((aligned(32)))
+#endif
+        MPoint {
+    double x, y, z;
+    unsigned long long idx; // insertion index (order of addToModel visits)
+};
+
+struct GridView {
+    double o[3];  // origin (min corner of the model bounding box)
+    double h;     // level-0 cell edge
+    double inv_h; // 1/h
+    double eps;   // geometric slack for pruning (1e-9 * h)
+    int dim[ICPB_MAX_LEVELS][3];
+    int L; // top level: dim[L] == {1,1,1}
+    const uint32_t *cell_start;
+    const uint8_t *mask[ICPB_MAX_LEVELS];
+    const MPoint *pts;
+    uint32_t n;
+};
+
+ICPB_HD double icpb_inf() { return __builtin_huge_val(); }
+
+// level-0 cell coordinate of a model point along one axis
+ICPB_HD int icpb_cell_coord(double p, double o, double inv_h, int dim)
+{
+    double t = floor((p - o) * inv_h);
+    if (!(t > 0.0)) t = 0.0;
+    if (t > (double)(dim - 1)) t = (double)(dim - 1);
+    return (int)t;
+}
+
+// squared distance from q to the box of cell (cx,cy,cz) at `level`, shrunk by eps
+ICPB_HD double icpb_cell_mindist2(const GridView &g, int level, int cx, int cy, int cz, double qx, double qy,
+                                  double qz)
+{
+    const double hl = g.h * (double)(1u << level);
+    double lo, gap, d2 = 0.0;
+    lo = g.o[0] + (double)cx * hl;
+    gap = fmax(fmax(lo - qx, qx - (lo + hl)) - g.eps, 0.0);
+    d2 += gap * gap;
+    lo = g.o[1] + (double)cy * hl;
+    gap = fmax(fmax(lo - qy, qy - (lo + hl)) - g.eps, 0.0);
+    d2 += gap * gap;
+    lo = g.o[2] + (double)cz * hl;
+    gap = fmax(fmax(lo - qz, qz - (lo + hl)) - g.eps, 0.0);
+    d2 += gap * gap;
+    return d2;
+}
+
+ICPB_HD void icpb_nn_eval(const MPoint &m, uint32_t pos, double qx, double qy, double qz, double &bd2,
+                          unsigned long long &bidx, uint32_t &bpos)
+{
+    const double dx = qx - m.x, dy = qy - m.y, dz = qz - m.z;
+    const double d2 = (dx * dx + dy * dy) + dz * dz;
+    if (d2 < bd2 || (d2 == bd2 && m.idx < bidx)) {
+        bd2 = d2;
+        bidx = m.idx;
+        bpos = pos;
+    }
+}
+
+ICPB_HD void icpb_scan_cell(const GridView &g, int cx, int cy, int cz, double qx, double qy, double qz, double &bd2,
+                            unsigned long long &bidx, uint32_t &bpos)
+{
+    const size_t c = ((size_t)cz * g.dim[0][1] + cy) * g.dim[0][0] + cx;
+    const uint32_t s = g.cell_start[c], e = g.cell_start[c + 1];
+    for (uint32_t p = s; p < e; ++p) icpb_nn_eval(g.pts[p], p, qx, qy, qz, bd2, bidx, bpos);
+}
+
+// Exact NN of q.  dbox2s = d_box^2 widened by a few ulps (+inf when unbounded);
+// warm_pos = position in pts[] of a candidate to seed the bound (ICPB_NONE for none).
+// Returns the position in pts[] (ICPB_NONE if the model is empty or nothing lies
+// within the bound) and the exact squared distance.  *visited counts cells scanned.
+ICPB_HD void icpb_nn_search(const GridView &g, double qx, double qy, double qz, double dbox2s, uint32_t warm_pos,
+                            uint32_t &out_pos, double &out_d2, int &start_level)
+{
+    const double INF = icpb_inf();
+    double bd2 = INF;
+    unsigned long long bidx = ~0ull;
+    uint32_t bpos = ICPB_NONE;
+    start_level = 0;
+    out_pos = ICPB_NONE;
+    out_d2 = INF;
+    if (g.n == 0) return;
+    if (warm_pos < g.n) icpb_nn_eval(g.pts[warm_pos], warm_pos, qx, qy, qz, bd2, bidx, bpos);
+
+    double bound = (dbox2s < bd2) ? dbox2s : bd2;
+    // start level: smallest l with h*2^l >= 2U, so the ball spans <= 2 cells per axis
+    int l = 0;
+    double U = INF;
+    if (bound < INF) {
+        U = sqrt(bound) * (1.0 + 1e-15) + g.eps;
+        const double ratio = 2.0 * U * g.inv_h;
+        while (l < g.L && (double)(1u << l) < ratio) ++l;
+    } else {
+        l = g.L;
+    }
+    start_level = l;
+
+    unsigned long long stack[ICPB_SEARCH_STACK];
+    int sp = 0;
+    {
+        const double inv_hl = g.inv_h / (double)(1u << l);
+        int lo[3], hi[3];
+        const double q[3] = {qx, qy, qz};
+        for (int a = 0; a < 3; ++a) {
+            const double dm1 = (double)(g.dim[l][a] - 1);
+            double flo = floor((q[a] - U - g.o[a]) * inv_hl);
+            double fhi = floor((q[a] + U - g.o[a]) * inv_hl);
+            if (!(flo > 0.0)) flo = 0.0; // also catches -inf / NaN
+            if (!(fhi < dm1)) fhi = dm1;
+            if (flo > dm1 || fhi < 0.0) { // ball misses the grid on this axis
+                out_pos = bpos;
+                out_d2 = bd2;
+                return;
+            }
+            lo[a] = (int)flo;
+            hi[a] = (int)fhi;
+        }
+        double best_md2 = INF;
+        int best_at = -1;
+        for (int z = lo[2]; z <= hi[2]; ++z)
+            for (int y = lo[1]; y <= hi[1]; ++y)
+                for (int x = lo[0]; x <= hi[0]; ++x) {
+                    const double md2 = icpb_cell_mindist2(g, l, x, y, z, qx, qy, qz);
+                    if (md2 > bound) continue;
+                    if (sp >= ICPB_SEARCH_STACK - 64) continue; // cannot happen (<= 27 roots)
+                    if (md2 < best_md2) {
+                        best_md2 = md2;
+                        best_at = sp;
+                    }
+                    stack[sp++] = ((unsigned long long)l << 60) | ((unsigned long long)z << 40) |
+                                  ((unsigned long long)y << 20) | (unsigned long long)x;
+                }
+        if (best_at >= 0) { // nearest root on top
+            const unsigned long long t = stack[best_at];
+            stack[best_at] = stack[sp - 1];
+            stack[sp - 1] = t;
+        }
+    }
+
+    const unsigned ORD = 0x76534210u; // child visiting order as XOR codes: 0,1,2,4,3,5,6,7
+    while (sp > 0) {
+        const unsigned long long e = stack[--sp];
+        const int lev = (int)(e >> 60);
+        const int cx = (int)(e & 0xFFFFFu), cy = (int)((e >> 20) & 0xFFFFFu), cz = (int)((e >> 40) & 0xFFFFFu);
+        bound = (dbox2s < bd2) ? dbox2s : bd2;
+        if (icpb_cell_mindist2(g, lev, cx, cy, cz, qx, qy, qz) > bound) continue;
+        if (lev == 0) {
+            icpb_scan_cell(g, cx, cy, cz, qx, qy, qz, bd2, bidx, bpos);
+            continue;
+        }
+        const size_t ci = ((size_t)cz * g.dim[lev][1] + cy) * g.dim[lev][0] + cx;
+        const unsigned m = g.mask[lev][ci];
+        if (!m) continue;
+        const double hc = g.h * (double)(1u << (lev - 1));
+        const unsigned near = (qx >= g.o[0] + (double)(2 * cx + 1) * hc ? 1u : 0u) |
+                              (qy >= g.o[1] + (double)(2 * cy + 1) * hc ? 2u : 0u) |
+                              (qz >= g.o[2] + (double)(2 * cz + 1) * hc ? 4u : 0u);
+        if (lev == 1) {
+            for (int k = 0; k < 8; ++k) {
+                const unsigned ch = near ^ ((ORD >> (4 * k)) & 7u);
+                if (!((m >> ch) & 1u)) continue;
+                const int x = 2 * cx + (int)(ch & 1u), y = 2 * cy + (int)((ch >> 1) & 1u),
+                          z = 2 * cz + (int)((ch >> 2) & 1u);
+                bound = (dbox2s < bd2) ? dbox2s : bd2;
+                if (icpb_cell_mindist2(g, 0, x, y, z, qx, qy, qz) > bound) continue;
+                icpb_scan_cell(g, x, y, z, qx, qy, qz, bd2, bidx, bpos);
+            }
+        } else {
+            for (int k = 7; k >= 0; --k) {
+                const unsigned ch = near ^ ((ORD >> (4 * k)) & 7u);
+                if (!((m >> ch) & 1u)) continue;
+                const int x = 2 * cx + (int)(ch & 1u), y = 2 * cy + (int)((ch >> 1) & 1u),
+                          z = 2 * cz + (int)((ch >> 2) & 1u);
+                if (icpb_cell_mindist2(g, lev - 1, x, y, z, qx, qy, qz) > bound) continue;
+                if (sp < ICPB_SEARCH_STACK)
+                    stack[sp++] = ((unsigned long long)(lev - 1) << 60) | ((unsigned long long)z << 40) |
+                                  ((unsigned long long)y << 20) | (unsigned long long)x;
+            }
+        }
+    }
+    out_pos = bpos;
+    out_d2 = bd2;
+}

@@ -1,0 +1,1038 @@
+// icpb_api.cu -- C ABI (include/icp_b200.h) over the sm_100a kernels.
+//
+// Host orchestration of the B200 trimmed-ICP path: model accumulation + grid
+// build, source upload, the _align loop (enqueued iteration by iteration, the
+// loop condition is evaluated on the device; the host only peeks at a pinned
+// flag so it never stalls the stream), and result read-back.
+// There is NO CPU fallback in this file: every compute step is a kernel.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/icp_b200.h"
+#include "grid_view.h"
+#include "pose.h"
+#include "primitives.cuh"
+#include "kernels.cuh"
+
+using namespace icpb;
+
+// ---------------------------------------------------------------------------
+// NCCL, resolved at run time (so the library loads on hosts without it and
+// shares libnccl.so.2 with whatever the embedding process already loaded)
+// ---------------------------------------------------------------------------
+namespace {
+typedef struct ncclComm *nccl_comm_t;
+typedef struct {
+    char internal[128];
+} nccl_uid_t;
+enum { NCCL_SUM = 0 };
+enum { NCCL_UINT32 = 3, NCCL_UINT64 = 5, NCCL_FLOAT64 = 8 };
+struct NcclApi {
+    void *handle = nullptr;
+    int (*GetUniqueId)(nccl_uid_t *) = nullptr;
+    int (*CommInitRank)(nccl_comm_t *, int, nccl_uid_t, int) = nullptr;
+    int (*CommDestroy)(nccl_comm_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+NcclApi g_nccl;
+bool nccl_load()
+{
+    if (g_nccl.ok) return true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names) {
+        g_nccl.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.handle) break;
+    }
+    if (!g_nccl.handle) return false;
+    g_nccl.GetUniqueId = (int (*)(nccl_uid_t *))dlsym(g_nccl.handle, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(nccl_comm_t *, int, nccl_uid_t, int))dlsym(g_nccl.handle, "ncclCommInitRank");
+    g_nccl.CommDestroy = (int (*)(nccl_comm_t))dlsym(g_nccl.handle, "ncclCommDestroy");
+    g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t))dlsym(
+        g_nccl.handle, "ncclAllReduce");
+    g_nccl.AllGather =
+        (int (*)(const void *, void *, size_t, int, nccl_comm_t, cudaStream_t))dlsym(g_nccl.handle, "ncclAllGather");
+    g_nccl.GetErrorString = (const char *(*)(int))dlsym(g_nccl.handle, "ncclGetErrorString");
+    g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.AllReduce &&
+                g_nccl.AllGather && g_nccl.GetErrorString;
+    return g_nccl.ok;
+}
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc((void **)&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    // grow, keeping the first `used` elements
+    cudaError_t ensure_keep(size_t n, size_t used, cudaStream_t s)
+    {
+        if (n <= cap) return cudaSuccess;
+        size_t nc = cap ? cap : 1024;
+        while (nc < n) nc *= 2;
+        T *q = nullptr;
+        cudaError_t e = cudaMalloc((void **)&q, nc * sizeof(T));
+        if (e != cudaSuccess) return e;
+        if (p && used) {
+            e = cudaMemcpyAsync(q, p, used * sizeof(T), cudaMemcpyDeviceToDevice, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        }
+        if (p) cudaFree(p);
+        p = q;
+        cap = nc;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+void cm_to_aff12(const double M[16], double a[12])
+{
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) a[r * 4 + c] = M[c * 4 + r];
+        a[r * 4 + 3] = M[12 + r];
+    }
+}
+void aff12_to_cm(const double a[12], double M[16])
+{
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) M[c * 4 + r] = a[r * 4 + c];
+        M[12 + r] = a[r * 4 + 3];
+        M[r * 4 + 3] = 0.0;
+    }
+    M[15] = 1.0;
+}
+
+// PointcloudAdapter iteration order (reference icp/icp.hpp:126-138):
+// idx = size_t(index); index += 1.0/density; stop when idx >= n
+const double *density_gather(const double *xyz, size_t n, double density, std::vector<double> &tmp, size_t *n_out)
+{
+    if (density == 1.0) {
+        *n_out = n;
+        return xyz;
+    }
+    tmp.clear();
+    double index = 0.0;
+    for (;;) {
+        const size_t idx = (size_t)index;
+        if (!(idx < n)) break;
+        tmp.push_back(xyz[3 * idx]);
+        tmp.push_back(xyz[3 * idx + 1]);
+        tmp.push_back(xyz[3 * idx + 2]);
+        index += 1.0 / density;
+    }
+    *n_out = tmp.size() / 3;
+    return tmp.data();
+}
+constexpr int MAX_DIM = 2048; // cells per axis (bounds the pyramid depth and the search stack)
+constexpr int EVENT_ITERS = 512;
+constexpr int FLAG_RING = 4096;
+} // namespace
+
+struct icpb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    // options
+    double opt_cell_size = 0.0, opt_target = 4.0, opt_max_cells = 64.0 * 1024 * 1024, opt_run_ahead = 2.0,
+           opt_warm = 1.0, opt_profile = 1.0;
+    // model
+    DevBuf<double> model_raw;
+    size_t model_n = 0;
+    bool grid_dirty = true;
+    DevBuf<MPoint> pts;
+    DevBuf<uint32_t> cell_start;
+    DevBuf<uint8_t> masks;
+    DevBuf<uint32_t> keys0, keys1, vals0, vals1, sort_scratch;
+    DevBuf<double> bbox_part;
+    GridView gv;
+    icpb_grid_info ginfo;
+    // source
+    DevBuf<double> stage;
+    DevBuf<double> sx, sy, sz;
+    size_t src_n = 0, adapter_size = 0;
+    double Cl2g[12];
+    bool have_source = false;
+    DevBuf<uint32_t> nn_pos;
+    DevBuf<double> nn_d;
+    // iteration
+    IcpState *d_state = nullptr;
+    IcpState *h_state = nullptr; // pinned
+    int *h_flags = nullptr;      // pinned
+    uint32_t *d_ghist = nullptr;
+    unsigned long long *d_counter = nullptr;
+    DevBuf<double> partials;
+    DevBuf<double> trace;
+    int trace_cap = 0;
+    int last_executed = 0;
+    bool last_valid = false, last_early = false;
+    // K7 / debug scratch
+    DevBuf<unsigned long long> kd0, kd1;
+    DevBuf<uint32_t> dbg_idx;
+    DevBuf<uint8_t> dbg_kept;
+    // timing
+    std::vector<cudaEvent_t> events;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_up0 = nullptr, ev_up1 = nullptr;
+    std::vector<cudaEvent_t> ring;
+    icpb_timing timing;
+    unsigned long long launches = 0;
+    // nccl
+    nccl_comm_t comm = nullptr;
+    int n_ranks = 1, rank = 0;
+    unsigned long long *d_gather = nullptr;
+
+    int fail(cudaError_t e, const char *what, int line)
+    {
+        char buf[512];
+        snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d [%s]", (int)e, cudaGetErrorString(e), __FILE__, line,
+                 what);
+        err = buf;
+        cudaGetLastError();
+        return ICPB_ERR_CUDA;
+    }
+    int fail_nccl(int rc, const char *what)
+    {
+        char buf[512];
+        snprintf(buf, sizeof(buf), "NCCL error %d (%s) in %s", rc,
+                 g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?", what);
+        err = buf;
+        return ICPB_ERR_NCCL;
+    }
+};
+
+#define CK(call)                                                    \
+    do {                                                            \
+        cudaError_t e_ = (call);                                    \
+        if (e_ != cudaSuccess) return ctx->fail(e_, #call, __LINE__); \
+    } while (0)
+#define CKL() CK(cudaGetLastError())
+#define NK(call)                                          \
+    do {                                                  \
+        int r_ = (call);                                  \
+        if (r_ != 0) return ctx->fail_nccl(r_, #call);    \
+    } while (0)
+
+static unsigned grid_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+extern "C" {
+
+const char *icpb_version(void) { return "icp_b200 0.1 (sm_100a)"; }
+
+const char *icpb_strerror(int s)
+{
+    switch (s) {
+    case ICPB_OK: return "ok";
+    case ICPB_ERR_CUDA: return "CUDA error (no device / runtime failure)";
+    case ICPB_ERR_ARG: return "invalid argument";
+    case ICPB_ERR_NO_MODEL: return "no model: call addToModel first";
+    case ICPB_ERR_NO_SOURCE: return "no source uploaded";
+    case ICPB_ERR_NCCL: return "NCCL error";
+    case ICPB_ERR_CAPACITY: return "output capacity too small";
+    case ICPB_ERR_NOT_ENOUGH_PAIRS: return "not enough pairs to get transform";
+    default: return "unknown status";
+    }
+}
+const char *icpb_last_error(const icpb_ctx *ctx) { return ctx ? ctx->err.c_str() : ""; }
+
+int icpb_create(icpb_ctx **out, int device_id)
+{
+    if (!out) return ICPB_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+        cudaGetLastError();
+        return ICPB_ERR_CUDA; // no CPU fallback
+    }
+    if (device_id < 0 || device_id >= count) return ICPB_ERR_ARG;
+    icpb_ctx *ctx = new icpb_ctx();
+    ctx->device = device_id;
+    memset(&ctx->gv, 0, sizeof(ctx->gv));
+    memset(&ctx->ginfo, 0, sizeof(ctx->ginfo));
+    memset(&ctx->timing, 0, sizeof(ctx->timing));
+    *out = ctx;
+    CK(cudaSetDevice(device_id));
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CK(cudaMalloc((void **)&ctx->d_state, sizeof(IcpState)));
+    CK(cudaMemset(ctx->d_state, 0, sizeof(IcpState)));
+    CK(cudaMallocHost((void **)&ctx->h_state, sizeof(IcpState)));
+    CK(cudaMallocHost((void **)&ctx->h_flags, FLAG_RING * sizeof(int)));
+    CK(cudaMalloc((void **)&ctx->d_ghist, (SEL_MAX_BINS + 64) * sizeof(uint32_t)));
+    CK(cudaMemset(ctx->d_ghist, 0, (SEL_MAX_BINS + 64) * sizeof(uint32_t)));
+    CK(cudaMalloc((void **)&ctx->d_counter, 8 * sizeof(unsigned long long)));
+    CK(cudaMalloc((void **)&ctx->d_gather, 64 * sizeof(unsigned long long)));
+    CK(cudaEventCreate(&ctx->ev_begin));
+    CK(cudaEventCreate(&ctx->ev_end));
+    CK(cudaEventCreate(&ctx->ev_up0));
+    CK(cudaEventCreate(&ctx->ev_up1));
+    ctx->ring.resize(64);
+    for (auto &e : ctx->ring) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return ICPB_OK;
+}
+
+void icpb_destroy(icpb_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
+    ctx->model_raw.release();
+    ctx->pts.release();
+    ctx->cell_start.release();
+    ctx->masks.release();
+    ctx->keys0.release();
+    ctx->keys1.release();
+    ctx->vals0.release();
+    ctx->vals1.release();
+    ctx->sort_scratch.release();
+    ctx->bbox_part.release();
+    ctx->stage.release();
+    ctx->sx.release();
+    ctx->sy.release();
+    ctx->sz.release();
+    ctx->nn_pos.release();
+    ctx->nn_d.release();
+    ctx->partials.release();
+    ctx->trace.release();
+    ctx->kd0.release();
+    ctx->kd1.release();
+    ctx->dbg_idx.release();
+    ctx->dbg_kept.release();
+    if (ctx->d_state) cudaFree(ctx->d_state);
+    if (ctx->h_state) cudaFreeHost(ctx->h_state);
+    if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
+    if (ctx->d_ghist) cudaFree(ctx->d_ghist);
+    if (ctx->d_counter) cudaFree(ctx->d_counter);
+    if (ctx->d_gather) cudaFree(ctx->d_gather);
+    for (auto e : ctx->events) cudaEventDestroy(e);
+    for (auto e : ctx->ring) cudaEventDestroy(e);
+    if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
+    if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+    if (ctx->ev_up0) cudaEventDestroy(ctx->ev_up0);
+    if (ctx->ev_up1) cudaEventDestroy(ctx->ev_up1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+static double *opt_slot(icpb_ctx *ctx, const char *key)
+{
+    if (!strcmp(key, "cell_size")) return &ctx->opt_cell_size;
+    if (!strcmp(key, "target_pts_per_cell")) return &ctx->opt_target;
+    if (!strcmp(key, "max_cells")) return &ctx->opt_max_cells;
+    if (!strcmp(key, "run_ahead") || !strcmp(key, "poll_every")) return &ctx->opt_run_ahead;
+    if (!strcmp(key, "warm_start")) return &ctx->opt_warm;
+    if (!strcmp(key, "profile")) return &ctx->opt_profile;
+    return nullptr;
+}
+int icpb_set_option(icpb_ctx *ctx, const char *key, double value)
+{
+    if (!ctx || !key) return ICPB_ERR_ARG;
+    double *s = opt_slot(ctx, key);
+    if (!s) return ICPB_ERR_ARG;
+    if (s == &ctx->opt_cell_size || s == &ctx->opt_target || s == &ctx->opt_max_cells) ctx->grid_dirty = true;
+    *s = value;
+    return ICPB_OK;
+}
+int icpb_get_option(const icpb_ctx *ctx, const char *key, double *value)
+{
+    if (!ctx || !key || !value) return ICPB_ERR_ARG;
+    double *s = opt_slot(const_cast<icpb_ctx *>(ctx), key);
+    if (!s) return ICPB_ERR_ARG;
+    *value = *s;
+    return ICPB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// model
+// ---------------------------------------------------------------------------
+int icpb_model_add(icpb_ctx *ctx, const double *xyz, size_t n, const double T[16], double density)
+{
+    if (!ctx || (!xyz && n) || !T || !(density > 0.0)) return ICPB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    std::vector<double> tmp;
+    size_t m = 0;
+    const double *src = density_gather(xyz, n, density, tmp, &m);
+    if (m == 0) return ICPB_OK;
+    if (ctx->model_n + m >= 0xFFFFFFF0ull) return ICPB_ERR_ARG;
+    CK(ctx->stage.ensure(3 * m));
+    CK(ctx->model_raw.ensure_keep(3 * (ctx->model_n + m), 3 * ctx->model_n, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->stage.p, src, 3 * m * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    Aff12 A;
+    cm_to_aff12(T, A.a);
+    transform_append_kernel<<<grid_for(m, 256), 256, 0, ctx->stream>>>(ctx->stage.p, m, A,
+                                                                       ctx->model_raw.p + 3 * ctx->model_n);
+    CKL();
+    CK(cudaStreamSynchronize(ctx->stream)); // tmp / caller buffer may go away
+    ctx->model_n += m;
+    ctx->grid_dirty = true;
+    return ICPB_OK;
+}
+
+int icpb_model_clear(icpb_ctx *ctx)
+{
+    if (!ctx) return ICPB_ERR_ARG;
+    ctx->model_n = 0;
+    ctx->grid_dirty = true;
+    ctx->gv.n = 0;
+    return ICPB_OK;
+}
+int icpb_model_size(const icpb_ctx *ctx, size_t *n)
+{
+    if (!ctx || !n) return ICPB_ERR_ARG;
+    *n = ctx->model_n;
+    return ICPB_OK;
+}
+
+static void dims_for(const double ext[3], double h, int d[3])
+{
+    for (int a = 0; a < 3; ++a) {
+        double v = floor(ext[a] / h) + 1.0;
+        if (v < 1.0) v = 1.0;
+        if (v > 1e9) v = 1e9;
+        d[a] = (int)v;
+    }
+}
+
+static int build_grid(icpb_ctx *ctx)
+{
+    const size_t n = ctx->model_n;
+    cudaStream_t s = ctx->stream;
+    memset(&ctx->ginfo, 0, sizeof(ctx->ginfo));
+    ctx->gv.n = 0;
+    ctx->grid_dirty = false;
+    if (n == 0) return ICPB_OK;
+    cudaEvent_t e0 = ctx->ev_up0, e1 = ctx->ev_up1;
+    CK(cudaEventRecord(e0, s));
+    // bounding box
+    const unsigned nbb = std::min<unsigned>(1024u, grid_for(n, 256));
+    CK(ctx->bbox_part.ensure((size_t)nbb * 6));
+    bbox_kernel<<<nbb, 256, 0, s>>>(ctx->model_raw.p, n, ctx->bbox_part.p);
+    CKL();
+    std::vector<double> hb((size_t)nbb * 6);
+    CK(cudaMemcpyAsync(hb.data(), ctx->bbox_part.p, hb.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (unsigned b = 0; b < nbb; ++b)
+        for (int a = 0; a < 3; ++a) {
+            mn[a] = fmin(mn[a], hb[(size_t)b * 6 + a]);
+            mx[a] = fmax(mx[a], hb[(size_t)b * 6 + 3 + a]);
+        }
+    double ext[3];
+    for (int a = 0; a < 3; ++a) {
+        ext[a] = mx[a] - mn[a];
+        if (!(ext[a] >= 0.0) || !isfinite(ext[a])) return ICPB_ERR_ARG; // NaN / inf vertices
+    }
+    double se[3] = {ext[0], ext[1], ext[2]};
+    std::sort(se, se + 3);
+    const double emax = se[2];
+    // smallest admissible cell edge: <= MAX_DIM cells per axis, <= max_cells cells in total
+    auto h_floor = [&](double h) {
+        if (emax > 0.0) h = fmax(h, emax / (double)(MAX_DIM - 1));
+        if (!(h > 0.0)) h = 1.0;
+        for (int it = 0; it < 200; ++it) {
+            int d[3];
+            dims_for(ext, h, d);
+            if ((double)d[0] * d[1] * d[2] <= ctx->opt_max_cells && d[0] <= MAX_DIM && d[1] <= MAX_DIM && d[2] <= MAX_DIM)
+                break;
+            h *= 1.1;
+        }
+        return h;
+    };
+    const bool auto_h = !(ctx->opt_cell_size > 0.0);
+    double h;
+    if (!auto_h)
+        h = h_floor(ctx->opt_cell_size);
+    else {
+        // first guess: points spread over the largest face of the bounding box
+        double area = se[2] * se[1];
+        if (!(area > 0.0)) area = se[2] * se[2];
+        h = area > 0.0 ? sqrt(ctx->opt_target * area / (double)n) : 1.0;
+        h = h_floor(h);
+    }
+    CK(ctx->keys0.ensure(n));
+    CK(ctx->keys1.ensure(n));
+    CK(ctx->vals0.ensure(n));
+    CK(ctx->vals1.ensure(n));
+    CK(ctx->sort_scratch.ensure(rs_scratch_elems(n)));
+
+    GridDims gd;
+    int dim0[3];
+    int sorted_in = 0;
+    unsigned long long occupied = 0;
+    for (int trial = 0;; ++trial) {
+        dims_for(ext, h, dim0);
+        for (int a = 0; a < 3; ++a) gd.o[a] = mn[a];
+        gd.h = h;
+        gd.inv_h = 1.0 / h;
+        gd.nx = dim0[0];
+        gd.ny = dim0[1];
+        gd.nz = dim0[2];
+        const size_t ncell = (size_t)dim0[0] * dim0[1] * dim0[2];
+        int bits = 1;
+        while (((size_t)1 << bits) < ncell) ++bits;
+        cell_keys_kernel<<<grid_for(n, 256), 256, 0, s>>>(ctx->model_raw.p, (uint32_t)n, gd, ctx->keys0.p,
+                                                          ctx->vals0.p);
+        CKL();
+        sorted_in = radix_sort<uint32_t, true>(ctx->keys0.p, ctx->vals0.p, ctx->keys1.p, ctx->vals1.p, n, bits,
+                                               ctx->sort_scratch.p, s, &ctx->launches);
+        CKL();
+        CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), s));
+        count_unique_kernel<<<std::min<unsigned>(1024u, grid_for(n, 256)), 256, 0, s>>>(
+            sorted_in ? ctx->keys1.p : ctx->keys0.p, (uint32_t)n, ctx->d_counter);
+        CKL();
+        CK(cudaMemcpyAsync(&occupied, ctx->d_counter, sizeof(occupied), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (!auto_h || trial >= 4 || occupied == 0) break;
+        const double avg = (double)n / (double)occupied;
+        if (avg >= 0.6 * ctx->opt_target && avg <= 1.6 * ctx->opt_target) break;
+        const double h_new = h_floor(h * sqrt(ctx->opt_target / avg));
+        if (fabs(h_new - h) <= 1e-3 * h) break; // clamped by the cell budget
+        h = h_new;
+    }
+    const uint32_t *keys_sorted = sorted_in ? ctx->keys1.p : ctx->keys0.p;
+    const uint32_t *perm = sorted_in ? ctx->vals1.p : ctx->vals0.p;
+    const size_t ncell = (size_t)dim0[0] * dim0[1] * dim0[2];
+
+    CK(ctx->pts.ensure(n));
+    CK(ctx->cell_start.ensure(ncell + 1 + scan_scratch_elems(ncell + 1)));
+    CK(cudaMemsetAsync(ctx->cell_start.p, 0, (ncell + 1) * sizeof(uint32_t), s));
+    gather_points_kernel<<<grid_for(n, 256), 256, 0, s>>>(ctx->model_raw.p, keys_sorted, perm, (uint32_t)n, ctx->pts.p,
+                                                          ctx->cell_start.p);
+    CKL();
+    exclusive_scan_u32(ctx->cell_start.p, ctx->cell_start.p, ncell + 1, ctx->cell_start.p + ncell + 1, s,
+                       &ctx->launches);
+    CKL();
+
+    // pyramid of occupancy masks
+    GridView &g = ctx->gv;
+    memset(&g, 0, sizeof(g));
+    for (int a = 0; a < 3; ++a) {
+        g.o[a] = mn[a];
+        g.dim[0][a] = dim0[a];
+    }
+    g.h = h;
+    g.inv_h = 1.0 / h;
+    g.eps = 1e-9 * h;
+    int L = 0;
+    size_t mask_total = 0;
+    size_t mask_off[ICPB_MAX_LEVELS] = {0};
+    while (g.dim[L][0] > 1 || g.dim[L][1] > 1 || g.dim[L][2] > 1) {
+        for (int a = 0; a < 3; ++a) g.dim[L + 1][a] = (g.dim[L][a] + 1) >> 1;
+        ++L;
+        mask_off[L] = mask_total;
+        mask_total += (size_t)g.dim[L][0] * g.dim[L][1] * g.dim[L][2];
+    }
+    g.L = L;
+    CK(ctx->masks.ensure(mask_total + 16));
+    for (int l = 1; l <= L; ++l) {
+        uint8_t *ml = ctx->masks.p + mask_off[l];
+        g.mask[l] = ml;
+        const size_t cells = (size_t)g.dim[l][0] * g.dim[l][1] * g.dim[l][2];
+        if (l == 1)
+            mask_level1_kernel<<<grid_for(cells, 256), 256, 0, s>>>(ctx->cell_start.p, g.dim[0][0], g.dim[0][1],
+                                                                    g.dim[0][2], g.dim[1][0], g.dim[1][1],
+                                                                    g.dim[1][2], ml);
+        else
+            mask_levelN_kernel<<<grid_for(cells, 256), 256, 0, s>>>(g.mask[l - 1], g.dim[l - 1][0], g.dim[l - 1][1],
+                                                                    g.dim[l - 1][2], g.dim[l][0], g.dim[l][1],
+                                                                    g.dim[l][2], ml);
+        CKL();
+    }
+    g.cell_start = ctx->cell_start.p;
+    g.pts = ctx->pts.p;
+    g.n = (uint32_t)n;
+    CK(cudaEventRecord(e1, s));
+    CK(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    icpb_grid_info &gi = ctx->ginfo;
+    for (int a = 0; a < 3; ++a) {
+        gi.origin[a] = mn[a];
+        gi.dims[a] = (uint32_t)dim0[a];
+    }
+    gi.cell_size = h;
+    gi.levels = (uint32_t)L;
+    gi.n_cells = ncell;
+    gi.n_points = n;
+    gi.n_occupied = occupied;
+    gi.build_ms = ms;
+    ctx->last_valid = false; // nn_pos of an earlier align refers to the old layout
+    return ICPB_OK;
+}
+
+int icpb_model_build(icpb_ctx *ctx, icpb_grid_info *info)
+{
+    if (!ctx) return ICPB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->grid_dirty) {
+        int rc = build_grid(ctx);
+        if (rc != ICPB_OK) return rc;
+    }
+    if (info) *info = ctx->ginfo;
+    return ICPB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// source
+// ---------------------------------------------------------------------------
+static int upload_points(icpb_ctx *ctx, const double *src, size_t m)
+{
+    cudaStream_t s = ctx->stream;
+    if (m >= 0xFFFFFFF0ull) return ICPB_ERR_ARG;
+    CK(cudaEventRecord(ctx->ev_up0, s));
+    CK(ctx->stage.ensure(3 * std::max<size_t>(m, 1)));
+    CK(ctx->sx.ensure(std::max<size_t>(m, 1)));
+    CK(ctx->sy.ensure(std::max<size_t>(m, 1)));
+    CK(ctx->sz.ensure(std::max<size_t>(m, 1)));
+    CK(ctx->nn_pos.ensure(std::max<size_t>(m, 1)));
+    CK(ctx->nn_d.ensure(std::max<size_t>(m, 1)));
+    if (m) {
+        CK(cudaMemcpyAsync(ctx->stage.p, src, 3 * m * sizeof(double), cudaMemcpyHostToDevice, s));
+        aos_to_soa_kernel<<<grid_for(m, 256), 256, 0, s>>>(ctx->stage.p, m, ctx->sx.p, ctx->sy.p, ctx->sz.p);
+        CKL();
+        ++ctx->launches;
+    }
+    CK(cudaEventRecord(ctx->ev_up1, s));
+    CK(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev_up0, ctx->ev_up1);
+    ctx->timing.upload_ms = ms;
+    ctx->src_n = m;
+    ctx->have_source = true;
+    ctx->last_valid = false;
+    return ICPB_OK;
+}
+
+int icpb_source_upload(icpb_ctx *ctx, const double *xyz, size_t n, const double T[16], double density)
+{
+    if (!ctx || (!xyz && n) || !T || !(density > 0.0)) return ICPB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    std::vector<double> tmp;
+    size_t m = 0;
+    const double *src = density_gather(xyz, n, density, tmp, &m);
+    cm_to_aff12(T, ctx->Cl2g);
+    ctx->adapter_size = (size_t)((double)n * density); // PointcloudAdapter::size() (icp/icp.hpp:143-146)
+    return upload_points(ctx, src, m);
+}
+
+int icpb_source_upload_shard(icpb_ctx *ctx, const double *xyz, size_t n_local, size_t adapter_size_global,
+                             const double T[16])
+{
+    if (!ctx || (!xyz && n_local) || !T) return ICPB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cm_to_aff12(T, ctx->Cl2g);
+    ctx->adapter_size = adapter_size_global;
+    return upload_points(ctx, xyz, n_local);
+}
+
+// ---------------------------------------------------------------------------
+// trim: the K4 launch sequence (shared by align and icpb_trim)
+// ---------------------------------------------------------------------------
+__global__ void tie_count_kernel(const double *__restrict__ nn_d, uint32_t n, IcpState *st)
+{
+    if (st->done || !st->need_tie) return;
+    const unsigned long long tau_bits = (unsigned long long)__double_as_longlong(st->tau);
+    unsigned c = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        c += ((unsigned long long)__double_as_longlong(nn_d[i]) == tau_bits) ? 1u : 0u;
+    c = __reduce_add_sync(0xFFFFFFFFu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&st->tie_local, (unsigned long long)c);
+}
+__global__ void tie_publish_kernel(IcpState *st, unsigned long long *slot)
+{
+    *slot = (st->done || !st->need_tie) ? 0ull : st->tie_local;
+}
+// ties are kept in global pair order: lower ranks first, then by local position
+__global__ void tie_quota_kernel(IcpState *st, const unsigned long long *gathered, int rank)
+{
+    if (st->done || !st->need_tie) return;
+    unsigned long long before = 0;
+    for (int r = 0; r < rank; ++r) before += gathered[r];
+    const unsigned long long local = st->tie_local;
+    unsigned long long q = st->quota > before ? st->quota - before : 0ull;
+    if (q > local) q = local;
+    st->quota = q;
+    st->cnt_eq = local;
+    st->tie_local = 0;
+    if (q == 0) {
+        st->p_cut = -1;
+        st->need_tie = 0;
+    } else if (q == local) {
+        st->p_cut = 0x100000000ll;
+        st->need_tie = 0;
+    }
+}
+
+static int launch_trim(icpb_ctx *ctx, uint32_t n)
+{
+    cudaStream_t s = ctx->stream;
+    const unsigned blocks = std::max(1u, std::min(grid_for(n, SEL_THREADS * 4), 148u * 4u));
+    const int fused = ctx->n_ranks == 1 ? 1 : 0;
+    if (!fused) // pairs found on all ranks
+        NK(g_nccl.AllReduce(&ctx->d_state->found, &ctx->d_state->found, 1, NCCL_UINT64, NCCL_SUM, ctx->comm, s));
+    for (int p = 0; p < SEL_D_PASSES; ++p) {
+        select_kernel<<<blocks, SEL_THREADS, 0, s>>>(ctx->nn_d.p, n, ctx->d_state, ctx->d_ghist, p, 0, fused, p);
+        CKL();
+        ++ctx->launches;
+        if (!fused) {
+            NK(g_nccl.AllReduce(ctx->d_ghist, ctx->d_ghist, SEL_MAX_BINS, NCCL_UINT32, NCCL_SUM, ctx->comm, s));
+            select_pick_kernel<<<1, SEL_THREADS, 0, s>>>(ctx->d_state, ctx->d_ghist, p, 0);
+            CKL();
+            ++ctx->launches;
+        }
+    }
+    if (!fused) { // split the tie quota over the ranks; the tie passes below are then rank-local
+        tie_count_kernel<<<blocks, SEL_THREADS, 0, s>>>(ctx->nn_d.p, n, ctx->d_state);
+        tie_publish_kernel<<<1, 1, 0, s>>>(ctx->d_state, ctx->d_gather + 32);
+        CKL();
+        NK(g_nccl.AllGather(ctx->d_gather + 32, ctx->d_gather, 1, NCCL_UINT64, ctx->comm, s));
+        tie_quota_kernel<<<1, 1, 0, s>>>(ctx->d_state, ctx->d_gather, ctx->rank);
+        CKL();
+        ctx->launches += 3;
+    }
+    for (int p = 0; p < SEL_T_PASSES; ++p) {
+        select_kernel<<<blocks, SEL_THREADS, 0, s>>>(ctx->nn_d.p, n, ctx->d_state, ctx->d_ghist, p, 1, 1, 6 + p);
+        CKL();
+        ++ctx->launches;
+    }
+    return ICPB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// align
+// ---------------------------------------------------------------------------
+int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
+{
+    if (!ctx || !prm || !out) return ICPB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->have_source) return ICPB_ERR_NO_SOURCE;
+    if (ctx->grid_dirty) {
+        int rc = build_grid(ctx);
+        if (rc != ICPB_OK) return rc;
+    }
+    cudaStream_t s = ctx->stream;
+    const uint32_t n = (uint32_t)ctx->src_n;
+    // n_po = measurement.size() * overlap  (icp/icp.hpp:472), size() from icp/icp.hpp:143-146
+    const size_t n_po = (size_t)((double)ctx->adapter_size * prm->overlap);
+    const size_t max_iter = prm->max_iter;
+
+    const unsigned mom_blocks = std::max(1u, std::min(grid_for(n, MOM_THREADS), 148u * 4u));
+    CK(ctx->partials.ensure((size_t)mom_blocks * ICPB_NSUMS));
+    ctx->trace_cap = (int)std::min<size_t>(std::max<size_t>(max_iter, 1), 65536);
+    CK(ctx->trace.ensure((size_t)ctx->trace_cap * ICPB_TRACE_COLS_DEV));
+    const bool profile = ctx->opt_profile != 0.0;
+    if (profile && ctx->events.empty()) {
+        ctx->events.resize((size_t)EVENT_ITERS * 4);
+        for (auto &e : ctx->events) CK(cudaEventCreate(&e));
+    }
+    const int fused = ctx->n_ranks == 1 ? 1 : 0;
+    const int run_ahead = (int)std::max(1.0, std::min(ctx->opt_run_ahead, 32.0));
+    const unsigned long long launches0 = ctx->launches;
+
+    CK(cudaEventRecord(ctx->ev_begin, s));
+    Aff12 A;
+    memcpy(A.a, ctx->Cl2g, sizeof(A.a));
+    init_state_kernel<<<1, 1, 0, s>>>(ctx->d_state, A, max_iter, prm->min_mse, prm->min_mse_diff, prm->overlap, n_po,
+                                      n, 0ull);
+    CKL();
+    ++ctx->launches;
+    for (int k = 0; k < FLAG_RING; ++k) ctx->h_flags[k] = -1;
+
+    size_t it = 0, checked = 0, timed_iters = 0;
+    bool stop = false;
+    for (; it < max_iter && !stop; ++it) {
+        // never run more than run_ahead iterations ahead of the device-side loop condition
+        if (it >= (size_t)run_ahead) {
+            CK(cudaEventSynchronize(ctx->ring[(it - run_ahead) % ctx->ring.size()]));
+        }
+        while (checked < it && ctx->h_flags[checked % FLAG_RING] != -1) {
+            if (ctx->h_flags[checked % FLAG_RING] == 1) stop = true;
+            ctx->h_flags[checked % FLAG_RING] = -1;
+            ++checked;
+        }
+        if (stop) break;
+        if (it - checked >= (size_t)FLAG_RING - 1) CK(cudaStreamSynchronize(s));
+        const bool timed = profile && it < (size_t)EVENT_ITERS;
+        cudaEvent_t *ev = timed ? &ctx->events[it * 4] : nullptr;
+        if (timed) CK(cudaEventRecord(ev[0], s));
+        search_kernel<<<grid_for(std::max<uint32_t>(n, 1), SEARCH_THREADS), SEARCH_THREADS, 0, s>>>(
+            ctx->gv, ctx->sx.p, ctx->sy.p, ctx->sz.p, n, ctx->d_state, ctx->nn_pos.p, ctx->nn_d.p,
+            ctx->opt_warm != 0.0 ? 1 : 0);
+        CKL();
+        ++ctx->launches;
+        if (timed) CK(cudaEventRecord(ev[1], s));
+        {
+            int rc = launch_trim(ctx, n);
+            if (rc != ICPB_OK) return rc;
+        }
+        if (timed) CK(cudaEventRecord(ev[2], s));
+        moments_kernel<<<mom_blocks, MOM_THREADS, 0, s>>>(ctx->gv, ctx->sx.p, ctx->sy.p, ctx->sz.p, n, ctx->d_state,
+                                                          ctx->nn_pos.p, ctx->nn_d.p, ctx->partials.p, ctx->trace.p,
+                                                          ctx->trace_cap, fused);
+        CKL();
+        ++ctx->launches;
+        if (!fused) {
+            NK(g_nccl.AllReduce(ctx->d_state->sums, ctx->d_state->sums, ICPB_NSUMS, NCCL_FLOAT64, NCCL_SUM, ctx->comm,
+                                s));
+            pose_kernel<<<1, 1, 0, s>>>(ctx->d_state, ctx->trace.p, ctx->trace_cap);
+            CKL();
+            ++ctx->launches;
+        }
+        if (timed) {
+            CK(cudaEventRecord(ev[3], s));
+            ++timed_iters;
+        }
+        CK(cudaMemcpyAsync(&ctx->h_flags[it % FLAG_RING], &ctx->d_state->done, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CK(cudaEventRecord(ctx->ring[it % ctx->ring.size()], s));
+    }
+    CK(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(IcpState), cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(ctx->ev_end, s));
+    CK(cudaStreamSynchronize(s));
+
+    const IcpState &hs = *ctx->h_state;
+    aff12_to_cm(hs.C, out->C_global2globalnew);
+    out->iter = (size_t)hs.iter;
+    out->pairs = (size_t)hs.pairs;
+    out->mse = hs.mse;
+    out->mse_diff = hs.mse_diff;
+    out->d_box = hs.d_box;
+    out->overlap = hs.overlap;
+    out->status = hs.early ? ICPB_ERR_NOT_ENOUGH_PAIRS : ICPB_OK;
+    ctx->last_executed = hs.executed;
+    ctx->last_early = hs.early != 0;
+    ctx->last_valid = hs.executed > 0;
+
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end);
+    ctx->timing.total_ms = ms;
+    ctx->timing.search_ms = ctx->timing.trim_ms = ctx->timing.solve_ms = 0.0;
+    const size_t exec_timed = std::min<size_t>(timed_iters, (size_t)hs.executed);
+    for (size_t k = 0; k < exec_timed; ++k) { // only iterations whose loop body really ran
+        float a = 0.f, b = 0.f, c = 0.f;
+        cudaEventElapsedTime(&a, ctx->events[k * 4], ctx->events[k * 4 + 1]);
+        cudaEventElapsedTime(&b, ctx->events[k * 4 + 1], ctx->events[k * 4 + 2]);
+        cudaEventElapsedTime(&c, ctx->events[k * 4 + 2], ctx->events[k * 4 + 3]);
+        ctx->timing.search_ms += a;
+        ctx->timing.trim_ms += b;
+        ctx->timing.solve_ms += c;
+    }
+    ctx->timing.iterations = exec_timed;
+    ctx->timing.kernels_launched = ctx->launches - launches0;
+    return ICPB_OK;
+}
+
+int icpb_align(icpb_ctx *ctx, const double *xyz, size_t n, const double T[16], double density, const icpb_params *prm,
+               icpb_result *out)
+{
+    int rc = icpb_source_upload(ctx, xyz, n, T, density);
+    if (rc != ICPB_OK) return rc;
+    return icpb_align_resident(ctx, prm, out);
+}
+
+int icpb_last_timing(const icpb_ctx *ctx, icpb_timing *out)
+{
+    if (!ctx || !out) return ICPB_ERR_ARG;
+    *out = ctx->timing;
+    return ICPB_OK;
+}
+
+int icpb_pairs_distance(icpb_ctx *ctx, double *out, size_t capacity, size_t *n_out)
+{
+    if (!ctx || !n_out) return ICPB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    *n_out = 0;
+    // _align returns before filling pairs_distance when pairs < MIN_PAIRS (icp/icp.hpp:475-476,500-504)
+    if (!ctx->last_valid || ctx->last_early) return ICPB_OK;
+    cudaStream_t s = ctx->stream;
+    const uint32_t n = (uint32_t)ctx->src_n;
+    const size_t kept = (size_t)ctx->h_state->pairs;
+    *n_out = kept;
+    if (!out) return ICPB_OK;
+    if (capacity < kept) return ICPB_ERR_CAPACITY;
+    if (kept == 0) return ICPB_OK;
+    CK(ctx->kd0.ensure(n));
+    CK(ctx->kd1.ensure(n));
+    CK(ctx->sort_scratch.ensure(rs_scratch_elems(n)));
+    unsigned int *cnt = (unsigned int *)(ctx->d_counter + 1);
+    CK(cudaMemsetAsync(cnt, 0, sizeof(unsigned int), s));
+    compact_kept_kernel<<<grid_for(n, 256), 256, 0, s>>>(ctx->nn_d.p, n, ctx->d_state, ctx->kd0.p, cnt);
+    CKL();
+    unsigned int h_cnt = 0;
+    CK(cudaMemcpyAsync(&h_cnt, cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if ((size_t)h_cnt != kept) {
+        ctx->err = "internal: kept-pair count mismatch";
+        return ICPB_ERR_CUDA;
+    }
+    // ascending like std::sort on distances (icp/icp.cpp:26): non-negative doubles sort as u64
+    const int where = radix_sort<unsigned long long, false>(ctx->kd0.p, nullptr, ctx->kd1.p, nullptr, kept, 64,
+                                                            ctx->sort_scratch.p, s, &ctx->launches);
+    CKL();
+    CK(cudaMemcpyAsync(out, where ? ctx->kd1.p : ctx->kd0.p, kept * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return ICPB_OK;
+}
+
+int icpb_debug_pairs(icpb_ctx *ctx, uint32_t *model_idx, double *dist, uint8_t *kept, size_t capacity, size_t *n_out)
+{
+    if (!ctx || !n_out) return ICPB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    *n_out = 0;
+    if (!ctx->last_valid) return ICPB_OK;
+    const uint32_t n = (uint32_t)ctx->src_n;
+    *n_out = n;
+    if (!model_idx && !dist && !kept) return ICPB_OK;
+    if (capacity < n) return ICPB_ERR_CAPACITY;
+    if (n == 0) return ICPB_OK;
+    cudaStream_t s = ctx->stream;
+    CK(ctx->dbg_idx.ensure(n));
+    CK(ctx->dbg_kept.ensure(n));
+    debug_pairs_kernel<<<grid_for(n, 256), 256, 0, s>>>(ctx->gv, ctx->nn_pos.p, ctx->nn_d.p, n, ctx->d_state,
+                                                        ctx->dbg_idx.p, ctx->dbg_kept.p);
+    CKL();
+    if (model_idx) CK(cudaMemcpyAsync(model_idx, ctx->dbg_idx.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    if (dist) CK(cudaMemcpyAsync(dist, ctx->nn_d.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (kept) CK(cudaMemcpyAsync(kept, ctx->dbg_kept.p, n * sizeof(uint8_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return ICPB_OK;
+}
+
+int icpb_trace(icpb_ctx *ctx, double *rows, size_t capacity_rows, size_t *n_rows)
+{
+    if (!ctx || !n_rows) return ICPB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)std::min(ctx->last_executed, ctx->trace_cap);
+    *n_rows = n;
+    if (!rows) return ICPB_OK;
+    if (capacity_rows < n) return ICPB_ERR_CAPACITY;
+    if (n) {
+        CK(cudaMemcpyAsync(rows, ctx->trace.p, n * ICPB_TRACE_COLS_DEV * sizeof(double), cudaMemcpyDeviceToHost,
+                           ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return ICPB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// kernel-level entry points
+// ---------------------------------------------------------------------------
+int icpb_find_pairs(icpb_ctx *ctx, const double *q, size_t n, double d_box, uint32_t *model_idx, double *dist)
+{
+    if (!ctx || (!q && n) || !model_idx || !dist) return ICPB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->grid_dirty) {
+        int rc = build_grid(ctx);
+        if (rc != ICPB_OK) return rc;
+    }
+    if (n == 0) return ICPB_OK;
+    if (n >= 0xFFFFFFF0ull) return ICPB_ERR_ARG;
+    cudaStream_t s = ctx->stream;
+    CK(ctx->stage.ensure(3 * n));
+    CK(ctx->dbg_idx.ensure(n));
+    CK(ctx->kd0.ensure(n));
+    CK(cudaMemcpyAsync(ctx->stage.p, q, 3 * n * sizeof(double), cudaMemcpyHostToDevice, s));
+    find_pairs_kernel<<<grid_for(n, SEARCH_THREADS), SEARCH_THREADS, 0, s>>>(ctx->gv, ctx->stage.p, (uint32_t)n, d_box,
+                                                                             ctx->dbg_idx.p, (double *)ctx->kd0.p);
+    CKL();
+    ++ctx->launches;
+    CK(cudaMemcpyAsync(model_idx, ctx->dbg_idx.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(dist, ctx->kd0.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    ctx->have_source = false; // stage / scratch were reused
+    ctx->last_valid = false;
+    return ICPB_OK;
+}
+
+__global__ void trim_setup_kernel(IcpState *st, unsigned long long n_po, unsigned long long found)
+{
+    st->done = 0;
+    st->n_po = n_po;
+    st->found = found;
+    st->need_tie = 0;
+    st->tie_local = 0;
+    st->p_cut = 0x100000000ll;
+    for (int i = 0; i < 16; ++i) st->tickets[i] = 0;
+}
+
+int icpb_trim(icpb_ctx *ctx, const double *dist, size_t n, size_t n_po, double *tau, size_t *kept, size_t *n_ties_kept)
+{
+    if (!ctx || (!dist && n) || !tau || !kept) return ICPB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (n >= 0xFFFFFFF0ull) return ICPB_ERR_ARG;
+    cudaStream_t s = ctx->stream;
+    CK(ctx->nn_d.ensure(std::max<size_t>(n, 1)));
+    size_t found = 0;
+    for (size_t i = 0; i < n; ++i) found += isfinite(dist[i]) ? 1 : 0;
+    if (n) CK(cudaMemcpyAsync(ctx->nn_d.p, dist, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    trim_setup_kernel<<<1, 1, 0, s>>>(ctx->d_state, n_po, found);
+    CKL();
+    const int saved_ranks = ctx->n_ranks;
+    ctx->n_ranks = 1; // stand-alone trim is always rank-local
+    int rc = launch_trim(ctx, (uint32_t)n);
+    ctx->n_ranks = saved_ranks;
+    if (rc != ICPB_OK) return rc;
+    CK(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(IcpState), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    *tau = ctx->h_state->sel_k > 0 ? ctx->h_state->tau : NAN;
+    *kept = (size_t)ctx->h_state->sel_k;
+    if (n_ties_kept) *n_ties_kept = (size_t)ctx->h_state->quota;
+    ctx->have_source = false;
+    ctx->last_valid = false;
+    return ICPB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// multi-GPU
+// ---------------------------------------------------------------------------
+int icpb_nccl_unique_id(uint8_t id_out[ICPB_NCCL_ID_BYTES])
+{
+    if (!id_out) return ICPB_ERR_ARG;
+    if (!nccl_load()) return ICPB_ERR_NCCL;
+    nccl_uid_t id;
+    if (g_nccl.GetUniqueId(&id) != 0) return ICPB_ERR_NCCL;
+    memcpy(id_out, &id, ICPB_NCCL_ID_BYTES);
+    return ICPB_OK;
+}
+
+int icpb_comm_init(icpb_ctx *ctx, int n_ranks, int rank, const uint8_t id_in[ICPB_NCCL_ID_BYTES])
+{
+    if (!ctx || n_ranks < 1 || n_ranks > 32 || rank < 0 || rank >= n_ranks || !id_in) return ICPB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (n_ranks == 1) {
+        ctx->n_ranks = 1;
+        ctx->rank = 0;
+        return ICPB_OK;
+    }
+    if (!nccl_load()) {
+        ctx->err = "libnccl.so.2 not found";
+        return ICPB_ERR_NCCL;
+    }
+    nccl_uid_t id;
+    memcpy(&id, id_in, ICPB_NCCL_ID_BYTES);
+    NK(g_nccl.CommInitRank(&ctx->comm, n_ranks, id, rank));
+    ctx->n_ranks = n_ranks;
+    ctx->rank = rank;
+    return ICPB_OK;
+}
+
+} // extern "C"

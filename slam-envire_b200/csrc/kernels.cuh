@@ -1,0 +1,516 @@
+// kernels.cuh -- the sm_100a kernels of the trimmed-ICP hot path.
+//
+//   K0  transform_append_kernel   model vertices -> global frame (addModel, icp/icp.hpp:231-240)
+//   K1  keys / gather / cell counts / occupancy masks: uniform-grid index build
+//   K2+K3 search_kernel           source transform fused with the exact NN search (findPairs, icp/icp.hpp:242-252)
+//   K4  select_kernel             radix-select of the n_po-th smallest distance (Pairs::trim, icp/icp.cpp:23-41)
+//   K5  moments_kernel            17 fp64 sums over the kept pairs (Pairs::getTransform, icp/icp.cpp:55-73)
+//   K6  pose step in the last block of K5 (icp/icp.cpp:76-99, icp/icp.hpp:479-485)
+//   K7  kept-distance compaction (+ radix sort) for getPairsDistance (icp/icp.hpp:500-504)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "grid_view.h"
+#include "pose.h"
+
+namespace icpb {
+
+// ---------------------------------------------------------------------------
+// K0: p = T * v  appended to the model (fp64 AoS in, AoS out)
+// ---------------------------------------------------------------------------
+struct Aff12 {
+    double a[12];
+};
+
+__global__ void transform_append_kernel(const double *__restrict__ in, size_t n, Aff12 T, double *__restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double px, py, pz;
+    icpb_aff_apply(T.a, in[3 * i], in[3 * i + 1], in[3 * i + 2], px, py, pz);
+    out[3 * i] = px;
+    out[3 * i + 1] = py;
+    out[3 * i + 2] = pz;
+}
+
+// AoS double[n][3] -> SoA x[], y[], z[] (coalesced loads for the search kernel)
+__global__ void aos_to_soa_kernel(const double *__restrict__ in, size_t n, double *__restrict__ x,
+                                  double *__restrict__ y, double *__restrict__ z)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    x[i] = in[3 * i];
+    y[i] = in[3 * i + 1];
+    z[i] = in[3 * i + 2];
+}
+
+// ---------------------------------------------------------------------------
+// K1: grid build
+// ---------------------------------------------------------------------------
+// per-block min/max of the model coordinates: out[block][6] = minx,miny,minz,maxx,maxy,maxz
+__global__ void __launch_bounds__(256) bbox_kernel(const double *__restrict__ pts, size_t n, double *__restrict__ out)
+{
+    double mn[3] = {icpb_inf(), icpb_inf(), icpb_inf()}, mx[3] = {-icpb_inf(), -icpb_inf(), -icpb_inf()};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        for (int a = 0; a < 3; ++a) {
+            const double v = pts[3 * i + a];
+            mn[a] = fmin(mn[a], v);
+            mx[a] = fmax(mx[a], v);
+        }
+    __shared__ double sm[8][6];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int a = 0; a < 3; ++a)
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[a] = fmin(mn[a], __shfl_xor_sync(0xFFFFFFFFu, mn[a], o));
+            mx[a] = fmax(mx[a], __shfl_xor_sync(0xFFFFFFFFu, mx[a], o));
+        }
+    if (lane == 0)
+        for (int a = 0; a < 3; ++a) {
+            sm[warp][a] = mn[a];
+            sm[warp][3 + a] = mx[a];
+        }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double v = sm[0][threadIdx.x];
+        for (int w = 1; w < 8; ++w) v = threadIdx.x < 3 ? fmin(v, sm[w][threadIdx.x]) : fmax(v, sm[w][threadIdx.x]);
+        out[(size_t)blockIdx.x * 6 + threadIdx.x] = v;
+    }
+}
+
+struct GridDims {
+    double o[3], h, inv_h;
+    int nx, ny, nz;
+};
+
+__global__ void cell_keys_kernel(const double *__restrict__ pts, uint32_t n, GridDims g, uint32_t *__restrict__ keys,
+                                 uint32_t *__restrict__ vals)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int cx = icpb_cell_coord(pts[3 * (size_t)i], g.o[0], g.inv_h, g.nx);
+    const int cy = icpb_cell_coord(pts[3 * (size_t)i + 1], g.o[1], g.inv_h, g.ny);
+    const int cz = icpb_cell_coord(pts[3 * (size_t)i + 2], g.o[2], g.inv_h, g.nz);
+    keys[i] = (uint32_t)(((size_t)cz * g.ny + cy) * g.nx + cx);
+    vals[i] = i;
+}
+
+// number of distinct keys in a sorted key array (occupied cells)
+__global__ void __launch_bounds__(256) count_unique_kernel(const uint32_t *__restrict__ keys, uint32_t n,
+                                                           unsigned long long *__restrict__ counter)
+{
+    unsigned c = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        c += (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(counter, (unsigned long long)c);
+}
+
+// sorted layout: pts_sorted[j] = {model[perm[j]], perm[j]}; cell_count[key[j]]++
+__global__ void gather_points_kernel(const double *__restrict__ raw, const uint32_t *__restrict__ keys,
+                                     const uint32_t *__restrict__ perm, uint32_t n, MPoint *__restrict__ out,
+                                     uint32_t *__restrict__ cell_count)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint32_t src = perm[j];
+    MPoint m;
+    m.x = raw[3 * (size_t)src];
+    m.y = raw[3 * (size_t)src + 1];
+    m.z = raw[3 * (size_t)src + 2];
+    m.idx = src;
+    out[j] = m;
+    atomicAdd(&cell_count[keys[j]], 1u);
+}
+
+// level-1 occupancy masks from the level-0 prefix array
+__global__ void mask_level1_kernel(const uint32_t *__restrict__ cell_start, int nx, int ny, int nz, int mx, int my,
+                                   int mz, uint8_t *__restrict__ mask)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)mx * my * mz) return;
+    const int cx = (int)(t % mx), cy = (int)((t / mx) % my), cz = (int)(t / ((size_t)mx * my));
+    unsigned m = 0;
+    for (int ch = 0; ch < 8; ++ch) {
+        const int x = 2 * cx + (ch & 1), y = 2 * cy + ((ch >> 1) & 1), z = 2 * cz + ((ch >> 2) & 1);
+        if (x >= nx || y >= ny || z >= nz) continue;
+        const size_t c = ((size_t)z * ny + y) * nx + x;
+        if (cell_start[c + 1] > cell_start[c]) m |= 1u << ch;
+    }
+    mask[t] = (uint8_t)m;
+}
+
+// level-l masks (l >= 2) from the masks one level below
+__global__ void mask_levelN_kernel(const uint8_t *__restrict__ below, int nx, int ny, int nz, int mx, int my, int mz,
+                                   uint8_t *__restrict__ mask)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)mx * my * mz) return;
+    const int cx = (int)(t % mx), cy = (int)((t / mx) % my), cz = (int)(t / ((size_t)mx * my));
+    unsigned m = 0;
+    for (int ch = 0; ch < 8; ++ch) {
+        const int x = 2 * cx + (ch & 1), y = 2 * cy + ((ch >> 1) & 1), z = 2 * cz + ((ch >> 2) & 1);
+        if (x >= nx || y >= ny || z >= nz) continue;
+        if (below[((size_t)z * ny + y) * nx + x]) m |= 1u << ch;
+    }
+    mask[t] = (uint8_t)m;
+}
+
+// ---------------------------------------------------------------------------
+// K2 + K3: transform the source vertex and find its exact nearest model point
+// ---------------------------------------------------------------------------
+constexpr int SEARCH_THREADS = 128;
+
+__global__ void __launch_bounds__(SEARCH_THREADS)
+    search_kernel(const GridView g, const double *__restrict__ sx, const double *__restrict__ sy,
+                  const double *__restrict__ sz, uint32_t n, IcpState *__restrict__ st, uint32_t *__restrict__ nn_pos,
+                  double *__restrict__ nn_d, int use_warm)
+{
+    if (st->done) return;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned found = 0, far = 0;
+    if (i < n) {
+        double qx, qy, qz;
+        icpb_aff_apply(st->M, sx[i], sy[i], sz[i], qx, qy, qz); // C_local2globalnew * v (icp/icp.hpp:130)
+        const double d_box = st->d_box;
+        const double dbox2s = d_box * d_box * (1.0 + 1e-12);
+        const uint32_t warm = (use_warm && st->warm) ? nn_pos[i] : ICPB_NONE;
+        uint32_t pos;
+        double d2;
+        int lvl;
+        icpb_nn_search(g, qx, qy, qz, dbox2s, warm, pos, d2, lvl);
+        const double d = sqrt(d2);
+        const bool ok = (pos != ICPB_NONE) && (d <= d_box); // inclusive ball (find_nearest(val, max))
+        nn_pos[i] = ok ? pos : ICPB_NONE;
+        nn_d[i] = ok ? d : icpb_inf();
+        found = ok ? 1u : 0u;
+        far = lvl > 0 ? 1u : 0u;
+    }
+    found = __reduce_add_sync(0xFFFFFFFFu, found);
+    far = __reduce_add_sync(0xFFFFFFFFu, far);
+    if ((threadIdx.x & 31) == 0) {
+        if (found) atomicAdd(&st->found, (unsigned long long)found);
+        if (far) atomicAdd(&st->far, (unsigned long long)far);
+    }
+}
+
+// stand-alone form for icpb_find_pairs(): queries already in the global frame (AoS)
+__global__ void __launch_bounds__(SEARCH_THREADS)
+    find_pairs_kernel(const GridView g, const double *__restrict__ q, uint32_t n, double d_box,
+                      uint32_t *__restrict__ idx_out, double *__restrict__ d_out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double dbox2s = d_box * d_box * (1.0 + 1e-12);
+    uint32_t pos;
+    double d2;
+    int lvl;
+    icpb_nn_search(g, q[3 * (size_t)i], q[3 * (size_t)i + 1], q[3 * (size_t)i + 2], dbox2s, ICPB_NONE, pos, d2, lvl);
+    const double d = sqrt(d2);
+    const bool ok = (pos != ICPB_NONE) && (d <= d_box);
+    idx_out[i] = ok ? (uint32_t)g.pts[pos].idx : ICPB_NONE;
+    d_out[i] = ok ? d : d_box; // find_nearest returns (end(), max) when nothing is found
+}
+
+// ---------------------------------------------------------------------------
+// K4: radix select.  Distances are non-negative doubles (or +inf = no pair),
+// so their bit patterns order like unsigned integers.
+// ---------------------------------------------------------------------------
+constexpr int SEL_THREADS = 256;
+constexpr int SEL_MAX_BINS = 2048;
+constexpr int SEL_D_PASSES = 6;
+constexpr int SEL_T_PASSES = 3;
+__constant__ int c_sel_d_shift[SEL_D_PASSES] = {52, 41, 30, 19, 8, 0};
+__constant__ int c_sel_d_bits[SEL_D_PASSES] = {11, 11, 11, 11, 11, 8};
+__constant__ int c_sel_t_shift[SEL_T_PASSES] = {21, 10, 0};
+__constant__ int c_sel_t_bits[SEL_T_PASSES] = {11, 11, 10};
+
+// the last block of a pass (or a stand-alone 1-block launch after the histogram
+// all-reduce) picks the bucket holding the k-th smallest key and narrows the prefix
+__device__ void select_pick(IcpState *st, uint32_t *ghist, int pass, bool tie_mode, uint32_t *smem /* >= 34 */)
+{
+    const int bits = tie_mode ? c_sel_t_bits[pass] : c_sel_d_bits[pass];
+    const int shift = tie_mode ? c_sel_t_shift[pass] : c_sel_d_shift[pass];
+    const int bins = 1 << bits;
+    const int per = (bins + SEL_THREADS - 1) / SEL_THREADS;
+    unsigned long long krem;
+    if (tie_mode)
+        krem = (pass == 0) ? st->quota : st->tie_krem;
+    else {
+        if (pass == 0) {
+            const unsigned long long k = st->n_po < st->found ? st->n_po : st->found; // min(n_po, found)
+            if (threadIdx.x == 0) st->sel_k = k;
+            krem = k;
+        } else
+            krem = st->sel_krem;
+    }
+    uint32_t c[8];
+    uint32_t local = 0;
+    for (int j = 0; j < per; ++j) {
+        const int b = threadIdx.x * per + j;
+        c[j] = b < bins ? ghist[b] : 0u;
+        local += c[j];
+    }
+    uint32_t total;
+    uint32_t before = block_exclusive_scan(local, smem, total);
+    __syncthreads();
+    for (int j = 0; j < per; ++j) { // zero for the next use
+        const int b = threadIdx.x * per + j;
+        if (b < bins) ghist[b] = 0u;
+    }
+    if (krem == 0 || krem > (unsigned long long)total) {
+        // nothing to select (no pairs / n_po == 0): tau = NaN, nothing kept
+        if (threadIdx.x == 0) {
+            if (!tie_mode) {
+                st->sel_krem = 0;
+                if (pass == SEL_D_PASSES - 1 || krem == 0) {
+                    st->tau = __builtin_nan("");
+                    st->cnt_eq = 0;
+                    st->quota = 0;
+                    st->need_tie = 0;
+                    st->p_cut = 0x100000000ll;
+                }
+            } else {
+                st->tie_krem = 0;
+                st->p_cut = 0x100000000ll;
+            }
+        }
+        return;
+    }
+    unsigned long long run = before;
+    for (int j = 0; j < per; ++j) {
+        const int b = threadIdx.x * per + j;
+        if (b < bins && run < krem && krem <= run + c[j]) {
+            if (!tie_mode) {
+                const unsigned long long prefix = (pass == 0 ? 0ull : st->sel_prefix) | ((unsigned long long)b << shift);
+                st->sel_prefix = prefix;
+                st->sel_krem = krem - run;
+                if (pass == SEL_D_PASSES - 1) {
+                    st->tau = __longlong_as_double((long long)prefix);
+                    st->cnt_eq = c[j];
+                    st->quota = krem - run;
+                    st->need_tie = (krem - run) < (unsigned long long)c[j] ? 1u : 0u;
+                    st->p_cut = 0x100000000ll;
+                }
+            } else {
+                const unsigned prefix = (pass == 0 ? 0u : st->tie_prefix) | ((unsigned)b << shift);
+                st->tie_prefix = prefix;
+                st->tie_krem = krem - run;
+                if (pass == SEL_T_PASSES - 1) st->p_cut = (long long)prefix;
+            }
+        }
+        run += c[j];
+    }
+}
+
+// One histogram pass.  tie_mode == 0: key = bits(nn_d[i]).  tie_mode == 1: key = i
+// restricted to entries with nn_d[i] == tau (decides WHICH equidistant pairs survive:
+// those at the lowest positions, i.e. a stable sort by (distance, pair index)).
+__global__ void __launch_bounds__(SEL_THREADS)
+    select_kernel(const double *__restrict__ nn_d, uint32_t n, IcpState *__restrict__ st, uint32_t *__restrict__ ghist,
+                  int pass, int tie_mode, int fused_pick, int ticket_slot)
+{
+    if (st->done) return;
+    if (tie_mode && !st->need_tie) return;
+    if (!tie_mode && pass > 0 && st->sel_krem == 0) return; // nothing to select this iteration
+    __shared__ uint32_t hist[SEL_MAX_BINS];
+    __shared__ uint32_t scan_smem[34];
+    __shared__ int is_last;
+    const int bits = tie_mode ? c_sel_t_bits[pass] : c_sel_d_bits[pass];
+    const int shift = tie_mode ? c_sel_t_shift[pass] : c_sel_d_shift[pass];
+    const int bins = 1 << bits;
+    for (int b = threadIdx.x; b < bins; b += SEL_THREADS) hist[b] = 0;
+    __syncthreads();
+    const unsigned bin_mask = (unsigned)bins - 1u;
+    if (!tie_mode) {
+        const unsigned long long prefix = pass == 0 ? 0ull : st->sel_prefix;
+        const int hs = shift + bits; // bits above the current digit must match the prefix
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const unsigned long long key = (unsigned long long)__double_as_longlong(nn_d[i]);
+            if (pass == 0 || (key >> hs) == (prefix >> hs)) atomicAdd(&hist[(unsigned)(key >> shift) & bin_mask], 1u);
+        }
+    } else {
+        const unsigned long long tau_bits = (unsigned long long)__double_as_longlong(st->tau);
+        const unsigned prefix = pass == 0 ? 0u : st->tie_prefix;
+        const int hs = shift + bits;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const unsigned long long key = (unsigned long long)__double_as_longlong(nn_d[i]);
+            if (key != tau_bits) continue;
+            if (pass == 0 || hs >= 32 || (i >> hs) == (prefix >> hs)) atomicAdd(&hist[(i >> shift) & bin_mask], 1u);
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < bins; b += SEL_THREADS)
+        if (hist[b]) atomicAdd(&ghist[b], hist[b]);
+    if (!fused_pick) return;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(&st->tickets[ticket_slot], 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) st->tickets[ticket_slot] = 0;
+    select_pick(st, ghist, pass, tie_mode != 0, scan_smem);
+}
+
+// stand-alone pick (multi-GPU: runs after the histogram all-reduce)
+__global__ void __launch_bounds__(SEL_THREADS) select_pick_kernel(IcpState *st, uint32_t *ghist, int pass, int tie_mode)
+{
+    if (st->done) return;
+    if (tie_mode && !st->need_tie) return;
+    if (!tie_mode && pass > 0 && st->sel_krem == 0) return;
+    __shared__ uint32_t scan_smem[34];
+    select_pick(st, ghist, pass, tie_mode != 0, scan_smem);
+}
+
+__device__ __forceinline__ bool pair_kept(double d, uint32_t i, double tau, long long p_cut)
+{
+    return d < tau || (d == tau && (long long)i <= p_cut);
+}
+
+// ---------------------------------------------------------------------------
+// K5 (+K6): moments over the kept pairs, deterministic two-stage reduction,
+// closed-form pose step in the last block
+// ---------------------------------------------------------------------------
+constexpr int MOM_THREADS = 256;
+
+__device__ __forceinline__ double shfl_xor_double(double v, int o)
+{
+    return __shfl_xor_sync(0xFFFFFFFFu, v, o);
+}
+
+__global__ void __launch_bounds__(MOM_THREADS)
+    moments_kernel(const GridView g, const double *__restrict__ sx, const double *__restrict__ sy,
+                   const double *__restrict__ sz, uint32_t n, IcpState *__restrict__ st,
+                   const uint32_t *__restrict__ nn_pos, const double *__restrict__ nn_d, double *__restrict__ partials,
+                   double *__restrict__ trace, int trace_cap, int fused_pose)
+{
+    if (st->done) return;
+    __shared__ double sm[MOM_THREADS / 32][ICPB_NSUMS];
+    __shared__ int is_last;
+    double acc[ICPB_NSUMS];
+#pragma unroll
+    for (int k = 0; k < ICPB_NSUMS; ++k) acc[k] = 0.0;
+    const double tau = st->tau;
+    const long long p_cut = st->p_cut;
+    const bool any = st->sel_k > 0;
+    double M[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) M[k] = st->M[k];
+    if (any)
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const double d = nn_d[i];
+            if (!pair_kept(d, i, tau, p_cut)) continue;
+            double px, py, pz;
+            icpb_aff_apply(M, sx[i], sy[i], sz[i], px, py, pz); // p: the transformed source vertex
+            const MPoint m = g.pts[nn_pos[i]];                  // x: its model point
+            acc[0] += px;
+            acc[1] += py;
+            acc[2] += pz;
+            acc[3] += m.x;
+            acc[4] += m.y;
+            acc[5] += m.z;
+            acc[6] += px * m.x;
+            acc[7] += px * m.y;
+            acc[8] += px * m.z;
+            acc[9] += py * m.x;
+            acc[10] += py * m.y;
+            acc[11] += py * m.z;
+            acc[12] += pz * m.x;
+            acc[13] += pz * m.y;
+            acc[14] += pz * m.z;
+            acc[15] += d * d; // mu_d += d*d (icp/icp.cpp:60-61)
+            acc[16] += 1.0;
+        }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < ICPB_NSUMS; ++k) {
+        double v = acc[k];
+        for (int o = 16; o > 0; o >>= 1) v += shfl_xor_double(v, o);
+        if (lane == 0) sm[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < ICPB_NSUMS) {
+        double v = 0.0;
+        for (int w = 0; w < MOM_THREADS / 32; ++w) v += sm[w][threadIdx.x];
+        partials[(size_t)blockIdx.x * ICPB_NSUMS + threadIdx.x] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(&st->tickets[15], 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // fixed-order reduction of the block partials: column k by warp (k % 8), lanes stride the blocks
+    for (int k = warp; k < ICPB_NSUMS; k += MOM_THREADS / 32) {
+        double v = 0.0;
+        for (unsigned b = lane; b < gridDim.x; b += 32) v += partials[(size_t)b * ICPB_NSUMS + k];
+        for (int o = 16; o > 0; o >>= 1) v += shfl_xor_double(v, o);
+        if (lane == 0) st->sums[k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        st->tickets[15] = 0;
+        if (fused_pose) {
+            const int row = st->executed;
+            icpb_iteration_finish(*st, row < trace_cap ? trace + (size_t)row * ICPB_TRACE_COLS_DEV : nullptr);
+        }
+    }
+}
+
+// stand-alone pose step (multi-GPU: after the all-reduce of the 17 sums)
+__global__ void pose_kernel(IcpState *st, double *trace, int trace_cap)
+{
+    if (st->done) return;
+    const int row = st->executed;
+    icpb_iteration_finish(*st, row < trace_cap ? trace + (size_t)row * ICPB_TRACE_COLS_DEV : nullptr);
+}
+
+__global__ void init_state_kernel(IcpState *st, Aff12 Cl2g, unsigned long long max_iter, double min_mse,
+                                  double min_mse_diff, double overlap, unsigned long long n_po,
+                                  unsigned long long n_local, unsigned long long n_offset)
+{
+    icpb_state_init(*st, Cl2g.a, max_iter, min_mse, min_mse_diff, overlap, n_po);
+    st->n_local = n_local;
+    st->n_global_offset = n_offset;
+    st->sel_prefix = st->sel_krem = st->sel_k = 0;
+    st->cnt_eq = st->quota = 0;
+    st->tie_prefix = 0;
+    st->tie_krem = 0;
+    st->tie_local = 0;
+    for (int k = 0; k < ICPB_NSUMS; ++k) st->sums[k] = 0.0;
+}
+
+// ---------------------------------------------------------------------------
+// K7 + debug: kept distances / correspondences of the last executed iteration
+// ---------------------------------------------------------------------------
+__global__ void compact_kept_kernel(const double *__restrict__ nn_d, uint32_t n, const IcpState *__restrict__ st,
+                                    unsigned long long *__restrict__ out_keys, unsigned int *__restrict__ counter)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool keep = false;
+    double d = 0.0;
+    if (i < n && st->sel_k > 0) {
+        d = nn_d[i];
+        keep = pair_kept(d, i, st->tau, st->p_cut);
+    }
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+    if (!m) return;
+    const int lane = threadIdx.x & 31;
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(counter, (unsigned)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (keep) out_keys[base + __popc(m & ((1u << lane) - 1u))] = (unsigned long long)__double_as_longlong(d);
+}
+
+__global__ void debug_pairs_kernel(const GridView g, const uint32_t *__restrict__ nn_pos,
+                                   const double *__restrict__ nn_d, uint32_t n, const IcpState *__restrict__ st,
+                                   uint32_t *__restrict__ idx_out, uint8_t *__restrict__ kept_out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t pos = nn_pos[i];
+    idx_out[i] = pos == ICPB_NONE ? ICPB_NONE : (uint32_t)g.pts[pos].idx;
+    kept_out[i] = (st->sel_k > 0 && pair_kept(nn_d[i], i, st->tau, st->p_cut)) ? 1 : 0;
+}
+
+} // namespace icpb
