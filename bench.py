@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py -- trimmed-ICP hot path on B200: ICP correspondences/s and ms per align.
+
+Workload (BASELINE.json configs[1], SURVEY.md section 8d "cfg2"): 1M-point model vs 1M-point source,
+perturbed copy (3 deg, 0.3 m) + Gaussian noise sigma 0.01 m, overlap 0.8.  One STEP = one complete
+Trimmed::_align (all iterations until the reference's own stopping rule fires) of that workload.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (B200 kernels through the C ABI)
+  python bench.py --impl reference ...                         the CPU restatement of the reference on host cores
+
+N > 1 (torchrun, one rank per GPU): the source is sharded (each rank holds its own 1M-point shard, weak
+scaling), the model grid is replicated, and the two per-iteration collectives go over NCCL.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_MODEL = 1_000_000
+N_SOURCE = 1_000_000
+ALIGN = dict(max_iter=50, min_mse=1e-10, min_mse_diff=1e-9, overlap=0.8)
+METRIC = "icp_correspondences_per_sec"
+UNIT = "correspondences/s"
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def workload(rank=0, scale=1.0):
+    synth = importlib.import_module("slam-envire_b200.synth")
+    n_m, n_s = int(N_MODEL * scale), int(N_SOURCE * scale)
+    model = synth.scene(n_m, 100.0, 2)
+    # every rank's shard is an independent noisy observation of the same scene under the same rigid motion
+    src, T = synth.perturbed_copy(model[:n_s] if n_s <= n_m else model, 3.0, 0.3, 0.01, seed=3 + rank)
+    return model, src, T
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(model, src, max_iter, threads):
+    """Time the CPU restatement of the reference (oracle) on a bounded sample: `max_iter` full-size iterations."""
+    from oracle import oracle as O
+    O.build()
+    t0 = time.perf_counter()
+    M = O.Model()
+    M.add(model)
+    t_build = time.perf_counter() - t0
+    run = O.Run()
+    t0 = time.perf_counter()
+    r = M.align(src, run=run, threads=threads, **dict(ALIGN, max_iter=max_iter))
+    dt = time.perf_counter() - t0
+    iters = max(len(run.trace()), 1)
+    return dict(corr_per_s=len(src) * iters / dt, ms_per_iter=1e3 * dt / iters, iters=iters, build_s=t_build,
+                timing=run.timing(), result=r)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    model, src, _ = workload(0)
+    vals, per_step_iters = [], 2
+    for k in range(args.warmup + args.steps):
+        # each step: a bounded sample of the workload = the first `per_step_iters` iterations at full size
+        out = cpu_reference_run(model, src, per_step_iters, cores)
+        if k >= args.warmup:
+            vals.append(out)
+        if k == 0 and out["ms_per_iter"] * per_step_iters * (args.warmup + args.steps) > 240e3:
+            break  # keep the whole run within a few minutes
+    if not vals:
+        vals = [out]
+    v = float(np.mean([o["corr_per_s"] for o in vals]))
+    ms = float(np.mean([o["ms_per_iter"] for o in vals])) * per_step_iters
+    sample = "first %d of ~%d iterations of the 1M-vs-1M align (kd-tree of 1M pts prebuilt, %.1f s)" % (
+        per_step_iters, ALIGN["max_iter"], vals[0]["build_s"])
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg2: 1M-pt model vs 1M-pt source, 3deg/0.3m + sigma 0.01 m noise, overlap 0.8",
+                   "align": ALIGN, "note": "CPU restatement of the reference (oracle/icp_oracle.c): the reference "
+                   "itself cannot be built here (no Eigen/Boost/libkdtree++); OpenMP over queries on all host cores"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module("slam-envire_b200")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    model, src, T_true = workload(rank)
+    n_s = len(src)
+    icp = pkg.Icp(local)
+    if world > 1:
+        uid = torch.zeros(pkg.NCCL_ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(pkg.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        icp.comm_init(world, rank, bytes(uid.cpu().numpy().tobytes()))
+    icp.add_to_model(model)
+    gi = icp.build()
+
+    # pinned host copy of this rank's source for the end-to-end leg
+    src_pinned = torch.from_numpy(src).pin_memory()
+    src_host = src_pinned.numpy()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def upload():
+        if world > 1:
+            icp.upload_source_shard(src_host, n_s * world)
+        else:
+            icp.upload_source(src_host)
+
+    # ---- device-resident leg: `value` ----
+    upload()
+    res = None
+    for _ in range(args.warmup):
+        flush.zero_()
+        barrier()
+        res = icp.align_resident(**ALIGN)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    dev_ms, search_ms, trim_ms, solve_ms, iters, launches = [], 0.0, 0.0, 0.0, 0, 0
+    barrier()
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        barrier()
+        res = icp.align_resident(**ALIGN)
+        t = icp.timing()
+        dev_ms.append(t["total_ms"])
+        search_ms += t["search_ms"]
+        trim_ms += t["trim_ms"]
+        solve_ms += t["solve_ms"]
+        iters += t["iterations"]
+        launches += t["kernels_launched"]
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = float(np.sum(dev_ms))
+    if world > 1:
+        tt = torch.tensor([step_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        step_ms = float(tt.item())
+    n_iter_per_step = len(icp.trace())
+    total_corr = float(n_s) * world * n_iter_per_step * args.steps
+    value = total_corr / (step_ms * 1e-3)
+
+    # ---- end-to-end leg: host buffers in, result out, every step ----
+    e2e_s = []
+    for k in range(max(1, min(args.warmup, 2)) + args.steps):
+        flush.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        if world > 1:
+            icp.upload_source_shard(src_host, n_s * world)
+            r2 = icp.align_resident(**ALIGN)
+        else:
+            r2 = icp.align(src_host, **ALIGN)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if k >= max(1, min(args.warmup, 2)):
+            e2e_s.append(dt)
+    e2e_total = float(np.sum(e2e_s))
+    if world > 1:
+        tt = torch.tensor([e2e_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_total = float(tt.item())
+    e2e_value = float(n_s) * world * len(icp.trace()) * len(e2e_s) / e2e_total
+
+    if rank == 0:
+        peak, peak_kind = measured_peak_gbs()
+        # K3 algorithmic bytes per launch: per source point 24 B read + 4 B idx + 8 B distance written,
+        # plus the model read once at 16 B/pt (DESIGN.md "Roofline accounting")
+        k3_bytes = n_s * 36.0 + len(model) * 16.0
+        k3_ms = search_ms / max(iters, 1)
+        achieved = k3_bytes / (k3_ms * 1e-3) / 1e9 if k3_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cfg2: 1M-pt model vs 1M-pt source per GPU, 3deg/0.3m + sigma 0.01 m noise, "
+                                   "overlap 0.8", "align": ALIGN, "iterations_per_align": n_iter_per_step,
+                       "ms_per_iteration": step_ms / args.steps / max(n_iter_per_step, 1),
+                       "sharding": "source sharded x%d, model grid replicated" % world,
+                       "l2": "256 MB buffer written between steps (L2 flush)",
+                       "grid": {"cell_size": gi.cell_size, "dims": list(gi.dims), "levels": gi.levels,
+                                "occupied_cells": gi.n_occupied, "build_ms": gi.build_ms},
+                       "final": {"mse": res.mse, "pairs": res.pairs, "iter": res.iter},
+                       "phase_ms_per_iteration": {"search": search_ms / max(iters, 1), "trim": trim_ms / max(iters, 1),
+                                                  "moments_pose": solve_ms / max(iters, 1)},
+                       "wall_s_timed_region": wall},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(src_host.nbytes),
+                    "d2h_bytes_per_step": 200 + 4 * len(icp.trace()), "ms_per_step": 1e3 * e2e_total / len(e2e_s)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "search_kernel (K2+K3)", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
+                         "launch_ms": k3_ms, "algorithmic_bytes_per_launch": k3_bytes},
+        }
+        if world == 1 and not args.no_cpu:
+            cb = cpu_reference_run(model, src, 2, os.cpu_count() or 1)
+            line["cpu_baseline"] = {"value": cb["corr_per_s"], "unit": UNIT, "cores": os.cpu_count() or 1,
+                                    "kind": "port",
+                                    "sample": "first 2 iterations of the same 1M-vs-1M align, OpenMP over queries "
+                                              "(%.0f ms/iteration; kd-tree build %.1f s not counted)" % (
+                                                  cb["ms_per_iter"], cb["build_s"])}
+        print(json.dumps(line))
+    icp.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -123,6 +123,8 @@ typedef struct {
     uint64_t iterations, kernels_launched;
 } icpb_timing;
 int icpb_last_timing(const icpb_ctx *, icpb_timing *out);
+/* per-iteration device times (ms) of the last align: rows of 3 doubles [search, trim, moments+pose] */
+int icpb_iteration_times(const icpb_ctx *, double *rows, size_t capacity_rows, size_t *n_rows);
 
 /* ---- kernel-level entry points (parity tests of single stages) -------- */
 /* K3: exact NN of n query points (already in the global frame) against the

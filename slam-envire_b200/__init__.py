@@ -25,7 +25,7 @@ SYMBOLS = [
     "icpb_create", "icpb_destroy", "icpb_strerror", "icpb_last_error", "icpb_version", "icpb_set_option",
     "icpb_get_option", "icpb_model_add", "icpb_model_clear", "icpb_model_size", "icpb_model_build",
     "icpb_source_upload", "icpb_align_resident", "icpb_align", "icpb_pairs_distance", "icpb_debug_pairs",
-    "icpb_trace", "icpb_last_timing", "icpb_find_pairs", "icpb_trim", "icpb_nccl_unique_id", "icpb_comm_init",
+    "icpb_trace", "icpb_last_timing", "icpb_iteration_times", "icpb_find_pairs", "icpb_trim", "icpb_nccl_unique_id", "icpb_comm_init",
     "icpb_source_upload_shard",
 ]
 
@@ -95,6 +95,7 @@ def load_library():
     L.icpb_debug_pairs.argtypes = [vp, up, dp, C.POINTER(C.c_uint8), C.c_size_t, sp]
     L.icpb_trace.argtypes = [vp, dp, C.c_size_t, sp]
     L.icpb_last_timing.argtypes = [vp, C.POINTER(Timing)]
+    L.icpb_iteration_times.argtypes = [vp, dp, C.c_size_t, sp]
     L.icpb_find_pairs.argtypes = [vp, dp, C.c_size_t, C.c_double, up, dp]
     L.icpb_trim.argtypes = [vp, dp, C.c_size_t, C.c_size_t, dp, sp, sp]
     L.icpb_nccl_unique_id.argtypes = [C.POINTER(C.c_uint8)]
@@ -237,6 +238,15 @@ class Icp:
         self._ck(self._L.icpb_last_timing(self._h, C.byref(t)))
         return dict(total_ms=t.total_ms, upload_ms=t.upload_ms, search_ms=t.search_ms, trim_ms=t.trim_ms,
                     solve_ms=t.solve_ms, iterations=t.iterations, kernels_launched=t.kernels_launched)
+
+    def iteration_times(self):
+        n = C.c_size_t()
+        self._ck(self._L.icpb_iteration_times(self._h, None, 0, C.byref(n)))
+        rows = np.zeros((n.value, 3))
+        if n.value:
+            self._ck(self._L.icpb_iteration_times(self._h, rows.ctypes.data_as(C.POINTER(C.c_double)), n.value,
+                                                  C.byref(n)))
+        return rows
 
     # -- single stages ----------------------------------------------------
     def find_pairs(self, q, d_box=np.inf):

@@ -196,6 +196,7 @@ struct icpb_ctx {
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_up0 = nullptr, ev_up1 = nullptr;
     std::vector<cudaEvent_t> ring;
     icpb_timing timing;
+    std::vector<double> iter_ms;
     unsigned long long launches = 0;
     // nccl
     nccl_comm_t comm = nullptr;
@@ -827,6 +828,7 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
     ctx->timing.total_ms = ms;
     ctx->timing.search_ms = ctx->timing.trim_ms = ctx->timing.solve_ms = 0.0;
     const size_t exec_timed = std::min<size_t>(timed_iters, (size_t)hs.executed);
+    ctx->iter_ms.assign(exec_timed * 3, 0.0);
     for (size_t k = 0; k < exec_timed; ++k) { // only iterations whose loop body really ran
         float a = 0.f, b = 0.f, c = 0.f;
         cudaEventElapsedTime(&a, ctx->events[k * 4], ctx->events[k * 4 + 1]);
@@ -835,6 +837,9 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
         ctx->timing.search_ms += a;
         ctx->timing.trim_ms += b;
         ctx->timing.solve_ms += c;
+        ctx->iter_ms[k * 3] = a;
+        ctx->iter_ms[k * 3 + 1] = b;
+        ctx->iter_ms[k * 3 + 2] = c;
     }
     ctx->timing.iterations = exec_timed;
     ctx->timing.kernels_launched = ctx->launches - launches0;
@@ -853,6 +858,17 @@ int icpb_last_timing(const icpb_ctx *ctx, icpb_timing *out)
 {
     if (!ctx || !out) return ICPB_ERR_ARG;
     *out = ctx->timing;
+    return ICPB_OK;
+}
+
+int icpb_iteration_times(const icpb_ctx *ctx, double *rows, size_t capacity_rows, size_t *n_rows)
+{
+    if (!ctx || !n_rows) return ICPB_ERR_ARG;
+    const size_t n = ctx->iter_ms.size() / 3;
+    *n_rows = n;
+    if (!rows) return ICPB_OK;
+    if (capacity_rows < n) return ICPB_ERR_CAPACITY;
+    memcpy(rows, ctx->iter_ms.data(), n * 3 * sizeof(double));
     return ICPB_OK;
 }
 

@@ -1,0 +1,259 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): correspondence indices bit-exact except equidistant ties, distances
+bit-exact, final transform within 1e-5 rad / 1e-6 of the scene extent, final MSE within 1e-5 relative.
+"""
+import numpy as np
+import pytest
+
+from conftest import assert_transform_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _pairs_match(i_gpu, d_gpu, i_ref, d_ref, d_box):
+    d_ref = np.where(i_ref == 0xFFFFFFFF, d_box, d_ref)
+    assert np.array_equal(d_gpu, d_ref), "distances must be bit-exact"
+    diff = i_gpu != i_ref
+    # a differing index is only admissible as an equidistant tie: same distance, both valid
+    assert not np.any(diff & ((i_gpu == 0xFFFFFFFF) | (i_ref == 0xFFFFFFFF)))
+    return int(diff.sum())
+
+
+@pytest.mark.parametrize("nm,nq,d_box,seed", [
+    (20000, 20000, np.inf, 1), (20000, 20000, 0.3, 2), (5, 1000, np.inf, 3), (1, 10, 0.5, 4),
+    (200000, 100000, np.inf, 5), (200000, 100000, 0.05, 6),
+])
+def test_find_pairs_random(icp, oracle, nm, nq, d_box, seed):
+    rng = np.random.default_rng(seed)
+    m = rng.uniform(-10, 10, (nm, 3))
+    q = rng.uniform(-12, 12, (nq, 3))
+    icp.clear_model()
+    icp.add_to_model(m)
+    M = oracle.Model()
+    M.add(m)
+    i_ref, d_ref = M.find_pairs(q, d_box=d_box)
+    i_gpu, d_gpu = icp.find_pairs(q, d_box=d_box)
+    assert _pairs_match(i_gpu, d_gpu, i_ref, d_ref, d_box) == 0  # random data: no ties at all
+
+
+def test_find_pairs_scene_accumulated_model(icp, oracle, synth):
+    """addToModel accumulates (icp/icp.hpp:231-240); model clouds carry their own C_local2global."""
+    m = synth.scene(60000, 20.0, 7)
+    T2 = synth.rigid((0, 0, 1), 0.3, (25.0, 0.0, 0.5))
+    icp.clear_model()
+    icp.add_to_model(m[:40000])
+    icp.add_to_model(m[40000:], T=T2, density=0.5)
+    M = oracle.Model()
+    M.add(m[:40000])
+    M.add(m[40000:], T=T2, density=0.5)
+    assert icp.model_size() == M.size() == 50000
+    q = synth.perturbed_copy(m, 4.0, 0.3, 0.01, seed=8)[0]
+    for d_box in (np.inf, 0.2):
+        i_ref, d_ref = M.find_pairs(q, d_box=d_box)
+        i_gpu, d_gpu = icp.find_pairs(q, d_box=d_box)
+        assert _pairs_match(i_gpu, d_gpu, i_ref, d_ref, d_box) == 0
+
+
+def test_find_pairs_grid_ties(icp, oracle):
+    """Lattice model + lattice-midpoint queries: every query has equidistant candidates; distances stay exact
+    and the GPU resolves ties to the lowest insertion index, like the oracle."""
+    g = np.arange(0, 16, dtype=np.float64)
+    m = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    q = m[:2000] + 0.5
+    icp.clear_model()
+    icp.add_to_model(m)
+    M = oracle.Model()
+    M.add(m)
+    i_ref, d_ref = M.find_pairs(q, brute=True)
+    i_gpu, d_gpu = icp.find_pairs(q)
+    _pairs_match(i_gpu, d_gpu, i_ref, d_ref, np.inf)
+    assert np.array_equal(i_gpu, i_ref)
+
+
+def test_find_pairs_empty_model_and_far_queries(icp, oracle):
+    icp.clear_model()
+    i, d = icp.find_pairs(np.zeros((4, 3)), d_box=1.0)
+    assert np.all(i == 0xFFFFFFFF) and np.all(d == 1.0)
+    m = np.random.default_rng(0).uniform(0, 1, (1000, 3))
+    icp.add_to_model(m)
+    q = np.array([[1e6, 0, 0], [-1e6, 5, 5], [0.5, 0.5, 1e5]])
+    M = oracle.Model()
+    M.add(m)
+    i_ref, d_ref = M.find_pairs(q, brute=True)
+    i_gpu, d_gpu = icp.find_pairs(q)
+    assert np.array_equal(i_gpu, i_ref) and np.array_equal(d_gpu, d_ref)
+
+
+@pytest.mark.parametrize("n,frac,seed", [(100000, 0.8, 1), (100000, 1.0, 2), (1000, 0.5, 3), (7, 0.9, 4), (3, 0.0, 5)])
+def test_trim_random(icp, oracle, n, frac, seed):
+    rng = np.random.default_rng(seed)
+    d = np.abs(rng.normal(0, 1, n)) * rng.choice([1e-3, 1.0, 50.0], n)
+    d[rng.random(n) < 0.1] = np.inf  # no pair
+    found = int(np.isfinite(d).sum())
+    n_po = int(n * frac)
+    order, tau_ref = oracle.trim(d[np.isfinite(d)], n_po)
+    tau, kept, ties = icp.trim(d, n_po)
+    assert kept == len(order) == min(n_po, found)
+    if kept:
+        assert tau == tau_ref
+        assert ties == 1
+    else:
+        assert np.isnan(tau) and np.isnan(tau_ref)
+
+
+def test_trim_massive_ties(icp, oracle):
+    d = np.repeat(np.array([0.0, 0.25, 0.5, 1.0]), 2500)
+    np.random.default_rng(0).shuffle(d)
+    for n_po in (1, 2499, 2500, 2501, 6000, 9999, 10000, 20000):
+        order, tau_ref = oracle.trim(d, n_po)
+        tau, kept, ties = icp.trim(d, n_po)
+        assert kept == len(order) and tau == tau_ref
+        assert ties == kept - int((d < tau).sum())
+
+
+def _align_both(icp, oracle, model, src, T_src=None, density=1.0, **prm):
+    icp.clear_model()
+    icp.add_to_model(model)
+    M = oracle.Model()
+    M.add(model)
+    run = oracle.Run()
+    r_ref = M.align(src, T=T_src, density=density, run=run, **prm)
+    r = icp.align(src, T=T_src, density=density, **prm)
+    return r, r_ref, run
+
+
+def _check_align(icp, r, r_ref, run, extent, check_pairs=True):
+    assert r.iter == r_ref.iter
+    assert r.pairs == r_ref.pairs
+    assert_transform_close(r.matrix(), r_ref.matrix(), extent)
+    if np.isfinite(r_ref.mse):
+        assert abs(r.mse - r_ref.mse) <= 1e-5 * abs(r_ref.mse) + 1e-300
+        assert abs(r.d_box - r_ref.d_box) <= 1e-9 * abs(r_ref.d_box) + 1e-300
+    tr, tr_ref = icp.trace(), run.trace()
+    assert len(tr) == len(tr_ref)
+    for a, b in zip(tr, tr_ref):
+        assert a["found"] == b["found"] and a["kept"] == b["kept"]
+    pd, pd_ref = icp.pairs_distance(), run.pairs_distance()
+    assert len(pd) == len(pd_ref)
+    assert np.all(np.diff(pd) >= 0)
+    if check_pairs and len(pd):
+        assert np.allclose(pd, pd_ref, rtol=1e-9, atol=1e-12)
+
+
+def test_align_cfg1_scaled(icp, oracle, synth):
+    """env_icp-style config (BASELINE configs[0]) at 1/5 scale: full convergence, ~40 iterations."""
+    m, s, T, prm = synth.config("cfg1", scale=0.2)
+    r, r_ref, run = _align_both(icp, oracle, m, s, **prm)
+    _check_align(icp, r, r_ref, run, 20.0)
+    assert r.iter > 20
+    assert_transform_close(r.matrix(), T, 20.0, rot_tol=1e-4, trans_tol_rel=1e-4)  # it also finds the truth
+
+
+def test_align_cfg1_full_gui_defaults(icp, oracle, synth):
+    """50k vs 50k with the enview GUI defaults (viz/enview/ICPHandler.cpp:31-35): 5 iterations."""
+    m, s, T, _ = synth.config("cfg1")
+    prm = dict(max_iter=5, min_mse=1e-5, min_mse_diff=1e-8, overlap=0.8)
+    r, r_ref, run = _align_both(icp, oracle, m, s, **prm)
+    _check_align(icp, r, r_ref, run, 20.0)
+    # Last iteration's correspondences.  C differs from the oracle's in the last bits (the 17 sums are reduced
+    # in a different order), so distances agree to ~1e-12 and an index may only differ at a numerical near-tie.
+    i_gpu, d_gpu, kept = icp.debug_pairs()
+    i_ref, d_ref = run.last_pairs()
+    d_ref = np.where(i_ref == 0xFFFFFFFF, np.inf, d_ref)
+    assert np.array_equal(np.isinf(d_gpu), np.isinf(d_ref))
+    fin = np.isfinite(d_ref)
+    assert np.allclose(d_gpu[fin], d_ref[fin], rtol=0, atol=1e-9)
+    assert (i_gpu != i_ref).sum() <= 5
+    assert kept.sum() == r.pairs
+    # First iteration (C = identity exactly): bit-exact distances and indices
+    r, r_ref, run = _align_both(icp, oracle, m, s, **dict(prm, max_iter=1))
+    i_gpu, d_gpu, kept = icp.debug_pairs()
+    i_ref, d_ref = run.last_pairs()
+    assert np.array_equal(d_gpu, d_ref) and np.array_equal(i_gpu, i_ref)
+    order, tau = oracle.trim(d_ref, r_ref.pairs)
+    ref_kept = np.zeros(len(d_ref), bool)
+    ref_kept[order] = True
+    assert np.array_equal(kept, ref_kept)
+
+
+def test_align_cfg2_scaled_noise_and_source_frame(icp, oracle, synth):
+    """1M-vs-1M config at 1/20 scale, Gaussian noise, overlap 0.8; the source cloud sits in its own frame."""
+    m, s, T, prm = synth.config("cfg2", scale=0.05)
+    T_src = synth.rigid((1, 0, 0), 0.02, (0.1, -0.2, 0.05))
+    s_local = (s - T_src[:3, 3]) @ T_src[:3, :3]  # so that T_src * s_local == s
+    prm = dict(prm, max_iter=12)
+    r, r_ref, run = _align_both(icp, oracle, m, s_local, T_src=T_src, **prm)
+    _check_align(icp, r, r_ref, run, 100.0)
+
+
+def test_align_density_subsampling(icp, oracle, synth):
+    m, s, T, prm = synth.config("cfg1", scale=0.2)
+    prm = dict(prm, max_iter=8)
+    for density in (0.5, 0.3):
+        r, r_ref, run = _align_both(icp, oracle, m, s, density=density, **prm)
+        _check_align(icp, r, r_ref, run, 20.0)
+
+
+def test_align_partial_overlap_outliers(icp, oracle, synth):
+    """cfg3-style: half of the source replaced by a disjoint region; overlap 0.5."""
+    m = synth.scene(40000, 60.0, 4)
+    s, T = synth.perturbed_copy(m, 1.0, 0.3, 0.01, seed=5, replace_frac=0.5, extent=60.0)
+    prm = dict(max_iter=10, min_mse=1e-10, min_mse_diff=1e-9, overlap=0.5)
+    r, r_ref, run = _align_both(icp, oracle, m, s, **prm)
+    _check_align(icp, r, r_ref, run, 60.0)
+
+
+def test_align_edge_cases(icp, oracle, synth):
+    m = synth.scene(2000, 10.0, 1)
+    # max_iter = 0: loop never runs
+    r, r_ref, run = _align_both(icp, oracle, m, m[:100], max_iter=0, min_mse=1e-4, min_mse_diff=1e-5, overlap=1.0)
+    assert r.iter == 0 and np.isinf(r.mse) and np.array_equal(r.matrix(), np.eye(4)) and len(icp.pairs_distance()) == 0
+    # fewer than MIN_PAIRS pairs: early return (icp/icp.hpp:475-476), pairs_distance stays empty
+    r, r_ref, run = _align_both(icp, oracle, m, m[:2], max_iter=5, min_mse=1e-4, min_mse_diff=1e-5, overlap=1.0)
+    assert r.iter == r_ref.iter == 0 and r.pairs == r_ref.pairs == 2
+    assert r.d_box == r_ref.d_box and len(icp.pairs_distance()) == 0 and r.status == 7
+    # overlap so small that n_po = 0 -> NaN d_box
+    r, r_ref, run = _align_both(icp, oracle, m, m[:50], max_iter=5, min_mse=1e-4, min_mse_diff=1e-5, overlap=0.001)
+    assert r.pairs == r_ref.pairs == 0 and np.isnan(r.d_box) and np.isnan(r_ref.d_box)
+    # identical clouds: mse = 0 after one iteration, loop stops on mse > min_mse
+    r, r_ref, run = _align_both(icp, oracle, m, m, max_iter=5, min_mse=1e-4, min_mse_diff=1e-5, overlap=1.0)
+    assert r.iter == r_ref.iter == 1 and r.mse == 0.0
+    # empty source
+    r, r_ref, run = _align_both(icp, oracle, m, np.zeros((0, 3)), max_iter=5, min_mse=1e-4, min_mse_diff=1e-5,
+                                overlap=1.0)
+    assert r.iter == r_ref.iter == 0 and r.pairs == 0
+
+
+def test_align_reference_fixtures(icp, oracle):
+    """The reference's own test inputs (test/unit/icp.cpp:52-91, 147-159): sine-wave cloud, 441 points, copy moved by
+    Translation(0,0,5)*AngleAxis(0.1, X).  Lattice data => massive exact ties; both sides order ties by pair index."""
+    pts = []
+    for i in range(-10, 11):
+        for j in range(-10, 11):
+            x, y = i * .1, j * .1
+            pts.append((x, y, .2 * np.cos(10.0 * np.sqrt(x * x + y * y))))
+    pts = np.array(pts)
+    c, s_ = np.cos(0.1), np.sin(0.1)
+    T_b = np.array([[1, 0, 0, 0], [0, c, -s_, 0], [0, s_, c, 5.0], [0, 0, 0, 1.0]])
+    for overlap in (1.0, 0.7, 0.4):
+        r, r_ref, run = _align_both(icp, oracle, pts, pts, T_src=T_b, max_iter=10, min_mse=1e-4, min_mse_diff=1e-5,
+                                    overlap=overlap)
+        _check_align(icp, r, r_ref, run, 2.0)
+
+
+def test_full_size_properties_1m(icp, synth):
+    """BASELINE configs[1] at full size (1M vs 1M): too slow for the oracle, so size-independent properties:
+    (a) aligning an exact rigid copy recovers the inverse motion; (b) NN distances of model points to the model are 0;
+    (c) kept count == n_po, pairs_distance ascending and bounded by tau."""
+    m = synth.scene(1_000_000, 100.0, 2)
+    icp.clear_model()
+    icp.add_to_model(m)
+    i, d = icp.find_pairs(m[:200000])
+    assert np.all(d == 0.0) and np.array_equal(i, np.arange(200000, dtype=np.uint32))
+    s, T = synth.perturbed_copy(m, 0.5, 0.1, 0.0, seed=3)
+    r = icp.align(s, max_iter=80, min_mse=1e-12, min_mse_diff=1e-14, overlap=0.8)
+    assert r.pairs == 800000
+    assert_transform_close(r.matrix(), T, 100.0, rot_tol=1e-5, trans_tol_rel=1e-5)
+    pd = icp.pairs_distance()
+    assert len(pd) == 800000 and np.all(np.diff(pd) >= 0) and pd[-1] * 2.0 == r.d_box
