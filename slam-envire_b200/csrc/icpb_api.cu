@@ -156,7 +156,7 @@ struct icpb_ctx {
     std::string err;
     // options
     double opt_cell_size = 0.0, opt_target = 4.0, opt_max_cells = 64.0 * 1024 * 1024, opt_run_ahead = 2.0,
-           opt_warm = 1.0, opt_profile = 1.0;
+           opt_warm = 1.0, opt_profile = 1.0, opt_sort = 1.0;
     // model
     DevBuf<double> model_raw;
     size_t model_n = 0;
@@ -174,7 +174,7 @@ struct icpb_ctx {
     size_t src_n = 0, adapter_size = 0;
     double Cl2g[12];
     bool have_source = false;
-    DevBuf<uint32_t> nn_pos;
+    DevBuf<uint32_t> nn_pos, src_perm;
     DevBuf<double> nn_d;
     // iteration
     IcpState *d_state = nullptr;
@@ -312,6 +312,7 @@ void icpb_destroy(icpb_ctx *ctx)
     ctx->sy.release();
     ctx->sz.release();
     ctx->nn_pos.release();
+    ctx->src_perm.release();
     ctx->nn_d.release();
     ctx->partials.release();
     ctx->trace.release();
@@ -343,6 +344,7 @@ static double *opt_slot(icpb_ctx *ctx, const char *key)
     if (!strcmp(key, "run_ahead") || !strcmp(key, "poll_every")) return &ctx->opt_run_ahead;
     if (!strcmp(key, "warm_start")) return &ctx->opt_warm;
     if (!strcmp(key, "profile")) return &ctx->opt_profile;
+    if (!strcmp(key, "sort_source")) return &ctx->opt_sort;
     return nullptr;
 }
 int icpb_set_option(icpb_ctx *ctx, const char *key, double value)
@@ -607,11 +609,50 @@ static int upload_points(icpb_ctx *ctx, const double *src, size_t m)
     CK(ctx->sz.ensure(std::max<size_t>(m, 1)));
     CK(ctx->nn_pos.ensure(std::max<size_t>(m, 1)));
     CK(ctx->nn_d.ensure(std::max<size_t>(m, 1)));
+    CK(ctx->src_perm.ensure(std::max<size_t>(m, 1)));
     if (m) {
         CK(cudaMemcpyAsync(ctx->stage.p, src, 3 * m * sizeof(double), cudaMemcpyHostToDevice, s));
-        aos_to_soa_kernel<<<grid_for(m, 256), 256, 0, s>>>(ctx->stage.p, m, ctx->sx.p, ctx->sy.p, ctx->sz.p);
-        CKL();
-        ++ctx->launches;
+        if (ctx->opt_sort != 0.0 && m > 1024) {
+            // Morton order of the source in its own frame: rigid motions keep neighbours together, so one
+            // sort per upload serves every iteration.  src_perm[] maps back to the adapter's visiting order.
+            const unsigned nbb = std::min<unsigned>(1024u, grid_for(m, 256));
+            CK(ctx->bbox_part.ensure((size_t)nbb * 6));
+            bbox_kernel<<<nbb, 256, 0, s>>>(ctx->stage.p, m, ctx->bbox_part.p);
+            CKL();
+            std::vector<double> hb((size_t)nbb * 6);
+            CK(cudaMemcpyAsync(hb.data(), ctx->bbox_part.p, hb.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+            for (unsigned b = 0; b < nbb; ++b)
+                for (int a = 0; a < 3; ++a) {
+                    mn[a] = fmin(mn[a], hb[(size_t)b * 6 + a]);
+                    mx[a] = fmax(mx[a], hb[(size_t)b * 6 + 3 + a]);
+                }
+            double ext = fmax(fmax(mx[0] - mn[0], mx[1] - mn[1]), mx[2] - mn[2]);
+            if (!(ext > 0.0) || !isfinite(ext)) ext = 1.0;
+            CK(ctx->keys0.ensure(m));
+            CK(ctx->keys1.ensure(m));
+            CK(ctx->vals0.ensure(m));
+            CK(ctx->vals1.ensure(m));
+            CK(ctx->sort_scratch.ensure(rs_scratch_elems(m)));
+            morton_keys_kernel<<<grid_for(m, 256), 256, 0, s>>>(ctx->stage.p, (uint32_t)m, mn[0], mn[1], mn[2],
+                                                               1023.999 / ext, ctx->keys0.p, ctx->vals0.p);
+            CKL();
+            const int w = radix_sort<uint32_t, true>(ctx->keys0.p, ctx->vals0.p, ctx->keys1.p, ctx->vals1.p, m, 30,
+                                                     ctx->sort_scratch.p, s, &ctx->launches);
+            CKL();
+            CK(cudaMemcpyAsync(ctx->src_perm.p, w ? ctx->vals1.p : ctx->vals0.p, m * sizeof(uint32_t),
+                               cudaMemcpyDeviceToDevice, s));
+            gather_soa_kernel<<<grid_for(m, 256), 256, 0, s>>>(ctx->stage.p, ctx->src_perm.p, (uint32_t)m, ctx->sx.p,
+                                                              ctx->sy.p, ctx->sz.p);
+            CKL();
+            ctx->launches += 3;
+        } else {
+            aos_to_soa_kernel<<<grid_for(m, 256), 256, 0, s>>>(ctx->stage.p, m, ctx->sx.p, ctx->sy.p, ctx->sz.p);
+            iota_kernel<<<grid_for(m, 256), 256, 0, s>>>(ctx->src_perm.p, (uint32_t)m);
+            CKL();
+            ctx->launches += 2;
+        }
     }
     CK(cudaEventRecord(ctx->ev_up1, s));
     CK(cudaStreamSynchronize(s));
@@ -692,7 +733,8 @@ static int launch_trim(icpb_ctx *ctx, uint32_t n)
     if (!fused) // pairs found on all ranks
         NK(g_nccl.AllReduce(&ctx->d_state->found, &ctx->d_state->found, 1, NCCL_UINT64, NCCL_SUM, ctx->comm, s));
     for (int p = 0; p < SEL_D_PASSES; ++p) {
-        select_kernel<<<blocks, SEL_THREADS, 0, s>>>(ctx->nn_d.p, n, ctx->d_state, ctx->d_ghist, p, 0, fused, p);
+        select_kernel<<<blocks, SEL_THREADS, 0, s>>>(ctx->nn_d.p, ctx->src_perm.p, n, ctx->d_state, ctx->d_ghist, p, 0,
+                                                     fused, p);
         CKL();
         ++ctx->launches;
         if (!fused) {
@@ -712,7 +754,8 @@ static int launch_trim(icpb_ctx *ctx, uint32_t n)
         ctx->launches += 3;
     }
     for (int p = 0; p < SEL_T_PASSES; ++p) {
-        select_kernel<<<blocks, SEL_THREADS, 0, s>>>(ctx->nn_d.p, n, ctx->d_state, ctx->d_ghist, p, 1, 1, 6 + p);
+        select_kernel<<<blocks, SEL_THREADS, 0, s>>>(ctx->nn_d.p, ctx->src_perm.p, n, ctx->d_state, ctx->d_ghist, p, 1, 1,
+                                                     6 + p);
         CKL();
         ++ctx->launches;
     }
@@ -788,8 +831,8 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
         }
         if (timed) CK(cudaEventRecord(ev[2], s));
         moments_kernel<<<mom_blocks, MOM_THREADS, 0, s>>>(ctx->gv, ctx->sx.p, ctx->sy.p, ctx->sz.p, n, ctx->d_state,
-                                                          ctx->nn_pos.p, ctx->nn_d.p, ctx->partials.p, ctx->trace.p,
-                                                          ctx->trace_cap, fused);
+                                                          ctx->nn_pos.p, ctx->nn_d.p, ctx->src_perm.p, ctx->partials.p,
+                                                          ctx->trace.p, ctx->trace_cap, fused);
         CKL();
         ++ctx->launches;
         if (!fused) {
@@ -891,7 +934,7 @@ int icpb_pairs_distance(icpb_ctx *ctx, double *out, size_t capacity, size_t *n_o
     CK(ctx->sort_scratch.ensure(rs_scratch_elems(n)));
     unsigned int *cnt = (unsigned int *)(ctx->d_counter + 1);
     CK(cudaMemsetAsync(cnt, 0, sizeof(unsigned int), s));
-    compact_kept_kernel<<<grid_for(n, 256), 256, 0, s>>>(ctx->nn_d.p, n, ctx->d_state, ctx->kd0.p, cnt);
+    compact_kept_kernel<<<grid_for(n, 256), 256, 0, s>>>(ctx->nn_d.p, ctx->src_perm.p, n, ctx->d_state, ctx->kd0.p, cnt);
     CKL();
     unsigned int h_cnt = 0;
     CK(cudaMemcpyAsync(&h_cnt, cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, s));
@@ -923,11 +966,13 @@ int icpb_debug_pairs(icpb_ctx *ctx, uint32_t *model_idx, double *dist, uint8_t *
     cudaStream_t s = ctx->stream;
     CK(ctx->dbg_idx.ensure(n));
     CK(ctx->dbg_kept.ensure(n));
-    debug_pairs_kernel<<<grid_for(n, 256), 256, 0, s>>>(ctx->gv, ctx->nn_pos.p, ctx->nn_d.p, n, ctx->d_state,
-                                                        ctx->dbg_idx.p, ctx->dbg_kept.p);
+    CK(ctx->kd0.ensure(n));
+    debug_pairs_kernel<<<grid_for(n, 256), 256, 0, s>>>(ctx->gv, ctx->nn_pos.p, ctx->nn_d.p, ctx->src_perm.p, n,
+                                                        ctx->d_state, ctx->dbg_idx.p, (double *)ctx->kd0.p,
+                                                        ctx->dbg_kept.p);
     CKL();
     if (model_idx) CK(cudaMemcpyAsync(model_idx, ctx->dbg_idx.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    if (dist) CK(cudaMemcpyAsync(dist, ctx->nn_d.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (dist) CK(cudaMemcpyAsync(dist, ctx->kd0.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (kept) CK(cudaMemcpyAsync(kept, ctx->dbg_kept.p, n * sizeof(uint8_t), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return ICPB_OK;
@@ -999,7 +1044,9 @@ int icpb_trim(icpb_ctx *ctx, const double *dist, size_t n, size_t n_po, double *
     CK(ctx->nn_d.ensure(std::max<size_t>(n, 1)));
     size_t found = 0;
     for (size_t i = 0; i < n; ++i) found += isfinite(dist[i]) ? 1 : 0;
+    CK(ctx->src_perm.ensure(std::max<size_t>(n, 1)));
     if (n) CK(cudaMemcpyAsync(ctx->nn_d.p, dist, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (n) iota_kernel<<<grid_for(n, 256), 256, 0, s>>>(ctx->src_perm.p, (uint32_t)n);
     trim_setup_kernel<<<1, 1, 0, s>>>(ctx->d_state, n_po, found);
     CKL();
     const int saved_ranks = ctx->n_ranks;

@@ -302,12 +302,13 @@ __device__ void select_pick(IcpState *st, uint32_t *ghist, int pass, bool tie_mo
     }
 }
 
-// One histogram pass.  tie_mode == 0: key = bits(nn_d[i]).  tie_mode == 1: key = i
+// One histogram pass.  tie_mode == 0: key = bits(nn_d[i]).  tie_mode == 1: key = perm[i] (the pair index)
 // restricted to entries with nn_d[i] == tau (decides WHICH equidistant pairs survive:
 // those at the lowest positions, i.e. a stable sort by (distance, pair index)).
 __global__ void __launch_bounds__(SEL_THREADS)
-    select_kernel(const double *__restrict__ nn_d, uint32_t n, IcpState *__restrict__ st, uint32_t *__restrict__ ghist,
-                  int pass, int tie_mode, int fused_pick, int ticket_slot)
+    select_kernel(const double *__restrict__ nn_d, const uint32_t *__restrict__ perm, uint32_t n,
+                  IcpState *__restrict__ st, uint32_t *__restrict__ ghist, int pass, int tie_mode, int fused_pick,
+                  int ticket_slot)
 {
     if (st->done) return;
     if (tie_mode && !st->need_tie) return;
@@ -335,7 +336,8 @@ __global__ void __launch_bounds__(SEL_THREADS)
         for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
             const unsigned long long key = (unsigned long long)__double_as_longlong(nn_d[i]);
             if (key != tau_bits) continue;
-            if (pass == 0 || hs >= 32 || (i >> hs) == (prefix >> hs)) atomicAdd(&hist[(i >> shift) & bin_mask], 1u);
+            const uint32_t pi = perm[i]; // pair index in the adapter's visiting order
+            if (pass == 0 || hs >= 32 || (pi >> hs) == (prefix >> hs)) atomicAdd(&hist[(pi >> shift) & bin_mask], 1u);
         }
     }
     __syncthreads();
@@ -381,8 +383,9 @@ __device__ __forceinline__ double shfl_xor_double(double v, int o)
 __global__ void __launch_bounds__(MOM_THREADS)
     moments_kernel(const GridView g, const double *__restrict__ sx, const double *__restrict__ sy,
                    const double *__restrict__ sz, uint32_t n, IcpState *__restrict__ st,
-                   const uint32_t *__restrict__ nn_pos, const double *__restrict__ nn_d, double *__restrict__ partials,
-                   double *__restrict__ trace, int trace_cap, int fused_pose)
+                   const uint32_t *__restrict__ nn_pos, const double *__restrict__ nn_d,
+                   const uint32_t *__restrict__ perm, double *__restrict__ partials, double *__restrict__ trace,
+                   int trace_cap, int fused_pose)
 {
     if (st->done) return;
     __shared__ double sm[MOM_THREADS / 32][ICPB_NSUMS];
@@ -399,7 +402,8 @@ __global__ void __launch_bounds__(MOM_THREADS)
     if (any)
         for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
             const double d = nn_d[i];
-            if (!pair_kept(d, i, tau, p_cut)) continue;
+            if (!(d <= tau)) continue;
+            if (!pair_kept(d, perm[i], tau, p_cut)) continue;
             double px, py, pz;
             icpb_aff_apply(M, sx[i], sy[i], sz[i], px, py, pz); // p: the transformed source vertex
             const MPoint m = g.pts[nn_pos[i]];                  // x: its model point
@@ -483,7 +487,8 @@ __global__ void init_state_kernel(IcpState *st, Aff12 Cl2g, unsigned long long m
 // ---------------------------------------------------------------------------
 // K7 + debug: kept distances / correspondences of the last executed iteration
 // ---------------------------------------------------------------------------
-__global__ void compact_kept_kernel(const double *__restrict__ nn_d, uint32_t n, const IcpState *__restrict__ st,
+__global__ void compact_kept_kernel(const double *__restrict__ nn_d, const uint32_t *__restrict__ perm, uint32_t n,
+                                    const IcpState *__restrict__ st,
                                     unsigned long long *__restrict__ out_keys, unsigned int *__restrict__ counter)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -491,7 +496,7 @@ __global__ void compact_kept_kernel(const double *__restrict__ nn_d, uint32_t n,
     double d = 0.0;
     if (i < n && st->sel_k > 0) {
         d = nn_d[i];
-        keep = pair_kept(d, i, st->tau, st->p_cut);
+        keep = pair_kept(d, perm[i], st->tau, st->p_cut);
     }
     const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
     if (!m) return;
@@ -503,14 +508,56 @@ __global__ void compact_kept_kernel(const double *__restrict__ nn_d, uint32_t n,
 }
 
 __global__ void debug_pairs_kernel(const GridView g, const uint32_t *__restrict__ nn_pos,
-                                   const double *__restrict__ nn_d, uint32_t n, const IcpState *__restrict__ st,
-                                   uint32_t *__restrict__ idx_out, uint8_t *__restrict__ kept_out)
+                                   const double *__restrict__ nn_d, const uint32_t *__restrict__ perm, uint32_t n,
+                                   const IcpState *__restrict__ st, uint32_t *__restrict__ idx_out,
+                                   double *__restrict__ d_out, uint8_t *__restrict__ kept_out)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t pos = nn_pos[i];
-    idx_out[i] = pos == ICPB_NONE ? ICPB_NONE : (uint32_t)g.pts[pos].idx;
-    kept_out[i] = (st->sel_k > 0 && pair_kept(nn_d[i], i, st->tau, st->p_cut)) ? 1 : 0;
+    const uint32_t o = perm[i]; // back to the adapter's visiting order
+    idx_out[o] = pos == ICPB_NONE ? ICPB_NONE : (uint32_t)g.pts[pos].idx;
+    d_out[o] = nn_d[i];
+    kept_out[o] = (st->sel_k > 0 && pair_kept(nn_d[i], o, st->tau, st->p_cut)) ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------
+// source upload: spatial (Morton) order so that a warp's 32 queries are neighbours
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t spread10(uint32_t v)
+{
+    v &= 1023u;
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__global__ void morton_keys_kernel(const double *__restrict__ aos, uint32_t n, double ox, double oy, double oz,
+                                   double inv, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double fx = fmin(fmax((aos[3 * (size_t)i] - ox) * inv, 0.0), 1023.0);
+    const double fy = fmin(fmax((aos[3 * (size_t)i + 1] - oy) * inv, 0.0), 1023.0);
+    const double fz = fmin(fmax((aos[3 * (size_t)i + 2] - oz) * inv, 0.0), 1023.0);
+    keys[i] = spread10((uint32_t)fx) | (spread10((uint32_t)fy) << 1) | (spread10((uint32_t)fz) << 2);
+    vals[i] = i;
+}
+__global__ void gather_soa_kernel(const double *__restrict__ aos, const uint32_t *__restrict__ perm, uint32_t n,
+                                  double *__restrict__ x, double *__restrict__ y, double *__restrict__ z)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const size_t s = perm[j];
+    x[j] = aos[3 * s];
+    y[j] = aos[3 * s + 1];
+    z[j] = aos[3 * s + 2];
+}
+__global__ void iota_kernel(uint32_t *__restrict__ v, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = i;
 }
 
 } // namespace icpb
