@@ -1,0 +1,130 @@
+"""CPU tier: the product's own host/device-shared code (no GPU needed).
+
+  * tests/harness runs grid_view.h (icpb_nn_search) and pose.h (state machine, closed-form pose) on the CPU
+  * the C-ABI library loads and exports every symbol include/icp_b200.h declares
+"""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, assert_transform_close
+
+
+@pytest.mark.parametrize("nm,nq,h,d_box,seed", [
+    (5000, 2000, 0.7, np.inf, 1), (5000, 2000, 0.25, np.inf, 2), (5000, 2000, 4.0, np.inf, 3),
+    (5000, 2000, 0.5, 0.4, 4), (5000, 2000, 0.5, 1.7, 5), (1, 50, 1.0, np.inf, 6), (9, 50, 1.0, 0.5, 7),
+])
+def test_grid_search_exact(harness, oracle, nm, nq, h, d_box, seed):
+    rng = np.random.default_rng(seed)
+    m = rng.uniform(-10, 10, (nm, 3))
+    q = rng.uniform(-14, 14, (nq, 3))
+    M = oracle.Model()
+    M.add(m)
+    i0, d0 = M.find_pairs(q, d_box=d_box, brute=True)
+    d0 = np.where(i0 == 0xFFFFFFFF, d_box, d0)
+    i1, d1, lv = harness.search(m, h, q, d_box)
+    assert np.array_equal(i0, i1) and np.array_equal(d0, d1)
+    # a warm-start candidate (previous iteration's pair) never changes the answer
+    w = rng.integers(0, nm, nq).astype(np.uint32)
+    i2, d2, _ = harness.search(m, h, q, d_box, warm=w)
+    assert np.array_equal(i1, i2) and np.array_equal(d1, d2)
+
+
+def test_grid_search_ties_lowest_index(harness, oracle):
+    g = np.arange(0, 8, dtype=np.float64)
+    m = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    m = np.concatenate([m, m[:64]])  # exact duplicates
+    q = np.concatenate([m[:300] + 0.5, m[:50]])
+    M = oracle.Model()
+    M.add(m)
+    i0, d0 = M.find_pairs(q, brute=True)
+    for h in (0.5, 1.0, 3.0):
+        i1, d1, _ = harness.search(m, h, q)
+        assert np.array_equal(i0, i1) and np.array_equal(d0, d1)
+
+
+def test_grid_search_surface_scene(harness, oracle, synth):
+    m, s, T, prm = synth.config("cfg1", 0.2)
+    M = oracle.Model()
+    M.add(m)
+    for d_box in (np.inf, 0.8):
+        i0, d0 = M.find_pairs(s, d_box=d_box)
+        d0 = np.where(i0 == 0xFFFFFFFF, d_box, d0)
+        i1, d1, lv = harness.search(m, 0.45, s, d_box)
+        assert np.array_equal(i0, i1) and np.array_equal(d0, d1)
+
+
+def test_pose_step_matches_oracle(harness, oracle):
+    rng = np.random.default_rng(3)
+    x = rng.normal(size=(400, 3)) * [5, 3, 1] + [10, -4, 2]
+    p = x @ np.array([[0.98, -0.17, 0.05], [0.17, 0.98, 0.02], [-0.05, -0.01, 1.0]]) + [0.3, -0.2, 0.1]
+    d = np.linalg.norm(p - x, axis=1)
+    T_ref, mse_ref = oracle.get_transform(p, x, d, np.arange(400))
+    sums = np.concatenate([p.sum(0), x.sum(0), (p[:, :, None] * x[:, None, :]).sum(0).reshape(9), [(d * d).sum(), 400]])
+    T, mse = harness.transform_from_sums(sums)
+    assert np.allclose(T, T_ref, rtol=0, atol=1e-12) and abs(mse - mse_ref) <= 1e-14 * mse_ref
+
+
+@pytest.mark.parametrize("warm", [0, 1])
+def test_emulated_device_loop_matches_oracle(harness, oracle, synth, warm):
+    m, s, T, prm = synth.config("cfg1", 0.1)
+    M = oracle.Model()
+    M.add(m)
+    run = oracle.Run()
+    r = M.align(s, run=run, **prm)
+    e = harness.align(m, 0.5, s, warm=warm, **prm)
+    assert e["iter"] == r.iter and e["pairs"] == r.pairs and not e["early"]
+    assert_transform_close(e["C"], r.matrix(), 20.0)
+    assert abs(e["mse"] - r.mse) <= 1e-5 * r.mse
+    tr = run.trace()
+    assert len(tr) == len(e["trace"])
+    for a, b in zip(tr, e["trace"]):
+        assert a["found"] == b[1] and a["kept"] == b[2] and abs(a["tau"] - b[3]) <= 1e-9
+
+
+def test_emulated_device_loop_edge_cases(harness, oracle, synth):
+    m = synth.scene(500, 10.0, 1)
+    M = oracle.Model()
+    M.add(m)
+    for src, prm in [(m[:2], dict(max_iter=5)), (m[:50], dict(max_iter=5, overlap=0.001)), (m[:50], dict(max_iter=0)),
+                     (m, dict(max_iter=5))]:
+        r = M.align(src, **prm)
+        e = harness.align(m, 0.6, src, **prm)
+        assert e["iter"] == r.iter and e["pairs"] == r.pairs
+        assert (np.isnan(e["d_box"]) and np.isnan(r.d_box)) or e["d_box"] == r.d_box
+        assert e["early"] == (r.pairs < 3 and prm["max_iter"] > 0)
+
+
+def test_c_abi_exports_every_declared_symbol(pkg):
+    """include/icp_b200.h is the boundary: every prototype in it must be exported by libicp_b200.so."""
+    hdr = open(os.path.join(ROOT, "include", "icp_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(icpb_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(pkg.SYMBOLS)
+    L = pkg.load_library()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.icpb_version().startswith(b"icp_b200")
+
+
+def test_no_cpu_fallback(pkg):
+    """Without a CUDA device the product must fail loudly, not fall back to a CPU path."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(pkg.IcpError) as ei:
+        pkg.Icp(0)
+    assert ei.value.status == pkg.ERR_CUDA
+
+
+def test_product_does_not_touch_oracle():
+    """oracle/ is test infrastructure: nothing under slam-envire_b200/ or include/ may reference it."""
+    for base in ("slam-envire_b200", "include"):
+        for dp, dn, fn in os.walk(os.path.join(ROOT, base)):
+            for f in fn:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                    txt = open(os.path.join(dp, f), errors="ignore").read()
+                    assert "icp_oracle" not in txt and "oracle." not in txt.replace("the oracle.", ""), f
