@@ -1,0 +1,3 @@
+#pragma once
+#include "core/FrameNode.hpp"
+#include "maps/Pointcloud.hpp"

@@ -1,0 +1,90 @@
+// envire-mini: the part of envire's core runtime the ICP boundary touches (4 calls).
+//   Environment::relativeTransform  (reference src/core/Environment.cpp:744-782)
+//   FrameNode::getTransform / setTransform -> itemModified (src/core/FrameNode.cpp:90-102)
+//   Environment::{getRootNode, addChild, attachItem}, EnvironmentItem::getEnvironment
+// Scene-graph bookkeeping, events, serialization and the operator graph are out of scope.
+#pragma once
+#include <Eigen/Geometry>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace envire {
+typedef Eigen::Affine3d Transform;
+class Environment;
+class FrameNode;
+
+class EnvironmentItem {
+public:
+    virtual ~EnvironmentItem() {}
+    Environment *getEnvironment() const { return env_; }
+    bool isAttached() const { return env_ != 0; }
+protected:
+    friend class Environment;
+    Environment *env_ = 0;
+};
+
+class FrameNode : public EnvironmentItem {
+public:
+    EIGEN_MAKE_ALIGNED_OPERATOR_NEW
+    FrameNode() : frame_(Transform::Identity()), parent_(0) {}
+    explicit FrameNode(const Transform &t) : frame_(t), parent_(0) {}
+    bool isRoot() const { return parent_ == 0; }
+    const FrameNode *getParent() const { return parent_; }
+    FrameNode *getParent() { return parent_; }
+    Transform const &getTransform() const { return frame_; }
+    inline void setTransform(Transform const &transform); // fires itemModified when attached
+    inline Transform relativeTransform(const FrameNode *to) const;
+private:
+    friend class Environment;
+    Transform frame_;
+    FrameNode *parent_;
+};
+
+class CartesianMap : public EnvironmentItem {
+public:
+    FrameNode *getFrameNode() const { return fn_; }
+    void setFrameNode(FrameNode *fn) { fn_ = fn; }
+private:
+    FrameNode *fn_ = 0;
+};
+
+class Environment {
+public:
+    Environment() : root_(new FrameNode()), modified_(0) { attachItem(root_); }
+    ~Environment() { for (size_t i = 0; i < owned_.size(); ++i) delete owned_[i]; }
+    FrameNode *getRootNode() { return root_; }
+    void attachItem(EnvironmentItem *item) { item->env_ = this; owned_.push_back(item); }
+    void addChild(FrameNode *parent, FrameNode *child)
+    {
+        if (!child->isAttached()) attachItem(child);
+        child->parent_ = parent;
+    }
+    void setFrameNode(CartesianMap *map, FrameNode *fn) { map->setFrameNode(fn); }
+    // product of the transforms up to the common root: tg^-1 * fg
+    Transform relativeTransform(const FrameNode *from, const FrameNode *to)
+    {
+        if (from == to) return Transform::Identity();
+        Transform fg = Transform::Identity(), tg = Transform::Identity();
+        const FrameNode *f = from, *t = to;
+        while (!f->isRoot()) { fg = f->getTransform() * fg; f = f->getParent(); }
+        while (!t->isRoot()) { tg = t->getTransform() * tg; t = t->getParent(); }
+        if (f != t) throw std::runtime_error("relativeTransform: FrameNodes don't have a common root.");
+        return tg.inverse() * fg;
+    }
+    void itemModified(EnvironmentItem *) { ++modified_; } // event fan-out is out of scope; counted for tests
+    size_t modifiedCount() const { return modified_; }
+private:
+    FrameNode *root_;
+    std::vector<EnvironmentItem *> owned_;
+    size_t modified_;
+};
+
+inline void FrameNode::setTransform(Transform const &transform)
+{
+    frame_ = transform;
+    if (isAttached()) env_->itemModified(this);
+}
+inline Transform FrameNode::relativeTransform(const FrameNode *to) const { return env_->relativeTransform(this, to); }
+} // namespace envire

@@ -1,0 +1,236 @@
+// icp_gpu.hpp -- host mirror of envire's icp/ interface over the B200 C ABI.
+//
+// envire::icp::TrimmedGPU has the public surface of envire::icp::TrimmedKD
+// (reference icp/icp.hpp:385-439, typedef at :522): addToModel, clearModel, align (fixed overlap), align (golden
+// section over the overlap), getNumIterations, getMeanSquareError, getMeanSquareErrorDiff, getOverlap, getPairs,
+// getPairsDistance -- same argument order, same getter semantics, adapters passed by value, exceptions where the
+// reference throws.  The compute (model index, correspondences, trim, pose, loop) runs in libicp_b200.so
+// (include/icp_b200.h); what stays on the host is exactly what the reference also does once per align on the host:
+// the adapter's frame lookup (Environment::relativeTransform), applyTransform -> FrameNode::setTransform, and the
+// golden-section driver.  There is no CPU fallback: constructing a TrimmedGPU without a CUDA device throws.
+//
+// Build against real Eigen3 + envire when they are installed; otherwise add slam-envire_b200/compat to the include
+// path (mini-Eigen + envire-mini with the same names).
+#ifndef ICP_B200_ICP_GPU_HPP
+#define ICP_B200_ICP_GPU_HPP
+
+#include <Eigen/Core>
+#include <Eigen/Geometry>
+#include <envire/core/EnvironmentItem.hpp>
+#include <envire/core/FrameNode.hpp>
+#include <envire/maps/Pointcloud.hpp>
+
+#include <cmath>
+#include <functional>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/icp_b200.h"
+
+namespace envire {
+namespace icp {
+
+/** Adapter concept of Trimmed<_Adapter,_FindPairs> (icp/icp.hpp:99-171) for envire::Pointcloud.  The iteration
+ * interface (reset/hasNext/next/size) is kept for code that walks an adapter itself; TrimmedGPU hands the whole
+ * vertex array, the density and C_local2global to the device instead of pulling points one by one. */
+class PointcloudAdapter {
+public:
+    PointcloudAdapter(envire::Pointcloud *cloud, double density) : cloud_(cloud), cursor_(0.0), density_(density)
+    {
+        envire::FrameNode *fn = cloud_->getFrameNode();
+        envire::Environment *env = cloud_->getEnvironment();
+        if (!fn || !env) throw std::runtime_error("PointcloudAdapter: pointcloud needs a FrameNode and an Environment");
+        local2global_ = env->relativeTransform(fn, env->getRootNode());
+        local2globalnew_ = local2global_;
+    }
+    void setOffsetTransform(const Eigen::Affine3d &C_global2globalnew) { local2globalnew_ = C_global2globalnew * local2global_; }
+    void reset() { cursor_ = 0.0; }
+    bool hasNext() const { return static_cast<size_t>(cursor_) < cloud_->vertices.size(); }
+    Eigen::Vector3d next()
+    {
+        const size_t i = static_cast<size_t>(cursor_);
+        cursor_ += 1.0 / density_;
+        return local2globalnew_ * cloud_->vertices[i];
+    }
+    size_t size() const { return cloud_->vertices.size() * density_; }
+
+    /** FrameNode update after an align (icp/icp.hpp:148-162): compose in the cloud's own frame, then take the
+     * rotation() of the result so numeric run-off cannot accumulate. */
+    void applyTransform(const Eigen::Affine3d &C_global2globalnew)
+    {
+        envire::FrameNode *fn = cloud_->getFrameNode();
+        Eigen::Affine3d updated = fn->getTransform() * local2global_.inverse(Eigen::Isometry) * C_global2globalnew * local2global_;
+        const Eigen::Matrix3d rot = updated.rotation();
+        updated.linear() = rot;
+        fn->setTransform(envire::Transform(updated));
+    }
+
+    // raw access for the device path
+    const double *vertexData() const { return cloud_->vertices.empty() ? 0 : cloud_->vertices[0].data(); }
+    size_t vertexCount() const { return cloud_->vertices.size(); }
+    double density() const { return density_; }
+    const Eigen::Affine3d &local2global() const { return local2global_; }
+
+protected:
+    envire::Pointcloud *cloud_;
+    Eigen::Affine3d local2global_, local2globalnew_;
+    double cursor_;
+    double density_;
+};
+
+/** Golden-section minimiser used by the overlap search (role of GoldenBracket, icp/icp.hpp:266-327): same bracket
+ * rule, same constant R = 0.6180339, same termination test, so the sequence of probed overlaps is identical. */
+template <class T> struct GoldenSection {
+    static T minimise(const std::function<T(double)> &f, double a, double b, double c, double eps)
+    {
+        const double R = 0.6180339, S = 1.0 - R;
+        double lo = a, hi = c, u, v;
+        if (std::fabs(c - b) > std::fabs(b - a)) { u = b; v = b + S * (c - b); }
+        else { v = b; u = b - S * (b - a); }
+        T fu = f(u), fv = f(v);
+        while (std::fabs(hi - lo) > eps * (std::fabs(u) + std::fabs(v))) {
+            if (fv < fu) {
+                const double probe = R * u + S * hi; // the reference forms the new point from the OLD inner point
+                lo = u; u = v; v = probe;
+                fu = fv; fv = f(v);
+            } else {
+                const double probe = R * v + S * lo;
+                hi = v; v = u; u = probe;
+                fv = fu; fu = f(u);
+            }
+        }
+        return (fu < fv) ? fu : fv;
+    }
+};
+
+class TrimmedGPU {
+    struct Result {
+        Eigen::Affine3d C_global2globalnew;
+        size_t iter, pairs;
+        double mse, mse_diff, d_box, overlap;
+        std::vector<double> pairs_distance;
+        Result() : C_global2globalnew(Eigen::Affine3d::Identity()), iter(0), pairs(0), mse(0), mse_diff(0), d_box(0), overlap(0) {}
+        double optFunc() const { return mse / std::pow(overlap, 3.0); } // gamma = 2 (icp/icp.hpp:349-362)
+        bool operator<(const Result &o) const { return optFunc() < o.optFunc(); }
+    };
+
+public:
+    explicit TrimmedGPU(int device = 0) : ctx_(0)
+    {
+        const int rc = icpb_create(&ctx_, device);
+        if (rc != ICPB_OK) {
+            std::string msg = std::string("TrimmedGPU: ") + icpb_strerror(rc);
+            if (ctx_) { msg += std::string(" / ") + icpb_last_error(ctx_); icpb_destroy(ctx_); ctx_ = 0; }
+            throw std::runtime_error(msg);
+        }
+    }
+    ~TrimmedGPU() { if (ctx_) icpb_destroy(ctx_); }
+    TrimmedGPU(const TrimmedGPU &) = delete;
+    TrimmedGPU &operator=(const TrimmedGPU &) = delete;
+
+    /** golden-section search for the overlap in [alpha, beta] (icp/icp.hpp:385-401) */
+    void align(PointcloudAdapter measurement, size_t max_iter, double min_mse, double min_mse_diff, double alpha, double beta, double eps)
+    {
+        upload(measurement); // the vertices do not change between probes: upload once, every probe restarts from identity
+        std::function<Result(double)> eval = [&](double overlap) { return alignResident(max_iter, min_mse, min_mse_diff, overlap, true); };
+        minResult_ = GoldenSection<Result>::minimise(eval, alpha, (alpha + beta) / 2.0, beta, eps);
+        measurement.applyTransform(minResult_.C_global2globalnew);
+    }
+    /** fixed overlap (icp/icp.hpp:413-418) */
+    void align(PointcloudAdapter measurement, size_t max_iter, double min_mse, double min_mse_diff, double overlap)
+    {
+        upload(measurement);
+        minResult_ = alignResident(max_iter, min_mse, min_mse_diff, overlap, false);
+        measurement.applyTransform(minResult_.C_global2globalnew);
+    }
+    void addToModel(PointcloudAdapter model)
+    {
+        double T[16];
+        toColMajor(model.local2global(), T);
+        check(icpb_model_add(ctx_, model.vertexData(), model.vertexCount(), T, model.density()));
+    }
+    void clearModel() { check(icpb_model_clear(ctx_)); }
+
+    size_t getNumIterations() { return minResult_.iter; }
+    double getMeanSquareError() { return minResult_.mse; }
+    double getMeanSquareErrorDiff() { return minResult_.mse_diff; }
+    double getOverlap() { return minResult_.overlap; }
+    size_t getPairs() { return minResult_.pairs; }
+    std::vector<double> getPairsDistance()
+    {
+        fetchPairsDistance(minResult_);
+        return minResult_.pairs_distance;
+    }
+
+    /** GPU-only knobs (cell size, warm start, ...): see icpb_set_option */
+    void setOption(const char *key, double value) { check(icpb_set_option(ctx_, key, value)); }
+    icpb_ctx *handle() { return ctx_; }
+    const Eigen::Affine3d &getTransform() const { return minResult_.C_global2globalnew; }
+
+private:
+    icpb_ctx *ctx_;
+    Result minResult_;
+    bool pd_pending_ = false;
+
+    void check(int rc)
+    {
+        if (rc != ICPB_OK) throw std::runtime_error(std::string("TrimmedGPU: ") + icpb_strerror(rc) + " / " + icpb_last_error(ctx_));
+    }
+    static void toColMajor(const Eigen::Affine3d &a, double T[16])
+    {
+        const Eigen::Matrix4d m = a.matrix();
+        for (int c = 0; c < 4; ++c)
+            for (int r = 0; r < 4; ++r) T[c * 4 + r] = m(r, c);
+    }
+    void upload(const PointcloudAdapter &meas)
+    {
+        double T[16];
+        toColMajor(meas.local2global(), T);
+        check(icpb_source_upload(ctx_, meas.vertexData(), meas.vertexCount(), T, meas.density()));
+    }
+    Result alignResident(size_t max_iter, double min_mse, double min_mse_diff, double overlap, bool eager_pairs)
+    {
+        icpb_params prm;
+        prm.max_iter = max_iter;
+        prm.min_mse = min_mse;
+        prm.min_mse_diff = min_mse_diff;
+        prm.overlap = overlap;
+        icpb_result r;
+        check(icpb_align_resident(ctx_, &prm, &r));
+        Result out;
+        Eigen::Matrix4d m;
+        for (int c = 0; c < 4; ++c)
+            for (int rr = 0; rr < 4; ++rr) m(rr, c) = r.C_global2globalnew[c * 4 + rr];
+        out.C_global2globalnew = Eigen::Affine3d(m);
+        out.iter = r.iter;
+        out.pairs = r.pairs;
+        out.mse = r.mse;
+        out.mse_diff = r.mse_diff;
+        out.d_box = r.d_box;
+        out.overlap = r.overlap;
+        pd_pending_ = true;
+        // golden section: later probes overwrite the device buffers, so each probe's distances are fetched right away
+        if (eager_pairs) fetchPairsDistance(out);
+        return out;
+    }
+    void fetchPairsDistance(Result &res)
+    {
+        if (!pd_pending_) return;
+        size_t n = 0;
+        check(icpb_pairs_distance(ctx_, 0, 0, &n));
+        res.pairs_distance.resize(n);
+        if (n) check(icpb_pairs_distance(ctx_, res.pairs_distance.data(), n, &n));
+        pd_pending_ = false;
+    }
+};
+
+#ifdef ICP_B200_REPLACE_TRIMMEDKD
+/** drop-in: existing callers of envire::icp::TrimmedKD (icp/icpLocalization.hpp, viz/enview/ICPHandler) pick up the GPU path */
+typedef TrimmedGPU TrimmedKD;
+#endif
+
+} // namespace icp
+} // namespace envire
+#endif

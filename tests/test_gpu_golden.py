@@ -1,0 +1,61 @@
+"""GPU tier: the CUDA path against the golden vectors of the reference's own code (tests/golden/golden.json), both
+through the C ABI (ctypes) and through the C++ host mirror envire::icp::TrimmedGPU driven like test/unit/icp.cpp."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, assert_transform_close
+from test_golden import CASES, GOLDEN, check_against_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", sorted(n for n in CASES if CASES[n]["kind"] == "fixed"))
+def test_c_abi_matches_reference_golden(icp, oracle, name):
+    c = CASES[name]
+    icp.clear_model()
+    for xyz, T, dens in c["model"]:
+        icp.add_to_model(xyz, T=T, density=dens)
+    r = icp.align(c["src"], T=c["T_src"], density=c["density"], **c["params"])
+    check_against_golden(name, r.matrix(), r.iter, r.pairs, r.mse, r.overlap, icp.pairs_distance(), oracle)
+
+
+@pytest.fixture(scope="module")
+def cli():
+    src = os.path.join(ROOT, "tests", "cpp", "icp_gpu_cli.cpp")
+    exe = os.path.join(ROOT, "tests", "cpp", "icp_gpu_cli")
+    pk = os.path.join(ROOT, "slam-envire_b200")
+    deps = [src, os.path.join(pk, "icp", "icp_gpu.hpp"), os.path.join(pk, "compat", "Eigen", "mini_eigen.hpp"),
+            os.path.join(pk, "libicp_b200.so")]
+    if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I" + pk, "-I" + os.path.join(pk, "compat"),
+                               "-o", exe, src, "-L" + pk, "-licp_b200", "-Wl,-rpath," + pk])
+    return exe
+
+
+@pytest.mark.parametrize("name", sorted(n for n in CASES if len(CASES[n]["model"]) == 1))
+def test_host_mirror_matches_reference_golden(cli, tmp_path, name):
+    """TrimmedGPU: addToModel / align (fixed and golden-section) / applyTransform -> FrameNode::setTransform / getters."""
+    c, g = CASES[name], GOLDEN[name]
+    mp, sp = str(tmp_path / "m.bin"), str(tmp_path / "s.bin")
+    np.ascontiguousarray(c["model"][0][0], dtype=np.float64).tofile(mp)
+    np.ascontiguousarray(c["src"], dtype=np.float64).tofile(sp)
+    T = np.eye(4) if c["T_src"] is None else np.asarray(c["T_src"])
+    p = c["params"]
+    args = [cli, mp, sp] + ["%.17g" % v for v in T.T.reshape(16)] + ["%.17g" % c["density"], c["kind"],
+                                                                      str(p["max_iter"]), "%.17g" % p["min_mse"],
+                                                                      "%.17g" % p["min_mse_diff"]]
+    args += ["%.17g" % p[k] for k in (("alpha", "beta", "eps") if c["kind"] == "golden" else ("overlap",))]
+    out = json.loads(subprocess.check_output(args).decode())
+    assert "error" not in out, out
+    extent = float(np.ptp(c["model"][0][0], axis=0).max())
+    assert out["iter"] == g["iter"] and out["pairs"] == g["pairs"]
+    assert abs(out["overlap"] - g["overlap"]) < 1e-12
+    assert_transform_close(np.array(out["fn_T"]), np.array(g["fn_T"]), extent)
+    assert abs(out["mse"] - g["mse"]) <= 1e-5 * abs(g["mse"])
+    assert out["n_pairs_distance"] == g["n_pairs_distance"] and out["pd_sorted"]
+    assert abs(out["pd_sum"] - g["pd_sum"]) <= 1e-7 * abs(g["pd_sum"]) + 1e-12
+    assert out["set_transform_events"] == 1  # applyTransform fires FrameNode::setTransform exactly once
