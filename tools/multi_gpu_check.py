@@ -1,0 +1,53 @@
+"""torchrun --nproc-per-node N tools/multi_gpu_check.py : sharded align (NCCL) vs the same align on one GPU.
+Every rank also runs the unsharded problem in a second context; results must agree (iter, pairs exactly; C, mse to
+fp64 re-association)."""
+import importlib, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+pkg = importlib.import_module("slam-envire_b200")
+synth = importlib.import_module("slam-envire_b200.synth")
+sharding = importlib.import_module("slam-envire_b200.sharding")
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+ok = True
+cases = [("cfg1", 0.2, 1.0, {}), ("cfg2", 0.05, 1.0, dict(max_iter=15)), ("cfg1", 0.1, 0.37, dict(max_iter=10, overlap=0.6)),
+         ("ties", 0, 1.0, {})]
+icp = pkg.Icp(local)
+sharding.init_comm(icp, dist, torch.device("cuda", local))
+single = pkg.Icp(local)
+for name, scale, density, over in cases:
+    if name == "ties":  # lattice data: massive equidistant ties at the threshold, split across ranks
+        g = np.arange(0, 24, dtype=np.float64)
+        m = np.stack(np.meshgrid(g, g, indexing="ij"), -1).reshape(-1, 2)
+        m = np.concatenate([m, np.zeros((len(m), 1))], 1)
+        s = m + [0.3, 0.2, 0.0]
+        prm = dict(max_iter=6, min_mse=1e-12, min_mse_diff=1e-14, overlap=0.55)
+    else:
+        m, s, T, prm = synth.config(name, scale)
+        prm = dict(prm, **over)
+    for c in (icp, single):
+        c.clear_model()
+        c.add_to_model(m)
+    local_pts, size = sharding.shard_source(s, density, world, rank)
+    icp.upload_source_shard(local_pts, size)
+    r = icp.align_resident(**prm)
+    r1 = single.align(s, density=density, **prm)
+    same = (r.iter == r1.iter and r.pairs == r1.pairs and np.abs(r.matrix() - r1.matrix()).max() < 1e-9
+            and abs(r.mse - r1.mse) <= 1e-9 * abs(r1.mse) + 1e-300)
+    tr, tr1 = icp.trace(), single.trace()
+    same = same and len(tr) == len(tr1) and all(a["kept"] == b["kept"] and a["found"] == b["found"] for a, b in zip(tr, tr1))
+    ok = ok and same
+    if rank == 0:
+        print(name, "world", world, "iter", r.iter, r1.iter, "pairs", r.pairs, r1.pairs, "mse", r.mse, r1.mse,
+              "dC", np.abs(r.matrix() - r1.matrix()).max(), "OK" if same else "MISMATCH", icp.timing()["total_ms"], single.timing()["total_ms"])
+flag = torch.tensor([1 if ok else 0], device="cuda")
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("MULTI_GPU_CHECK", "PASS" if flag.item() == 1 else "FAIL")
+icp.close(); single.close()
+dist.destroy_process_group()
+sys.exit(0 if flag.item() == 1 else 1)
