@@ -95,6 +95,34 @@ ICPB_HD double icpb_cell_mindist2(const GridView &g, int level, int cx, int cy, 
     return d2;
 }
 
+// The same lower bound in fp32 "cell units" (u = (q - o)/h), used by the traversal: cell corners are small
+// integers (exact in fp32), the query coordinate carries a conversion error that `slack` (>= that error plus
+// the cell-assignment slack, in cells) absorbs, and the sum is scaled down to stay below the true value.
+// Conservative by construction: never larger than the true squared distance (in cells^2) to any point filed
+// under the cell, so pruning with it cannot lose a candidate.
+ICPB_HD float icpb_cell_mindist2f(int level, int cx, int cy, int cz, float ux, float uy, float uz, float slack)
+{
+    const float s = (float)(1u << level);
+    float lo, gap, d2;
+    lo = (float)cx * s;
+    gap = fmaxf(fmaxf(lo - ux, ux - (lo + s)) - slack, 0.0f);
+    d2 = gap * gap;
+    lo = (float)cy * s;
+    gap = fmaxf(fmaxf(lo - uy, uy - (lo + s)) - slack, 0.0f);
+    d2 += gap * gap;
+    lo = (float)cz * s;
+    gap = fmaxf(fmaxf(lo - uz, uz - (lo + s)) - slack, 0.0f);
+    d2 += gap * gap;
+    return d2 * 0.999999f;
+}
+// upper bound of (bound * inv_h^2) in fp32
+ICPB_HD float icpb_bound_cells(double bound, double inv_h2)
+{
+    const double b = bound * inv_h2;
+    if (!(b < 3.0e38)) return (float)icpb_inf();
+    return (float)b * 1.000001f + 1e-30f;
+}
+
 ICPB_HD void icpb_nn_eval(const MPoint &m, uint32_t pos, double qx, double qy, double qz, double &bd2,
                           unsigned long long &bidx, uint32_t &bpos)
 {
@@ -145,6 +173,13 @@ ICPB_HD void icpb_nn_search(const GridView &g, double qx, double qy, double qz, 
     }
     start_level = l;
 
+    // traversal state in fp32 cell units
+    const double inv_h2 = g.inv_h * g.inv_h;
+    const double uxd = (qx - g.o[0]) * g.inv_h, uyd = (qy - g.o[1]) * g.inv_h, uzd = (qz - g.o[2]) * g.inv_h;
+    const float ux = (float)uxd, uy = (float)uyd, uz = (float)uzd;
+    const float slack = 1e-6f * (fmaxf(fmaxf(fabsf(ux), fabsf(uy)), fabsf(uz)) + 4096.0f);
+    float boundf = icpb_bound_cells(bound, inv_h2);
+
     unsigned long long stack[ICPB_SEARCH_STACK];
     int sp = 0;
     {
@@ -165,13 +200,13 @@ ICPB_HD void icpb_nn_search(const GridView &g, double qx, double qy, double qz, 
             lo[a] = (int)flo;
             hi[a] = (int)fhi;
         }
-        double best_md2 = INF;
+        float best_md2 = (float)INF;
         int best_at = -1;
         for (int z = lo[2]; z <= hi[2]; ++z)
             for (int y = lo[1]; y <= hi[1]; ++y)
                 for (int x = lo[0]; x <= hi[0]; ++x) {
-                    const double md2 = icpb_cell_mindist2(g, l, x, y, z, qx, qy, qz);
-                    if (md2 > bound) continue;
+                    const float md2 = icpb_cell_mindist2f(l, x, y, z, ux, uy, uz, slack);
+                    if (md2 > boundf) continue;
                     if (sp >= ICPB_SEARCH_STACK - 64) continue; // cannot happen (<= 27 roots)
                     if (md2 < best_md2) {
                         best_md2 = md2;
@@ -192,28 +227,29 @@ ICPB_HD void icpb_nn_search(const GridView &g, double qx, double qy, double qz, 
         const unsigned long long e = stack[--sp];
         const int lev = (int)(e >> 60);
         const int cx = (int)(e & 0xFFFFFu), cy = (int)((e >> 20) & 0xFFFFFu), cz = (int)((e >> 40) & 0xFFFFFu);
-        bound = (dbox2s < bd2) ? dbox2s : bd2;
-        if (icpb_cell_mindist2(g, lev, cx, cy, cz, qx, qy, qz) > bound) continue;
+        if (icpb_cell_mindist2f(lev, cx, cy, cz, ux, uy, uz, slack) > boundf) continue;
         if (lev == 0) {
+            const double before = bd2;
             icpb_scan_cell(g, cx, cy, cz, qx, qy, qz, bd2, bidx, bpos);
+            if (bd2 < before) boundf = icpb_bound_cells((dbox2s < bd2) ? dbox2s : bd2, inv_h2);
             continue;
         }
         const size_t ci = ((size_t)cz * g.dim[lev][1] + cy) * g.dim[lev][0] + cx;
         const unsigned m = g.mask[lev][ci];
         if (!m) continue;
-        const double hc = g.h * (double)(1u << (lev - 1));
-        const unsigned near = (qx >= g.o[0] + (double)(2 * cx + 1) * hc ? 1u : 0u) |
-                              (qy >= g.o[1] + (double)(2 * cy + 1) * hc ? 2u : 0u) |
-                              (qz >= g.o[2] + (double)(2 * cz + 1) * hc ? 4u : 0u);
+        const float hc = (float)(1u << (lev - 1));
+        const unsigned near = (ux >= (float)(2 * cx + 1) * hc ? 1u : 0u) | (uy >= (float)(2 * cy + 1) * hc ? 2u : 0u) |
+                              (uz >= (float)(2 * cz + 1) * hc ? 4u : 0u);
         if (lev == 1) {
             for (int k = 0; k < 8; ++k) {
                 const unsigned ch = near ^ ((ORD >> (4 * k)) & 7u);
                 if (!((m >> ch) & 1u)) continue;
                 const int x = 2 * cx + (int)(ch & 1u), y = 2 * cy + (int)((ch >> 1) & 1u),
                           z = 2 * cz + (int)((ch >> 2) & 1u);
-                bound = (dbox2s < bd2) ? dbox2s : bd2;
-                if (icpb_cell_mindist2(g, 0, x, y, z, qx, qy, qz) > bound) continue;
+                if (icpb_cell_mindist2f(0, x, y, z, ux, uy, uz, slack) > boundf) continue;
+                const double before = bd2;
                 icpb_scan_cell(g, x, y, z, qx, qy, qz, bd2, bidx, bpos);
+                if (bd2 < before) boundf = icpb_bound_cells((dbox2s < bd2) ? dbox2s : bd2, inv_h2);
             }
         } else {
             for (int k = 7; k >= 0; --k) {
@@ -221,7 +257,7 @@ ICPB_HD void icpb_nn_search(const GridView &g, double qx, double qy, double qz, 
                 if (!((m >> ch) & 1u)) continue;
                 const int x = 2 * cx + (int)(ch & 1u), y = 2 * cy + (int)((ch >> 1) & 1u),
                           z = 2 * cz + (int)((ch >> 2) & 1u);
-                if (icpb_cell_mindist2(g, lev - 1, x, y, z, qx, qy, qz) > bound) continue;
+                if (icpb_cell_mindist2f(lev - 1, x, y, z, ux, uy, uz, slack) > boundf) continue;
                 if (sp < ICPB_SEARCH_STACK)
                     stack[sp++] = ((unsigned long long)(lev - 1) << 60) | ((unsigned long long)z << 40) |
                                   ((unsigned long long)y << 20) | (unsigned long long)x;
