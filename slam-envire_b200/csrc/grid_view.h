@@ -41,6 +41,9 @@
 #define ICPB_MAX_LEVELS 16
 #define ICPB_NONE 0xFFFFFFFFu
 #define ICPB_SEARCH_STACK 112
+#ifndef ICPB_COUNT
+#define ICPB_COUNT(what) // instrumentation hook (tests/harness defines it to count traversal work)
+#endif
 
 struct
 #ifdef __CUDACC__
@@ -53,6 +56,18 @@ struct
     unsigned long long idx; // insertion index (order of addToModel visits)
 };
 
+// fp32 copy of a model point in cell units relative to the grid origin: the candidate pre-filter reads these
+// (16 B, coalesced float4 loads); only candidates that can still win are re-evaluated exactly from pts[].
+struct
+#ifdef __CUDACC__
+    __align__(16)
+#else
+    __attribute__((aligned(16)))
+#endif
+        FPoint {
+    float x, y, z, w;
+};
+
 struct GridView {
     double o[3];  // origin (min corner of the model bounding box)
     double h;     // level-0 cell edge
@@ -63,6 +78,7 @@ struct GridView {
     const uint32_t *cell_start;
     const uint8_t *mask[ICPB_MAX_LEVELS];
     const MPoint *pts;
+    const FPoint *ptsf; // same order as pts
     uint32_t n;
 };
 
@@ -135,12 +151,35 @@ ICPB_HD void icpb_nn_eval(const MPoint &m, uint32_t pos, double qx, double qy, d
     }
 }
 
-ICPB_HD void icpb_scan_cell(const GridView &g, int cx, int cy, int cz, double qx, double qy, double qz, double &bd2,
-                            unsigned long long &bidx, uint32_t &bpos)
+// squared fp32 radius (cell units) inside which a candidate must be re-evaluated exactly: the fp32 distance of a
+// point that can still beat (or tie) the best is at most sqrt(bound) + (conversion errors of query and point)
+ICPB_HD float icpb_cand_radius2(float boundf, float slack)
 {
-    const size_t c = ((size_t)cz * g.dim[0][1] + cy) * g.dim[0][0] + cx;
+    const float r = sqrtf(boundf) + 2.0f * slack;
+    return r * r * 1.00001f;
+}
+
+ICPB_HD void icpb_scan_cell(const GridView &g, int cx, int cy, int cz, double qx, double qy, double qz, float ux, float uy,
+                            float uz, float slack, double dbox2s, double inv_h2, double &bd2, unsigned long long &bidx,
+                            uint32_t &bpos, float &boundf, float &candf)
+{
+    const uint32_t c = ((uint32_t)cz * (uint32_t)g.dim[0][1] + (uint32_t)cy) * (uint32_t)g.dim[0][0] + (uint32_t)cx;
     const uint32_t s = g.cell_start[c], e = g.cell_start[c + 1];
-    for (uint32_t p = s; p < e; ++p) icpb_nn_eval(g.pts[p], p, qx, qy, qz, bd2, bidx, bpos);
+    ICPB_COUNT(cells);
+    for (uint32_t p = s; p < e; ++p) {
+        ICPB_COUNT(cands);
+        const FPoint f = g.ptsf[p];
+        const float dx = ux - f.x, dy = uy - f.y, dz = uz - f.z;
+        const float d2f = dx * dx + dy * dy + dz * dz;
+        if (d2f > candf) continue; // cannot be nearer than the best so far (nor tie with it)
+        ICPB_COUNT(exact);
+        const double before = bd2;
+        icpb_nn_eval(g.pts[p], p, qx, qy, qz, bd2, bidx, bpos);
+        if (bd2 < before) {
+            boundf = icpb_bound_cells((dbox2s < bd2) ? dbox2s : bd2, inv_h2);
+            candf = icpb_cand_radius2(boundf, slack);
+        }
+    }
 }
 
 // Exact NN of q.  dbox2s = d_box^2 widened by a few ulps (+inf when unbounded);
@@ -179,6 +218,7 @@ ICPB_HD void icpb_nn_search(const GridView &g, double qx, double qy, double qz, 
     const float ux = (float)uxd, uy = (float)uyd, uz = (float)uzd;
     const float slack = 1e-6f * (fmaxf(fmaxf(fabsf(ux), fabsf(uy)), fabsf(uz)) + 4096.0f);
     float boundf = icpb_bound_cells(bound, inv_h2);
+    float candf = icpb_cand_radius2(boundf, slack);
 
     unsigned long long stack[ICPB_SEARCH_STACK];
     int sp = 0;
@@ -225,17 +265,17 @@ ICPB_HD void icpb_nn_search(const GridView &g, double qx, double qy, double qz, 
     const unsigned ORD = 0x76534210u; // child visiting order as XOR codes: 0,1,2,4,3,5,6,7
     while (sp > 0) {
         const unsigned long long e = stack[--sp];
+        ICPB_COUNT(pops);
         const int lev = (int)(e >> 60);
         const int cx = (int)(e & 0xFFFFFu), cy = (int)((e >> 20) & 0xFFFFFu), cz = (int)((e >> 40) & 0xFFFFFu);
         if (icpb_cell_mindist2f(lev, cx, cy, cz, ux, uy, uz, slack) > boundf) continue;
         if (lev == 0) {
-            const double before = bd2;
-            icpb_scan_cell(g, cx, cy, cz, qx, qy, qz, bd2, bidx, bpos);
-            if (bd2 < before) boundf = icpb_bound_cells((dbox2s < bd2) ? dbox2s : bd2, inv_h2);
+            icpb_scan_cell(g, cx, cy, cz, qx, qy, qz, ux, uy, uz, slack, dbox2s, inv_h2, bd2, bidx, bpos, boundf, candf);
             continue;
         }
         const size_t ci = ((size_t)cz * g.dim[lev][1] + cy) * g.dim[lev][0] + cx;
         const unsigned m = g.mask[lev][ci];
+        ICPB_COUNT(nodes);
         if (!m) continue;
         const float hc = (float)(1u << (lev - 1));
         const unsigned near = (ux >= (float)(2 * cx + 1) * hc ? 1u : 0u) | (uy >= (float)(2 * cy + 1) * hc ? 2u : 0u) |
@@ -247,9 +287,7 @@ ICPB_HD void icpb_nn_search(const GridView &g, double qx, double qy, double qz, 
                 const int x = 2 * cx + (int)(ch & 1u), y = 2 * cy + (int)((ch >> 1) & 1u),
                           z = 2 * cz + (int)((ch >> 2) & 1u);
                 if (icpb_cell_mindist2f(0, x, y, z, ux, uy, uz, slack) > boundf) continue;
-                const double before = bd2;
-                icpb_scan_cell(g, x, y, z, qx, qy, qz, bd2, bidx, bpos);
-                if (bd2 < before) boundf = icpb_bound_cells((dbox2s < bd2) ? dbox2s : bd2, inv_h2);
+                icpb_scan_cell(g, x, y, z, qx, qy, qz, ux, uy, uz, slack, dbox2s, inv_h2, bd2, bidx, bpos, boundf, candf);
             }
         } else {
             for (int k = 7; k >= 0; --k) {

@@ -162,6 +162,7 @@ struct icpb_ctx {
     size_t model_n = 0;
     bool grid_dirty = true;
     DevBuf<MPoint> pts;
+    DevBuf<FPoint> ptsf;
     DevBuf<uint32_t> cell_start;
     DevBuf<uint8_t> masks;
     DevBuf<uint32_t> keys0, keys1, vals0, vals1, sort_scratch;
@@ -299,6 +300,7 @@ void icpb_destroy(icpb_ctx *ctx)
     if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
     ctx->model_raw.release();
     ctx->pts.release();
+    ctx->ptsf.release();
     ctx->cell_start.release();
     ctx->masks.release();
     ctx->keys0.release();
@@ -517,10 +519,11 @@ static int build_grid(icpb_ctx *ctx)
     const size_t ncell = (size_t)dim0[0] * dim0[1] * dim0[2];
 
     CK(ctx->pts.ensure(n));
+    CK(ctx->ptsf.ensure(n));
     CK(ctx->cell_start.ensure(ncell + 1 + scan_scratch_elems(ncell + 1)));
     CK(cudaMemsetAsync(ctx->cell_start.p, 0, (ncell + 1) * sizeof(uint32_t), s));
-    gather_points_kernel<<<grid_for(n, 256), 256, 0, s>>>(ctx->model_raw.p, keys_sorted, perm, (uint32_t)n, ctx->pts.p,
-                                                          ctx->cell_start.p);
+    gather_points_kernel<<<grid_for(n, 256), 256, 0, s>>>(ctx->model_raw.p, keys_sorted, perm, (uint32_t)n, gd,
+                                                          ctx->pts.p, ctx->ptsf.p, ctx->cell_start.p);
     CKL();
     exclusive_scan_u32(ctx->cell_start.p, ctx->cell_start.p, ncell + 1, ctx->cell_start.p + ncell + 1, s,
                        &ctx->launches);
@@ -563,6 +566,7 @@ static int build_grid(icpb_ctx *ctx)
     }
     g.cell_start = ctx->cell_start.p;
     g.pts = ctx->pts.p;
+    g.ptsf = ctx->ptsf.p;
     g.n = (uint32_t)n;
     CK(cudaEventRecord(e1, s));
     CK(cudaStreamSynchronize(s));

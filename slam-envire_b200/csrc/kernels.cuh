@@ -107,7 +107,8 @@ __global__ void __launch_bounds__(256) count_unique_kernel(const uint32_t *__res
 
 // sorted layout: pts_sorted[j] = {model[perm[j]], perm[j]}; cell_count[key[j]]++
 __global__ void gather_points_kernel(const double *__restrict__ raw, const uint32_t *__restrict__ keys,
-                                     const uint32_t *__restrict__ perm, uint32_t n, MPoint *__restrict__ out,
+                                     const uint32_t *__restrict__ perm, uint32_t n, GridDims g,
+                                     MPoint *__restrict__ out, FPoint *__restrict__ outf,
                                      uint32_t *__restrict__ cell_count)
 {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -119,6 +120,12 @@ __global__ void gather_points_kernel(const double *__restrict__ raw, const uint3
     m.z = raw[3 * (size_t)src + 2];
     m.idx = src;
     out[j] = m;
+    FPoint f;
+    f.x = (float)((m.x - g.o[0]) * g.inv_h);
+    f.y = (float)((m.y - g.o[1]) * g.inv_h);
+    f.z = (float)((m.z - g.o[2]) * g.inv_h);
+    f.w = 0.0f;
+    outf[j] = f;
     atomicAdd(&cell_count[keys[j]], 1u);
 }
 

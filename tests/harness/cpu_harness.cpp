@@ -13,6 +13,9 @@
 #include <numeric>
 #include <vector>
 
+struct HsCounters { unsigned long long cells, cands, pops, nodes, exact; };
+static HsCounters g_cnt;
+#define ICPB_COUNT(what) (++g_cnt.what)
 #include "../../slam-envire_b200/csrc/grid_view.h"
 #include "../../slam-envire_b200/csrc/pose.h"
 
@@ -20,6 +23,7 @@ namespace {
 struct HostGrid {
     GridView g;
     std::vector<MPoint> pts;
+    std::vector<FPoint> ptsf;
     std::vector<uint32_t> cell_start;
     std::vector<std::vector<uint8_t>> masks;
     std::vector<uint32_t> pos_of_idx;
@@ -53,6 +57,7 @@ void build(HostGrid &G, const double *model, size_t n, double h)
     std::iota(perm.begin(), perm.end(), 0u);
     std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
     G.pts.resize(n);
+    G.ptsf.resize(n);
     G.pos_of_idx.resize(n);
     G.cell_start.assign(ncell + 1, 0);
     for (size_t j = 0; j < n; ++j) {
@@ -61,6 +66,10 @@ void build(HostGrid &G, const double *model, size_t n, double h)
         G.pts[j].y = model[3 * s + 1];
         G.pts[j].z = model[3 * s + 2];
         G.pts[j].idx = s;
+        G.ptsf[j].x = (float)((model[3 * s] - g.o[0]) * g.inv_h);
+        G.ptsf[j].y = (float)((model[3 * s + 1] - g.o[1]) * g.inv_h);
+        G.ptsf[j].z = (float)((model[3 * s + 2] - g.o[2]) * g.inv_h);
+        G.ptsf[j].w = 0.0f;
         G.pos_of_idx[s] = (uint32_t)j;
         G.cell_start[key[s] + 1]++;
     }
@@ -90,11 +99,17 @@ void build(HostGrid &G, const double *model, size_t n, double h)
     for (int l = 1; l <= L; ++l) g.mask[l] = G.masks[l].data();
     g.cell_start = G.cell_start.data();
     g.pts = G.pts.data();
+    g.ptsf = G.ptsf.data();
     g.n = (uint32_t)n;
 }
 } // namespace
 
 extern "C" {
+void hs_counters(unsigned long long *out, int reset)
+{
+    out[0] = g_cnt.cells; out[1] = g_cnt.cands; out[2] = g_cnt.pops; out[3] = g_cnt.nodes; out[4] = g_cnt.exact;
+    if (reset) memset(&g_cnt, 0, sizeof(g_cnt));
+}
 
 // exact NN of every query through icpb_nn_search; warm_idx (insertion indices, may be NULL) seeds the bound
 int hs_search(const double *model, size_t nm, double h, const double *q, size_t nq, double d_box,
