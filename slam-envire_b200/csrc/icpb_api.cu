@@ -757,12 +757,9 @@ static int launch_trim(icpb_ctx *ctx, uint32_t n)
         CKL();
         ctx->launches += 3;
     }
-    for (int p = 0; p < SEL_T_PASSES; ++p) {
-        select_kernel<<<blocks, SEL_THREADS, 0, s>>>(ctx->nn_d.p, ctx->src_perm.p, n, ctx->d_state, ctx->d_ghist, p, 1, 1,
-                                                     6 + p);
-        CKL();
-        ++ctx->launches;
-    }
+    tie_select_kernel<<<1, 1024, 0, s>>>(ctx->nn_d.p, ctx->src_perm.p, n, ctx->d_state, ctx->d_ghist);
+    CKL();
+    ++ctx->launches;
     return ICPB_OK;
 }
 
@@ -784,7 +781,7 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
     const size_t n_po = (size_t)((double)ctx->adapter_size * prm->overlap);
     const size_t max_iter = prm->max_iter;
 
-    const unsigned mom_blocks = std::max(1u, std::min(grid_for(n, MOM_THREADS), 148u * 4u));
+    const unsigned mom_blocks = std::max(1u, std::min(grid_for(n, MOM_THREADS), 148u * 6u));
     CK(ctx->partials.ensure((size_t)mom_blocks * ICPB_NSUMS));
     ctx->trace_cap = (int)std::min<size_t>(std::max<size_t>(max_iter, 1), 65536);
     CK(ctx->trace.ensure((size_t)ctx->trace_cap * ICPB_TRACE_COLS_DEV));

@@ -238,7 +238,8 @@ __device__ void select_pick(IcpState *st, uint32_t *ghist, int pass, bool tie_mo
     const int bits = tie_mode ? c_sel_t_bits[pass] : c_sel_d_bits[pass];
     const int shift = tie_mode ? c_sel_t_shift[pass] : c_sel_d_shift[pass];
     const int bins = 1 << bits;
-    const int per = (bins + SEL_THREADS - 1) / SEL_THREADS;
+    const int nthr = (int)blockDim.x;
+    const int per = (bins + nthr - 1) / nthr;
     unsigned long long krem;
     if (tie_mode)
         krem = (pass == 0) ? st->quota : st->tie_krem;
@@ -332,9 +333,21 @@ __global__ void __launch_bounds__(SEL_THREADS)
     if (!tie_mode) {
         const unsigned long long prefix = pass == 0 ? 0ull : st->sel_prefix;
         const int hs = shift + bits; // bits above the current digit must match the prefix
-        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-            const unsigned long long key = (unsigned long long)__double_as_longlong(nn_d[i]);
-            if (pass == 0 || (key >> hs) == (prefix >> hs)) atomicAdd(&hist[(unsigned)(key >> shift) & bin_mask], 1u);
+        // four independent loads in flight per thread before the (dependent) shared-memory atomics
+        const uint32_t T = gridDim.x * blockDim.x;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 4u * T) {
+            unsigned long long key[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t j = i + (uint32_t)u * T;
+                key[u] = j < n && j >= i ? (unsigned long long)__double_as_longlong(nn_d[j]) : ~0ull;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (key[u] == ~0ull) continue; // out of range (a NaN pattern never occurs in nn_d)
+                if (pass == 0 || (key[u] >> hs) == (prefix >> hs))
+                    atomicAdd(&hist[(unsigned)(key[u] >> shift) & bin_mask], 1u);
+            }
         }
     } else {
         const unsigned long long tau_bits = (unsigned long long)__double_as_longlong(st->tau);
@@ -371,6 +384,33 @@ __global__ void __launch_bounds__(SEL_THREADS) select_pick_kernel(IcpState *st, 
     select_pick(st, ghist, pass, tie_mode != 0, scan_smem);
 }
 
+// Tie-break in one launch: which of the pairs at distance == tau survive is decided by pair index (a stable
+// sort by (distance, index)).  Only needed when fewer ties are kept than exist (need_tie), which is rare on
+// real-valued data, so a single block walks the three index digits back to back instead of three grid launches.
+__global__ void __launch_bounds__(1024)
+    tie_select_kernel(const double *__restrict__ nn_d, const uint32_t *__restrict__ perm, uint32_t n, IcpState *st,
+                      uint32_t *ghist)
+{
+    if (st->done || !st->need_tie) return;
+    __shared__ uint32_t scan_smem[34];
+    const unsigned long long tau_bits = (unsigned long long)__double_as_longlong(st->tau);
+    for (int pass = 0; pass < SEL_T_PASSES; ++pass) {
+        const int bits = c_sel_t_bits[pass], shift = c_sel_t_shift[pass], hs = shift + bits;
+        const unsigned bin_mask = (1u << bits) - 1u;
+        const unsigned prefix = pass == 0 ? 0u : st->tie_prefix;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            if ((unsigned long long)__double_as_longlong(nn_d[i]) != tau_bits) continue;
+            const uint32_t pi = perm[i];
+            if (pass == 0 || hs >= 32 || (pi >> hs) == (prefix >> hs)) atomicAdd(&ghist[(pi >> shift) & bin_mask], 1u);
+        }
+        __threadfence();
+        __syncthreads();
+        select_pick(st, ghist, pass, true, scan_smem);
+        __threadfence();
+        __syncthreads();
+    }
+}
+
 __device__ __forceinline__ bool pair_kept(double d, uint32_t i, double tau, long long p_cut)
 {
     return d < tau || (d == tau && (long long)i <= p_cut);
@@ -387,7 +427,7 @@ __device__ __forceinline__ double shfl_xor_double(double v, int o)
     return __shfl_xor_sync(0xFFFFFFFFu, v, o);
 }
 
-__global__ void __launch_bounds__(MOM_THREADS)
+__global__ void __launch_bounds__(MOM_THREADS, 3)
     moments_kernel(const GridView g, const double *__restrict__ sx, const double *__restrict__ sy,
                    const double *__restrict__ sz, uint32_t n, IcpState *__restrict__ st,
                    const uint32_t *__restrict__ nn_pos, const double *__restrict__ nn_d,
@@ -403,9 +443,9 @@ __global__ void __launch_bounds__(MOM_THREADS)
     const double tau = st->tau;
     const long long p_cut = st->p_cut;
     const bool any = st->sel_k > 0;
-    double M[12];
-#pragma unroll
-    for (int k = 0; k < 12; ++k) M[k] = st->M[k];
+    __shared__ double M[12]; // broadcast reads instead of 24 registers per thread
+    if (threadIdx.x < 12) M[threadIdx.x] = st->M[threadIdx.x];
+    __syncthreads();
     if (any)
         for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
             const double d = nn_d[i];
