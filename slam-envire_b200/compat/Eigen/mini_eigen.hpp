@@ -71,6 +71,7 @@ public:
     Matrix(const T &x, const T &y, const T &z, const T &w) { static_assert(R * C == 4, "4-vector"); d[0] = x; d[1] = y; d[2] = z; d[3] = w; }
 
     static Matrix Zero() { return Matrix(); }
+    static Matrix Ones() { Matrix m; for (int i = 0; i < R * C; ++i) m.d[i] = T(1); return m; }
     static Matrix Identity() { Matrix m; for (int i = 0; i < (R < C ? R : C); ++i) m(i, i) = T(1); return m; }
     static Matrix UnitX() { Matrix m; m.d[0] = T(1); return m; }
     static Matrix UnitY() { Matrix m; m.d[1] = T(1); return m; }

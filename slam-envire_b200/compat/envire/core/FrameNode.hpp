@@ -56,6 +56,20 @@ public:
     ~Environment() { for (size_t i = 0; i < owned_.size(); ++i) delete owned_[i]; }
     FrameNode *getRootNode() { return root_; }
     void attachItem(EnvironmentItem *item) { item->env_ = this; owned_.push_back(item); }
+    /** hands the item back to the caller (who then owns it), like Environment::detachItem */
+    void detachItem(EnvironmentItem *item)
+    {
+        for (size_t i = 0; i < owned_.size(); ++i)
+            if (owned_[i] == item) { owned_.erase(owned_.begin() + i); break; }
+        item->env_ = 0;
+    }
+    template <class T> std::vector<T *> getItems()
+    {
+        std::vector<T *> out;
+        for (size_t i = 0; i < owned_.size(); ++i)
+            if (T *t = dynamic_cast<T *>(owned_[i])) out.push_back(t);
+        return out;
+    }
     void addChild(FrameNode *parent, FrameNode *child)
     {
         if (!child->isAttached()) attachItem(child);

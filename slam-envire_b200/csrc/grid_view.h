@@ -262,34 +262,37 @@ ICPB_HD void icpb_nn_search(const GridView &g, double qx, double qy, double qz, 
         }
     }
 
+    // Two-phase ("while-while") traversal: every lane first walks the pyramid until it holds a cell group to scan
+    // (a level-1 node, or a level-0 root cell), then scans it -- lanes of a warp stay in the same code section
+    // instead of interleaving node expansion with candidate evaluation.
     const unsigned ORD = 0x76534210u; // child visiting order as XOR codes: 0,1,2,4,3,5,6,7
-    while (sp > 0) {
-        const unsigned long long e = stack[--sp];
-        ICPB_COUNT(pops);
-        const int lev = (int)(e >> 60);
-        const int cx = (int)(e & 0xFFFFFu), cy = (int)((e >> 20) & 0xFFFFFu), cz = (int)((e >> 40) & 0xFFFFFu);
-        if (icpb_cell_mindist2f(lev, cx, cy, cz, ux, uy, uz, slack) > boundf) continue;
-        if (lev == 0) {
-            icpb_scan_cell(g, cx, cy, cz, qx, qy, qz, ux, uy, uz, slack, dbox2s, inv_h2, bd2, bidx, bpos, boundf, candf);
-            continue;
-        }
-        const size_t ci = ((size_t)cz * g.dim[lev][1] + cy) * g.dim[lev][0] + cx;
-        const unsigned m = g.mask[lev][ci];
-        ICPB_COUNT(nodes);
-        if (!m) continue;
-        const float hc = (float)(1u << (lev - 1));
-        const unsigned near = (ux >= (float)(2 * cx + 1) * hc ? 1u : 0u) | (uy >= (float)(2 * cy + 1) * hc ? 2u : 0u) |
-                              (uz >= (float)(2 * cz + 1) * hc ? 4u : 0u);
-        if (lev == 1) {
-            for (int k = 0; k < 8; ++k) {
-                const unsigned ch = near ^ ((ORD >> (4 * k)) & 7u);
-                if (!((m >> ch) & 1u)) continue;
-                const int x = 2 * cx + (int)(ch & 1u), y = 2 * cy + (int)((ch >> 1) & 1u),
-                          z = 2 * cz + (int)((ch >> 2) & 1u);
-                if (icpb_cell_mindist2f(0, x, y, z, ux, uy, uz, slack) > boundf) continue;
-                icpb_scan_cell(g, x, y, z, qx, qy, qz, ux, uy, uz, slack, dbox2s, inv_h2, bd2, bidx, bpos, boundf, candf);
+    for (;;) {
+        int have = 0, lx = 0, ly = 0, lz = 0;
+        unsigned lmask = 0;
+        while (sp > 0) {
+            const unsigned long long e = stack[--sp];
+            ICPB_COUNT(pops);
+            const int lev = (int)(e >> 60);
+            const int cx = (int)(e & 0xFFFFFu), cy = (int)((e >> 20) & 0xFFFFFu), cz = (int)((e >> 40) & 0xFFFFFu);
+            if (icpb_cell_mindist2f(lev, cx, cy, cz, ux, uy, uz, slack) > boundf) continue;
+            if (lev == 0) {
+                have = 1;
+                lx = cx, ly = cy, lz = cz;
+                break;
             }
-        } else {
+            const size_t ci = ((size_t)cz * g.dim[lev][1] + cy) * g.dim[lev][0] + cx;
+            const unsigned m = g.mask[lev][ci];
+            ICPB_COUNT(nodes);
+            if (!m) continue;
+            if (lev == 1) {
+                have = 2;
+                lmask = m;
+                lx = cx, ly = cy, lz = cz;
+                break;
+            }
+            const float hc = (float)(1u << (lev - 1));
+            const unsigned near = (ux >= (float)(2 * cx + 1) * hc ? 1u : 0u) | (uy >= (float)(2 * cy + 1) * hc ? 2u : 0u) |
+                                  (uz >= (float)(2 * cz + 1) * hc ? 4u : 0u);
             for (int k = 7; k >= 0; --k) {
                 const unsigned ch = near ^ ((ORD >> (4 * k)) & 7u);
                 if (!((m >> ch) & 1u)) continue;
@@ -299,6 +302,21 @@ ICPB_HD void icpb_nn_search(const GridView &g, double qx, double qy, double qz, 
                 if (sp < ICPB_SEARCH_STACK)
                     stack[sp++] = ((unsigned long long)(lev - 1) << 60) | ((unsigned long long)z << 40) |
                                   ((unsigned long long)y << 20) | (unsigned long long)x;
+            }
+        }
+        if (!have) break;
+        if (have == 1) {
+            icpb_scan_cell(g, lx, ly, lz, qx, qy, qz, ux, uy, uz, slack, dbox2s, inv_h2, bd2, bidx, bpos, boundf, candf);
+        } else {
+            const unsigned near = (ux >= (float)(2 * lx + 1) ? 1u : 0u) | (uy >= (float)(2 * ly + 1) ? 2u : 0u) |
+                                  (uz >= (float)(2 * lz + 1) ? 4u : 0u);
+            for (int k = 0; k < 8; ++k) {
+                const unsigned ch = near ^ ((ORD >> (4 * k)) & 7u);
+                if (!((lmask >> ch) & 1u)) continue;
+                const int x = 2 * lx + (int)(ch & 1u), y = 2 * ly + (int)((ch >> 1) & 1u),
+                          z = 2 * lz + (int)((ch >> 2) & 1u);
+                if (icpb_cell_mindist2f(0, x, y, z, ux, uy, uz, slack) > boundf) continue;
+                icpb_scan_cell(g, x, y, z, qx, qy, qz, ux, uy, uz, slack, dbox2s, inv_h2, bd2, bidx, bpos, boundf, candf);
             }
         }
     }
