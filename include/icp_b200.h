@@ -77,6 +77,11 @@ int icpb_get_option(const icpb_ctx *, const char *key, double *value);
  * maps each by T_local2global, ACCUMULATES across calls. */
 int icpb_model_add(icpb_ctx *, const double *xyz_aos, size_t n_vertices, const double T_local2global[16],
                    double density);
+/* Replaces: TrimmedKDEAN::addToModel(PointcloudEdgeAndNormalAdapter(model,density)) (icp/icp.hpp:176-198,513-521):
+ * vertices with per-vertex normals (VERTEX_NORMAL, mapped by T.linear()) and attributes (VERTEX_ATTRIBUTES, int per
+ * vertex; bit (1 << SCAN_EDGE) marks scan edges).  A model is either all edge-and-normal or all plain. */
+int icpb_model_add_ean(icpb_ctx *, const double *xyz_aos, const double *normals_aos, const int32_t *attrs,
+                       size_t n_vertices, const double T_local2global[16], double density);
 /* Replaces: Trimmed::clearModel (icp/icp.hpp:432). */
 int icpb_model_clear(icpb_ctx *);
 int icpb_model_size(const icpb_ctx *, size_t *n_points);
@@ -96,6 +101,10 @@ int icpb_model_build(icpb_ctx *, icpb_grid_info *info /* may be NULL */);
  * (setOffsetTransform, icp/icp.hpp:121-124). */
 int icpb_source_upload(icpb_ctx *, const double *xyz_aos, size_t n_vertices, const double T_local2global[16],
                        double density);
+/* The same for a PointcloudEdgeAndNormalAdapter measurement: the following aligns apply EdgeAndNormalPairFilter
+ * (icp/icp.hpp:206-221) to each nearest neighbour (needs an edge-and-normal model). */
+int icpb_source_upload_ean(icpb_ctx *, const double *xyz_aos, const double *normals_aos, const int32_t *attrs,
+                           size_t n_vertices, const double T_local2global[16], double density);
 /* One Trimmed::_align (icp/icp.hpp:453-507) on the resident source. */
 int icpb_align_resident(icpb_ctx *, const icpb_params *, icpb_result *out);
 /* upload + _align in one call: what Trimmed::align(meas, max_iter, min_mse,

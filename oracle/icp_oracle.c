@@ -27,6 +27,9 @@
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
 
 /* ------------------------------------------------------------------ */
 /* small affine algebra in Eigen's evaluation order                    */
@@ -154,6 +157,9 @@ void orc_transform_points(const double M[16], const double *xyz, size_t n, doubl
 /* ------------------------------------------------------------------ */
 struct orc_model {
     double *pt; /* 3*n, global frame, insertion order */
+    double *nrm;          /* 3*n normals in the global frame (EAN models only) */
+    unsigned char *edge;  /* n edge flags (EAN models only) */
+    int ean;
     int32_t *left, *right;
     size_t n, cap;
     int depth;
@@ -167,11 +173,14 @@ void orc_model_clear(orc_model *m)
 {
     m->n = 0;
     m->depth = 0;
+    m->ean = 0;
 }
 void orc_model_free(orc_model *m)
 {
     if (!m) return;
     free(m->pt);
+    free(m->nrm);
+    free(m->edge);
     free(m->left);
     free(m->right);
     free(m);
@@ -186,6 +195,8 @@ static void model_reserve(orc_model *m, size_t want)
     size_t nc = m->cap ? m->cap : 1024;
     while (nc < want) nc *= 2;
     m->pt = (double *)realloc(m->pt, nc * 3 * sizeof(double));
+    m->nrm = (double *)realloc(m->nrm, nc * 3 * sizeof(double));
+    m->edge = (unsigned char *)realloc(m->edge, nc);
     m->left = (int32_t *)realloc(m->left, nc * sizeof(int32_t));
     m->right = (int32_t *)realloc(m->right, nc * sizeof(int32_t));
     m->cap = nc;
@@ -229,6 +240,30 @@ void orc_model_add(orc_model *m, const double *xyz, size_t n, const double T[16]
         double p[3];
         aff_apply(&a, xyz + 3 * idx, p);
         model_insert(m, p);
+        index += 1.0 / density;
+    }
+}
+
+#define ORC_SCAN_EDGE_BIT (1 << 0x01) /* attrs[idx] & (1 << envire::Pointcloud::SCAN_EDGE), SCAN_EDGE = 0x01 */
+
+void orc_model_add_ean(orc_model *m, const double *xyz, const double *normals, const int32_t *attrs, size_t n,
+                       const double T[16], double density)
+{
+    aff a;
+    aff_from_cm(T, &a);
+    double index = 0.0;
+    m->ean = 1;
+    for (;;) {
+        const size_t idx = (size_t)index;
+        if (!(idx < n)) break;
+        double p[3];
+        aff_apply(&a, xyz + 3 * idx, p);
+        model_insert(m, p);
+        const size_t id = m->n - 1;
+        const double *v = normals + 3 * idx;
+        for (int r = 0; r < 3; r++) /* C_local2globalnew.linear() * normal */
+            m->nrm[3 * id + r] = (a.L[r][0] * v[0] + a.L[r][1] * v[1]) + a.L[r][2] * v[2];
+        m->edge[id] = (attrs[idx] & ORC_SCAN_EDGE_BIT) ? 1 : 0;
         index += 1.0 / density;
     }
 }
@@ -572,8 +607,27 @@ static void trace_push(orc_run *run, const orc_trace_row *row)
     run->trace[run->n_trace++] = *row;
 }
 
+static int align_core(const orc_model *m, const double *xyz, const double *normals, const int32_t *attrs, size_t n,
+                      const double T_l2g[16], double density, const orc_params *prm, orc_result *out, orc_run *run,
+                      int threads);
+
 int orc_align(const orc_model *m, const double *xyz, size_t n, const double T_l2g[16], double density,
               const orc_params *prm, orc_result *out, orc_run *run, int threads)
+{
+    return align_core(m, xyz, NULL, NULL, n, T_l2g, density, prm, out, run, threads);
+}
+
+int orc_align_ean(const orc_model *m, const double *xyz, const double *normals, const int32_t *attrs, size_t n,
+                  const double T_l2g[16], double density, const orc_params *prm, orc_result *out, orc_run *run,
+                  int threads)
+{
+    if (!m->ean && m->n) return -1;
+    return align_core(m, xyz, normals, attrs, n, T_l2g, density, prm, out, run, threads);
+}
+
+static int align_core(const orc_model *m, const double *xyz, const double *normals, const int32_t *attrs, size_t n,
+                      const double T_l2g[16], double density, const orc_params *prm, orc_result *out, orc_run *run,
+                      int threads)
 {
     orc_run *own = NULL;
     if (!run) run = own = orc_run_new();
@@ -585,6 +639,16 @@ int orc_align(const orc_model *m, const double *xyz, size_t n, const double T_l2
     orc_density_indices(n, density, sel, n_it);
     double *v = (double *)malloc((n_it ? n_it : 1) * 3 * sizeof(double));
     for (size_t k = 0; k < n_it; k++) memcpy(v + 3 * k, xyz + 3 * sel[k], 3 * sizeof(double));
+    double *vn = NULL;
+    unsigned char *vedge = NULL;
+    if (normals) { /* PointcloudEdgeAndNormalAdapter: normals and the SCAN_EDGE bit ride along */
+        vn = (double *)malloc((n_it ? n_it : 1) * 3 * sizeof(double));
+        vedge = (unsigned char *)malloc(n_it ? n_it : 1);
+        for (size_t k = 0; k < n_it; k++) {
+            memcpy(vn + 3 * k, normals + 3 * sel[k], 3 * sizeof(double));
+            vedge[k] = (attrs[sel[k]] & ORC_SCAN_EDGE_BIT) ? 1 : 0;
+        }
+    }
     free(sel);
     const size_t meas_size = orc_adapter_size(n, density);
 
@@ -619,6 +683,22 @@ int orc_align(const orc_model *m, const double *xyz, size_t n, const double T_l2
         double t0 = now_s();
         for (size_t k = 0; k < n_it; k++) aff_apply(&C_l2g_new, v + 3 * k, node + 3 * k);
         orc_find_pairs(m, node, n_it, res.d_box, nn_idx, nn_d, threads);
+        if (vn) { /* EdgeAndNormalPairFilter (icp/icp.hpp:206-221), applied to the nearest neighbour only */
+            for (size_t k = 0; k < n_it; k++) {
+                if (nn_idx[k] == ORC_NO_PAIR) continue;
+                const double *sn = vn + 3 * k, *mn = m->nrm + 3 * (size_t)nn_idx[k];
+                double an[3];
+                for (int r = 0; r < 3; r++)
+                    an[r] = (C_l2g_new.L[r][0] * sn[0] + C_l2g_new.L[r][1] * sn[1]) + C_l2g_new.L[r][2] * sn[2];
+                const double dot = (an[0] * mn[0] + an[1] * mn[1]) + an[2] * mn[2];
+                const int edge = vedge[k] || m->edge[nn_idx[k]];
+                const double normal_angle = acos(dot < 1.0 ? dot : 1.0); /* std::min(1.0, dot) */
+                if (!(!edge && (normal_angle < M_PI / 8.0))) {
+                    nn_idx[k] = ORC_NO_PAIR;
+                    nn_d[k] = res.d_box;
+                }
+            }
+        }
         size_t found = 0;
         for (size_t k = 0; k < n_it; k++) {
             if (nn_idx[k] == ORC_NO_PAIR) continue;
@@ -688,6 +768,8 @@ int orc_align(const orc_model *m, const double *xyz, size_t n, const double T_l2
     *out = res;
 
     free(v);
+    free(vn);
+    free(vedge);
     free(node);
     free(nn_idx);
     free(nn_d);

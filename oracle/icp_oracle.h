@@ -56,6 +56,10 @@ void orc_model_clear(orc_model *);
 /* addModel: density-stepped iteration (icp/icp.hpp:126-138), each vertex
  * mapped by T_local2global, inserted without rebalancing.  Accumulates. */
 void orc_model_add(orc_model *, const double *xyz_aos, size_t n, const double T[16], double density);
+/* FindPairsKDEAN model (icp/icp.hpp:184-193,513-515): vertices with normals (mapped by T.linear()) and the
+ * SCAN_EDGE attribute bit; a model is either all-EAN or all-plain */
+void orc_model_add_ean(orc_model *, const double *xyz_aos, const double *normals_aos, const int32_t *attrs, size_t n,
+                       const double T[16], double density);
 size_t orc_model_size(const orc_model *);
 /* copy of the stored (global-frame) model points in insertion order */
 void orc_model_points(const orc_model *, double *xyz_out);
@@ -90,6 +94,11 @@ orc_run *orc_run_new(void);
 void orc_run_free(orc_run *);
 int orc_align(const orc_model *, const double *xyz_aos, size_t n, const double T_local2global[16],
               double density, const orc_params *, orc_result *out, orc_run *run, int threads);
+/* Trimmed<PointcloudEdgeAndNormalAdapter, FindPairsKDEAN>::_align: the pair filter of icp/icp.hpp:206-221 is
+ * applied AFTER the nearest neighbour is found (a rejected source vertex gets no pair) */
+int orc_align_ean(const orc_model *, const double *xyz_aos, const double *normals_aos, const int32_t *attrs, size_t n,
+                  const double T_local2global[16], double density, const orc_params *, orc_result *out, orc_run *run,
+                  int threads);
 /* golden-section variant (icp/icp.hpp:385-401, 284-326); returns #evaluations */
 int orc_align_golden(const orc_model *, const double *xyz_aos, size_t n, const double T_local2global[16],
                      double density, size_t max_iter, double min_mse, double min_mse_diff,

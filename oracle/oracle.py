@@ -60,6 +60,9 @@ def lib():
     L.orc_model_free.argtypes = [vp]
     L.orc_model_clear.argtypes = [vp]
     L.orc_model_add.argtypes = [vp, dp, C.c_size_t, dp, C.c_double]
+    L.orc_model_add_ean.argtypes = [vp, dp, dp, C.POINTER(C.c_int32), C.c_size_t, dp, C.c_double]
+    L.orc_align_ean.argtypes = [vp, dp, dp, C.POINTER(C.c_int32), C.c_size_t, dp, C.c_double, C.POINTER(Params),
+                                C.POINTER(Result), vp, C.c_int]
     L.orc_model_size.argtypes = [vp]
     L.orc_model_size.restype = C.c_size_t
     L.orc_model_points.argtypes = [vp, dp]
@@ -224,6 +227,27 @@ class Model:
         a, ap = _d(xyz)
         t, tp = _cm(np.eye(4) if T is None else T)
         lib().orc_model_add(self._h, ap, a.shape[0], tp, density)
+
+    def add_ean(self, xyz, normals, attrs, T=None, density=1.0):
+        a, ap = _d(xyz)
+        nn, np_ = _d(normals)
+        at = np.ascontiguousarray(attrs, dtype=np.int32)
+        t, tp = _cm(np.eye(4) if T is None else T)
+        lib().orc_model_add_ean(self._h, ap, np_, at.ctypes.data_as(C.POINTER(C.c_int32)), a.shape[0], tp, density)
+
+    def align_ean(self, xyz, normals, attrs, T=None, density=1.0, max_iter=10, min_mse=1e-4, min_mse_diff=1e-5,
+                  overlap=1.0, run=None, threads=0):
+        a, ap = _d(xyz)
+        nn, np_ = _d(normals)
+        at = np.ascontiguousarray(attrs, dtype=np.int32)
+        t, tp = _cm(np.eye(4) if T is None else T)
+        prm = Params(max_iter, min_mse, min_mse_diff, overlap)
+        res = Result()
+        rc = lib().orc_align_ean(self._h, ap, np_, at.ctypes.data_as(C.POINTER(C.c_int32)), a.shape[0], tp, density,
+                                 C.byref(prm), C.byref(res), run._h if run is not None else None, threads)
+        if rc != 0:
+            raise RuntimeError("model has no normals/attributes")
+        return res
 
     def clear(self):
         lib().orc_model_clear(self._h)

@@ -30,6 +30,10 @@ def lib():
                                 dp, C.c_size_t, sp]
         L.ref_align_golden.argtypes = [vp, dp, C.c_size_t, dp, C.c_double, C.c_size_t, C.c_double, C.c_double,
                                        C.c_double, C.c_double, C.c_double, dp, dp, C.c_size_t, sp]
+        ip = C.POINTER(C.c_int32)
+        L.ref_add_model_ean.argtypes = [vp, dp, dp, ip, C.c_size_t, dp, C.c_double]
+        L.ref_align_ean.argtypes = [vp, dp, dp, ip, C.c_size_t, dp, C.c_double, C.c_size_t, C.c_double, C.c_double,
+                                    C.c_double, dp, dp, C.c_size_t, sp]
         L.ref_pairs.argtypes = [dp, dp, dp, C.c_size_t, C.c_size_t, dp, dp, dp]
         L.ref_pairs.restype = C.c_long
         _lib = L
@@ -68,6 +72,24 @@ class Ref:
 
     def clear_model(self):
         lib().ref_clear_model(self._h)
+
+    def add_to_model_ean(self, xyz, normals, attrs, T=None, density=1.0):
+        a, ap = _d(xyz)
+        n_, np_ = _d(normals)
+        at = np.ascontiguousarray(attrs, dtype=np.int32)
+        t, tp = _cm(T)
+        lib().ref_add_model_ean(self._h, ap, np_, at.ctypes.data_as(C.POINTER(C.c_int32)), a.shape[0], tp, density)
+
+    def align_ean(self, xyz, normals, attrs, T=None, density=1.0, max_iter=10, min_mse=1e-4, min_mse_diff=1e-5, overlap=1.0):
+        a, ap = _d(xyz)
+        n_, np_ = _d(normals)
+        at = np.ascontiguousarray(attrs, dtype=np.int32)
+        t, tp = _cm(T)
+        out, pd, n = np.zeros(32), np.zeros(max(len(a), 1)), C.c_size_t()
+        lib().ref_align_ean(self._h, ap, np_, at.ctypes.data_as(C.POINTER(C.c_int32)), a.shape[0], tp, density, max_iter,
+                            min_mse, min_mse_diff, overlap, out.ctypes.data_as(C.POINTER(C.c_double)),
+                            pd.ctypes.data_as(C.POINTER(C.c_double)), len(pd), C.byref(n))
+        return _unpack(out, pd, n.value)
 
     def align(self, xyz, T=None, density=1.0, max_iter=10, min_mse=1e-4, min_mse_diff=1e-5, overlap=1.0):
         a, ap = _d(xyz)

@@ -15,6 +15,7 @@ namespace {
 struct Ref {
     envire::Environment env;
     envire::icp::TrimmedKD icp;
+    envire::icp::TrimmedKDEAN icp_ean;
 };
 envire::Pointcloud *make_cloud(Ref *r, const double *xyz, size_t n, const double T[16])
 {
@@ -29,6 +30,29 @@ envire::Pointcloud *make_cloud(Ref *r, const double *xyz, size_t n, const double
     pc->vertices.reserve(n);
     for (size_t i = 0; i < n; ++i) pc->vertices.push_back(Eigen::Vector3d(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]));
     return pc;
+}
+void add_ean_data(envire::Pointcloud *pc, const double *normals, const int *attrs, size_t n)
+{
+    std::vector<Eigen::Vector3d> &nv = pc->getVertexData<Eigen::Vector3d>(envire::Pointcloud::VERTEX_NORMAL);
+    std::vector<envire::Pointcloud::vertex_attr> &av = pc->getVertexData<envire::Pointcloud::vertex_attr>(envire::Pointcloud::VERTEX_ATTRIBUTES);
+    for (size_t i = 0; i < n; ++i) {
+        nv.push_back(Eigen::Vector3d(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]));
+        av.push_back(attrs[i]);
+    }
+}
+template <class ICP> void fill_out_t(ICP &icp, envire::Pointcloud *pc, double *out, double *pd, size_t cap, size_t *n_pd)
+{
+    const Eigen::Matrix4d M = pc->getFrameNode()->getTransform().matrix();
+    for (int c = 0; c < 4; ++c)
+        for (int rr = 0; rr < 4; ++rr) out[c * 4 + rr] = M(rr, c);
+    out[16] = (double)icp.getNumIterations();
+    out[17] = (double)icp.getPairs();
+    out[18] = icp.getMeanSquareError();
+    out[19] = icp.getMeanSquareErrorDiff();
+    out[20] = icp.getOverlap();
+    const std::vector<double> v = icp.getPairsDistance();
+    *n_pd = v.size();
+    for (size_t i = 0; i < v.size() && i < cap; ++i) pd[i] = v[i];
 }
 void fill_out(Ref *r, envire::Pointcloud *pc, double *out, double *pd, size_t cap, size_t *n_pd)
 {
@@ -73,6 +97,25 @@ void ref_align_golden(void *h, const double *xyz, size_t n, const double T[16], 
     envire::Pointcloud *pc = make_cloud(r, xyz, n, T);
     r->icp.align(envire::icp::PointcloudAdapter(pc, density), max_iter, min_mse, min_mse_diff, alpha, beta, eps);
     fill_out(r, pc, out, pd, cap, n_pd);
+}
+// the same through TrimmedKDEAN = Trimmed<PointcloudEdgeAndNormalAdapter, FindPairsKDEAN> (icp/icp.hpp:513-521)
+void ref_add_model_ean(void *h, const double *xyz, const double *normals, const int *attrs, size_t n, const double T[16],
+                       double density)
+{
+    Ref *r = static_cast<Ref *>(h);
+    envire::Pointcloud *pc = make_cloud(r, xyz, n, T);
+    add_ean_data(pc, normals, attrs, n);
+    r->icp_ean.addToModel(envire::icp::PointcloudEdgeAndNormalAdapter(pc, density));
+}
+void ref_align_ean(void *h, const double *xyz, const double *normals, const int *attrs, size_t n, const double T[16],
+                   double density, size_t max_iter, double min_mse, double min_mse_diff, double overlap, double *out,
+                   double *pd, size_t cap, size_t *n_pd)
+{
+    Ref *r = static_cast<Ref *>(h);
+    envire::Pointcloud *pc = make_cloud(r, xyz, n, T);
+    add_ean_data(pc, normals, attrs, n);
+    r->icp_ean.align(envire::icp::PointcloudEdgeAndNormalAdapter(pc, density), max_iter, min_mse, min_mse_diff, overlap);
+    fill_out_t(r->icp_ean, pc, out, pd, cap, n_pd);
 }
 // Pairs::add x n, trim(n_po), getTransform() on caller-supplied pairs.  Returns the kept count (or -1 on throw).
 long ref_pairs(const double *x, const double *p, const double *d, size_t n, size_t n_po, double *T16, double *mse,

@@ -23,7 +23,7 @@ OK, ERR_CUDA, ERR_ARG, ERR_NO_MODEL, ERR_NO_SOURCE, ERR_NCCL, ERR_CAPACITY, ERR_
 # every symbol include/icp_b200.h declares
 SYMBOLS = [
     "icpb_create", "icpb_destroy", "icpb_strerror", "icpb_last_error", "icpb_version", "icpb_set_option",
-    "icpb_get_option", "icpb_model_add", "icpb_model_clear", "icpb_model_size", "icpb_model_build",
+    "icpb_get_option", "icpb_model_add", "icpb_model_add_ean", "icpb_source_upload_ean", "icpb_model_clear", "icpb_model_size", "icpb_model_build",
     "icpb_source_upload", "icpb_align_resident", "icpb_align", "icpb_pairs_distance", "icpb_debug_pairs",
     "icpb_trace", "icpb_last_timing", "icpb_iteration_times", "icpb_find_pairs", "icpb_trim", "icpb_nccl_unique_id", "icpb_comm_init",
     "icpb_source_upload_shard",
@@ -85,6 +85,8 @@ def load_library():
     L.icpb_set_option.argtypes = [vp, C.c_char_p, C.c_double]
     L.icpb_get_option.argtypes = [vp, C.c_char_p, dp]
     L.icpb_model_add.argtypes = [vp, dp, C.c_size_t, dp, C.c_double]
+    L.icpb_model_add_ean.argtypes = [vp, dp, dp, C.POINTER(C.c_int32), C.c_size_t, dp, C.c_double]
+    L.icpb_source_upload_ean.argtypes = [vp, dp, dp, C.POINTER(C.c_int32), C.c_size_t, dp, C.c_double]
     L.icpb_model_clear.argtypes = [vp]
     L.icpb_model_size.argtypes = [vp, sp]
     L.icpb_model_build.argtypes = [vp, C.POINTER(GridInfo)]
@@ -160,6 +162,22 @@ class Icp:
         a, ap = _d(xyz)
         t, tp = _cm(T)
         self._ck(self._L.icpb_model_add(self._h, ap, a.shape[0], tp, density))
+
+    def add_to_model_ean(self, xyz, normals, attrs, T=None, density=1.0):
+        a, ap = _d(xyz)
+        nn, np_ = _d(normals)
+        at = np.ascontiguousarray(attrs, dtype=np.int32)
+        t, tp = _cm(T)
+        self._ck(self._L.icpb_model_add_ean(self._h, ap, np_, at.ctypes.data_as(C.POINTER(C.c_int32)), a.shape[0], tp,
+                                            density))
+
+    def upload_source_ean(self, xyz, normals, attrs, T=None, density=1.0):
+        a, ap = _d(xyz)
+        nn, np_ = _d(normals)
+        at = np.ascontiguousarray(attrs, dtype=np.int32)
+        t, tp = _cm(T)
+        self._ck(self._L.icpb_source_upload_ean(self._h, ap, np_, at.ctypes.data_as(C.POINTER(C.c_int32)), a.shape[0],
+                                                tp, density))
 
     def clear_model(self):
         self._ck(self._L.icpb_model_clear(self._h))

@@ -145,6 +145,21 @@ const double *density_gather(const double *xyz, size_t n, double density, std::v
     *n_out = tmp.size() / 3;
     return tmp.data();
 }
+// the same visiting order applied to a parallel per-vertex array of `width` items
+template <typename T>
+const T *density_gather_t(const T *v, size_t n, int width, double density, std::vector<T> &tmp)
+{
+    if (density == 1.0) return v;
+    tmp.clear();
+    double index = 0.0;
+    for (;;) {
+        const size_t idx = (size_t)index;
+        if (!(idx < n)) break;
+        for (int k = 0; k < width; ++k) tmp.push_back(v[width * idx + k]);
+        index += 1.0 / density;
+    }
+    return tmp.data();
+}
 constexpr int MAX_DIM = 2048; // cells per axis (bounds the pyramid depth and the search stack)
 constexpr int EVENT_ITERS = 512;
 constexpr int FLAG_RING = 4096;
@@ -158,7 +173,11 @@ struct icpb_ctx {
     double opt_cell_size = 0.0, opt_target = 4.0, opt_max_cells = 64.0 * 1024 * 1024, opt_run_ahead = 2.0,
            opt_warm = 1.0, opt_profile = 1.0, opt_sort = 1.0;
     // model
-    DevBuf<double> model_raw;
+    DevBuf<double> model_raw, model_nrm;
+    DevBuf<uint8_t> model_edge;
+    DevBuf<NPoint> npts;
+    bool model_ean = false;
+    DevBuf<int> stage_i;
     size_t model_n = 0;
     bool grid_dirty = true;
     DevBuf<MPoint> pts;
@@ -171,7 +190,9 @@ struct icpb_ctx {
     icpb_grid_info ginfo;
     // source
     DevBuf<double> stage;
-    DevBuf<double> sx, sy, sz;
+    DevBuf<double> sx, sy, sz, snx, sny, snz;
+    DevBuf<uint8_t> sedge, sedge_tmp;
+    bool src_ean = false;
     size_t src_n = 0, adapter_size = 0;
     double Cl2g[12];
     bool have_source = false;
@@ -299,6 +320,15 @@ void icpb_destroy(icpb_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
     ctx->model_raw.release();
+    ctx->model_nrm.release();
+    ctx->model_edge.release();
+    ctx->npts.release();
+    ctx->stage_i.release();
+    ctx->snx.release();
+    ctx->sny.release();
+    ctx->snz.release();
+    ctx->sedge.release();
+    ctx->sedge_tmp.release();
     ctx->pts.release();
     ctx->ptsf.release();
     ctx->cell_start.release();
@@ -370,10 +400,14 @@ int icpb_get_option(const icpb_ctx *ctx, const char *key, double *value)
 // ---------------------------------------------------------------------------
 // model
 // ---------------------------------------------------------------------------
-int icpb_model_add(icpb_ctx *ctx, const double *xyz, size_t n, const double T[16], double density)
+static int model_add(icpb_ctx *ctx, const double *xyz, const double *normals, const int32_t *attrs, size_t n,
+                     const double T[16], double density)
 {
     if (!ctx || (!xyz && n) || !T || !(density > 0.0)) return ICPB_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
+    const bool ean = normals != nullptr;
+    if (ean && !attrs) return ICPB_ERR_ARG;
+    if (ctx->model_n > 0 && ean != ctx->model_ean) return ICPB_ERR_ARG; // all plain or all edge-and-normal
     std::vector<double> tmp;
     size_t m = 0;
     const double *src = density_gather(xyz, n, density, tmp, &m);
@@ -388,15 +422,43 @@ int icpb_model_add(icpb_ctx *ctx, const double *xyz, size_t n, const double T[16
                                                                        ctx->model_raw.p + 3 * ctx->model_n);
     CKL();
     CK(cudaStreamSynchronize(ctx->stream)); // tmp / caller buffer may go away
+    if (ean) {
+        std::vector<double> tn;
+        std::vector<int32_t> ta;
+        const double *nsrc = density_gather_t(normals, n, 3, density, tn);
+        const int32_t *asrc = density_gather_t(attrs, n, 1, density, ta);
+        CK(ctx->stage_i.ensure(m));
+        CK(ctx->model_nrm.ensure_keep(3 * (ctx->model_n + m), 3 * ctx->model_n, ctx->stream));
+        CK(ctx->model_edge.ensure_keep(ctx->model_n + m, ctx->model_n, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->stage.p, nsrc, 3 * m * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->stage_i.p, asrc, m * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        rotate_append_kernel<<<grid_for(m, 256), 256, 0, ctx->stream>>>(ctx->stage.p, m, A, ctx->model_nrm.p + 3 * ctx->model_n);
+        edge_flags_kernel<<<grid_for(m, 256), 256, 0, ctx->stream>>>(ctx->stage_i.p, m, ctx->model_edge.p + ctx->model_n);
+        CKL();
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->model_ean = ean;
     ctx->model_n += m;
     ctx->grid_dirty = true;
     return ICPB_OK;
+}
+
+int icpb_model_add(icpb_ctx *ctx, const double *xyz, size_t n, const double T[16], double density)
+{
+    return model_add(ctx, xyz, nullptr, nullptr, n, T, density);
+}
+int icpb_model_add_ean(icpb_ctx *ctx, const double *xyz, const double *normals, const int32_t *attrs, size_t n,
+                       const double T[16], double density)
+{
+    if (!normals || !attrs) return ICPB_ERR_ARG;
+    return model_add(ctx, xyz, normals, attrs, n, T, density);
 }
 
 int icpb_model_clear(icpb_ctx *ctx)
 {
     if (!ctx) return ICPB_ERR_ARG;
     ctx->model_n = 0;
+    ctx->model_ean = false;
     ctx->grid_dirty = true;
     ctx->gv.n = 0;
     return ICPB_OK;
@@ -528,6 +590,11 @@ static int build_grid(icpb_ctx *ctx)
     exclusive_scan_u32(ctx->cell_start.p, ctx->cell_start.p, ncell + 1, ctx->cell_start.p + ncell + 1, s,
                        &ctx->launches);
     CKL();
+    if (ctx->model_ean) {
+        CK(ctx->npts.ensure(n));
+        gather_ean_kernel<<<grid_for(n, 256), 256, 0, s>>>(ctx->model_nrm.p, ctx->model_edge.p, perm, (uint32_t)n, ctx->npts.p);
+        CKL();
+    }
 
     // pyramid of occupancy masks
     GridView &g = ctx->gv;
@@ -665,6 +732,7 @@ static int upload_points(icpb_ctx *ctx, const double *src, size_t m)
     ctx->timing.upload_ms = ms;
     ctx->src_n = m;
     ctx->have_source = true;
+    ctx->src_ean = false;
     ctx->last_valid = false;
     return ICPB_OK;
 }
@@ -679,6 +747,39 @@ int icpb_source_upload(icpb_ctx *ctx, const double *xyz, size_t n, const double 
     cm_to_aff12(T, ctx->Cl2g);
     ctx->adapter_size = (size_t)((double)n * density); // PointcloudAdapter::size() (icp/icp.hpp:143-146)
     return upload_points(ctx, src, m);
+}
+
+int icpb_source_upload_ean(icpb_ctx *ctx, const double *xyz, const double *normals, const int32_t *attrs, size_t n,
+                           const double T[16], double density)
+{
+    if (!normals || !attrs) return ICPB_ERR_ARG;
+    int rc = icpb_source_upload(ctx, xyz, n, T, density);
+    if (rc != ICPB_OK) return rc;
+    const size_t m = ctx->src_n;
+    cudaStream_t s = ctx->stream;
+    std::vector<double> tn;
+    std::vector<int32_t> ta;
+    const double *nsrc = density_gather_t(normals, n, 3, density, tn);
+    const int32_t *asrc = density_gather_t(attrs, n, 1, density, ta);
+    CK(ctx->snx.ensure(std::max<size_t>(m, 1)));
+    CK(ctx->sny.ensure(std::max<size_t>(m, 1)));
+    CK(ctx->snz.ensure(std::max<size_t>(m, 1)));
+    CK(ctx->sedge.ensure(std::max<size_t>(m, 1)));
+    CK(ctx->sedge_tmp.ensure(std::max<size_t>(m, 1)));
+    CK(ctx->stage_i.ensure(std::max<size_t>(m, 1)));
+    if (m) { // same (Morton) order as the vertices: src_perm maps slot -> visiting index
+        CK(cudaMemcpyAsync(ctx->stage.p, nsrc, 3 * m * sizeof(double), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->stage_i.p, asrc, m * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        gather_soa_kernel<<<grid_for(m, 256), 256, 0, s>>>(ctx->stage.p, ctx->src_perm.p, (uint32_t)m, ctx->snx.p, ctx->sny.p,
+                                                          ctx->snz.p);
+        edge_flags_kernel<<<grid_for(m, 256), 256, 0, s>>>(ctx->stage_i.p, m, ctx->sedge_tmp.p);
+        gather_u8_kernel<<<grid_for(m, 256), 256, 0, s>>>(ctx->sedge_tmp.p, ctx->src_perm.p, (uint32_t)m, ctx->sedge.p);
+        CKL();
+        CK(cudaStreamSynchronize(s));
+        ctx->launches += 3;
+    }
+    ctx->src_ean = true;
+    return ICPB_OK;
 }
 
 int icpb_source_upload_shard(icpb_ctx *ctx, const double *xyz, size_t n_local, size_t adapter_size_global,
@@ -775,8 +876,19 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
         int rc = build_grid(ctx);
         if (rc != ICPB_OK) return rc;
     }
+    if (ctx->src_ean && ctx->model_n > 0 && !ctx->model_ean) return ICPB_ERR_ARG; // filter needs model normals
     cudaStream_t s = ctx->stream;
     const uint32_t n = (uint32_t)ctx->src_n;
+    EanView ean;
+    memset(&ean, 0, sizeof(ean));
+    if (ctx->src_ean && ctx->model_n > 0) {
+        ean.mn = ctx->npts.p;
+        ean.snx = ctx->snx.p;
+        ean.sny = ctx->sny.p;
+        ean.snz = ctx->snz.p;
+        ean.sedge = ctx->sedge.p;
+        ean.on = 1;
+    }
     // n_po = measurement.size() * overlap  (icp/icp.hpp:472), size() from icp/icp.hpp:143-146
     const size_t n_po = (size_t)((double)ctx->adapter_size * prm->overlap);
     const size_t max_iter = prm->max_iter;
@@ -820,9 +932,14 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
         const bool timed = profile && it < (size_t)EVENT_ITERS;
         cudaEvent_t *ev = timed ? &ctx->events[it * 4] : nullptr;
         if (timed) CK(cudaEventRecord(ev[0], s));
-        search_kernel<<<grid_for(std::max<uint32_t>(n, 1), SEARCH_THREADS), SEARCH_THREADS, 0, s>>>(
-            ctx->gv, ctx->sx.p, ctx->sy.p, ctx->sz.p, n, ctx->d_state, ctx->nn_pos.p, ctx->nn_d.p,
-            ctx->opt_warm != 0.0 ? 1 : 0);
+        if (ean.on)
+            search_kernel<true><<<grid_for(std::max<uint32_t>(n, 1), SEARCH_THREADS), SEARCH_THREADS, 0, s>>>(
+                ctx->gv, ctx->sx.p, ctx->sy.p, ctx->sz.p, n, ctx->d_state, ctx->nn_pos.p, ctx->nn_d.p,
+                ctx->opt_warm != 0.0 ? 1 : 0, ean);
+        else
+            search_kernel<false><<<grid_for(std::max<uint32_t>(n, 1), SEARCH_THREADS), SEARCH_THREADS, 0, s>>>(
+                ctx->gv, ctx->sx.p, ctx->sy.p, ctx->sz.p, n, ctx->d_state, ctx->nn_pos.p, ctx->nn_d.p,
+                ctx->opt_warm != 0.0 ? 1 : 0, ean);
         CKL();
         ++ctx->launches;
         if (timed) CK(cudaEventRecord(ev[1], s));

@@ -33,6 +33,55 @@ __global__ void transform_append_kernel(const double *__restrict__ in, size_t n,
     out[3 * i + 2] = pz;
 }
 
+// n = L * v  (normals ride with the vertices: PointcloudEdgeAndNormalAdapter::next, icp/icp.hpp:184-193)
+__global__ void rotate_append_kernel(const double *__restrict__ in, size_t n, Aff12 T, double *__restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double vx = in[3 * i], vy = in[3 * i + 1], vz = in[3 * i + 2];
+    out[3 * i] = (T.a[0] * vx + T.a[1] * vy) + T.a[2] * vz;
+    out[3 * i + 1] = (T.a[4] * vx + T.a[5] * vy) + T.a[6] * vz;
+    out[3 * i + 2] = (T.a[8] * vx + T.a[9] * vy) + T.a[10] * vz;
+}
+// SCAN_EDGE bit of the vertex attributes: attrs[idx] & (1 << envire::Pointcloud::SCAN_EDGE), SCAN_EDGE = 0x01
+__global__ void edge_flags_kernel(const int *__restrict__ attrs, size_t n, uint8_t *__restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (attrs[i] & (1 << 0x01)) ? 1 : 0;
+}
+
+// model normal + edge flag in the sorted order of pts[] (FindPairsKDEAN nodes, icp/icp.hpp:91-97)
+struct __align__(32) NPoint {
+    double nx, ny, nz;
+    unsigned long long edge;
+};
+// the edge/normal pair filter inputs of one align (all null/0 for the plain TrimmedKD path)
+struct EanView {
+    const NPoint *mn;                // model, sorted like GridView::pts
+    const double *snx, *sny, *snz;   // source normals (local frame), in the order of sx/sy/sz
+    const uint8_t *sedge;
+    int on;
+};
+__global__ void gather_ean_kernel(const double *__restrict__ nrm, const uint8_t *__restrict__ edge,
+                                  const uint32_t *__restrict__ perm, uint32_t n, NPoint *__restrict__ out)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const size_t s = perm[j];
+    NPoint p;
+    p.nx = nrm[3 * s];
+    p.ny = nrm[3 * s + 1];
+    p.nz = nrm[3 * s + 2];
+    p.edge = edge[s];
+    out[j] = p;
+}
+__global__ void gather_u8_kernel(const uint8_t *__restrict__ in, const uint32_t *__restrict__ perm, uint32_t n,
+                                 uint8_t *__restrict__ out)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) out[j] = in[perm[j]];
+}
+
 // AoS double[n][3] -> SoA x[], y[], z[] (coalesced loads for the search kernel)
 __global__ void aos_to_soa_kernel(const double *__restrict__ in, size_t n, double *__restrict__ x,
                                   double *__restrict__ y, double *__restrict__ z)
@@ -167,10 +216,11 @@ __global__ void mask_levelN_kernel(const uint8_t *__restrict__ below, int nx, in
 // ---------------------------------------------------------------------------
 constexpr int SEARCH_THREADS = 128;
 
+template <bool EAN>
 __global__ void __launch_bounds__(SEARCH_THREADS)
     search_kernel(const GridView g, const double *__restrict__ sx, const double *__restrict__ sy,
                   const double *__restrict__ sz, uint32_t n, IcpState *__restrict__ st, uint32_t *__restrict__ nn_pos,
-                  double *__restrict__ nn_d, int use_warm)
+                  double *__restrict__ nn_d, int use_warm, const EanView ean)
 {
     if (st->done) return;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -186,7 +236,20 @@ __global__ void __launch_bounds__(SEARCH_THREADS)
         int lvl;
         icpb_nn_search(g, qx, qy, qz, dbox2s, warm, pos, d2, lvl);
         const double d = sqrt(d2);
-        const bool ok = (pos != ICPB_NONE) && (d <= d_box); // inclusive ball (find_nearest(val, max))
+        bool ok = (pos != ICPB_NONE) && (d <= d_box); // inclusive ball (find_nearest(val, max))
+        if (EAN && ok) {
+            // EdgeAndNormalPairFilter (icp/icp.hpp:206-221) on the nearest neighbour: neither vertex on a scan edge,
+            // normals (source normal mapped by C_local2globalnew.linear()) less than pi/8 apart
+            const double ax = ean.snx[i], ay = ean.sny[i], az = ean.snz[i];
+            const double bx = (st->M[0] * ax + st->M[1] * ay) + st->M[2] * az;
+            const double by = (st->M[4] * ax + st->M[5] * ay) + st->M[6] * az;
+            const double bz = (st->M[8] * ax + st->M[9] * ay) + st->M[10] * az;
+            const NPoint mn = ean.mn[pos];
+            const double dot = (bx * mn.nx + by * mn.ny) + bz * mn.nz;
+            const bool edge = ean.sedge[i] || mn.edge;
+            const double normal_angle = acos(fmin(1.0, dot));
+            ok = !edge && (normal_angle < 3.14159265358979323846 / 8.0);
+        }
         nn_pos[i] = ok ? pos : ICPB_NONE;
         nn_d[i] = ok ? d : icpb_inf();
         found = ok ? 1u : 0u;

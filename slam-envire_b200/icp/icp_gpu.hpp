@@ -80,6 +80,46 @@ protected:
     double density_;
 };
 
+/** Adapter with per-vertex normals and scan-edge attributes (role of PointcloudEdgeAndNormalAdapter,
+ * icp/icp.hpp:173-198).  Passing it to TrimmedGPU slices it to the plain adapter, exactly as passing the reference's
+ * adapter to TrimmedKD does (test/unit/icp.cpp:155); TrimmedGPUEAN applies the pair filter. */
+class PointcloudEdgeAndNormalAdapter : public PointcloudAdapter {
+public:
+    PointcloudEdgeAndNormalAdapter(envire::Pointcloud *cloud, double density) : PointcloudAdapter(cloud, density)
+    {
+        attrs_ = &cloud->getVertexData<envire::Pointcloud::vertex_attr>(envire::Pointcloud::VERTEX_ATTRIBUTES);
+        normals_ = &cloud->getVertexData<Eigen::Vector3d>(envire::Pointcloud::VERTEX_NORMAL);
+        if (attrs_->size() != cloud->vertices.size() || normals_->size() != cloud->vertices.size())
+            throw std::runtime_error("PointcloudEdgeAndNormalAdapter: normals / attributes do not match the vertices");
+    }
+    const double *normalData() const { return normals_->empty() ? 0 : (*normals_)[0].data(); }
+    const int32_t *attrData() const { return attrs_->empty() ? 0 : reinterpret_cast<const int32_t *>(attrs_->data()); }
+
+private:
+    std::vector<Eigen::Vector3d> *normals_;
+    std::vector<envire::Pointcloud::vertex_attr> *attrs_;
+};
+
+namespace detail {
+// how an adapter type reaches the device: plain vertices, or vertices + normals + attributes
+inline int modelAdd(icpb_ctx *c, const PointcloudAdapter &a, const double T[16])
+{
+    return icpb_model_add(c, a.vertexData(), a.vertexCount(), T, a.density());
+}
+inline int modelAdd(icpb_ctx *c, const PointcloudEdgeAndNormalAdapter &a, const double T[16])
+{
+    return icpb_model_add_ean(c, a.vertexData(), a.normalData(), a.attrData(), a.vertexCount(), T, a.density());
+}
+inline int sourceUpload(icpb_ctx *c, const PointcloudAdapter &a, const double T[16])
+{
+    return icpb_source_upload(c, a.vertexData(), a.vertexCount(), T, a.density());
+}
+inline int sourceUpload(icpb_ctx *c, const PointcloudEdgeAndNormalAdapter &a, const double T[16])
+{
+    return icpb_source_upload_ean(c, a.vertexData(), a.normalData(), a.attrData(), a.vertexCount(), T, a.density());
+}
+} // namespace detail
+
 /** Golden-section minimiser used by the overlap search (role of GoldenBracket, icp/icp.hpp:266-327): same bracket
  * rule, same constant R = 0.6180339, same termination test, so the sequence of probed overlaps is identical. */
 template <class T> struct GoldenSection {
@@ -105,7 +145,8 @@ template <class T> struct GoldenSection {
     }
 };
 
-class TrimmedGPU {
+/** Trimmed<_Adapter, ...> over the device path; _Adapter selects plain (TrimmedKD) or edge-and-normal (TrimmedKDEAN) pairing */
+template <class _Adapter> class TrimmedGPUT {
     struct Result {
         Eigen::Affine3d C_global2globalnew;
         size_t iter, pairs;
@@ -117,7 +158,7 @@ class TrimmedGPU {
     };
 
 public:
-    explicit TrimmedGPU(int device = 0) : ctx_(0)
+    explicit TrimmedGPUT(int device = 0) : ctx_(0)
     {
         const int rc = icpb_create(&ctx_, device);
         if (rc != ICPB_OK) {
@@ -126,12 +167,12 @@ public:
             throw std::runtime_error(msg);
         }
     }
-    ~TrimmedGPU() { if (ctx_) icpb_destroy(ctx_); }
-    TrimmedGPU(const TrimmedGPU &) = delete;
-    TrimmedGPU &operator=(const TrimmedGPU &) = delete;
+    ~TrimmedGPUT() { if (ctx_) icpb_destroy(ctx_); }
+    TrimmedGPUT(const TrimmedGPUT &) = delete;
+    TrimmedGPUT &operator=(const TrimmedGPUT &) = delete;
 
     /** golden-section search for the overlap in [alpha, beta] (icp/icp.hpp:385-401) */
-    void align(PointcloudAdapter measurement, size_t max_iter, double min_mse, double min_mse_diff, double alpha, double beta, double eps)
+    void align(_Adapter measurement, size_t max_iter, double min_mse, double min_mse_diff, double alpha, double beta, double eps)
     {
         upload(measurement); // the vertices do not change between probes: upload once, every probe restarts from identity
         std::function<Result(double)> eval = [&](double overlap) { return alignResident(max_iter, min_mse, min_mse_diff, overlap, true); };
@@ -139,17 +180,17 @@ public:
         measurement.applyTransform(minResult_.C_global2globalnew);
     }
     /** fixed overlap (icp/icp.hpp:413-418) */
-    void align(PointcloudAdapter measurement, size_t max_iter, double min_mse, double min_mse_diff, double overlap)
+    void align(_Adapter measurement, size_t max_iter, double min_mse, double min_mse_diff, double overlap)
     {
         upload(measurement);
         minResult_ = alignResident(max_iter, min_mse, min_mse_diff, overlap, false);
         measurement.applyTransform(minResult_.C_global2globalnew);
     }
-    void addToModel(PointcloudAdapter model)
+    void addToModel(_Adapter model)
     {
         double T[16];
         toColMajor(model.local2global(), T);
-        check(icpb_model_add(ctx_, model.vertexData(), model.vertexCount(), T, model.density()));
+        check(detail::modelAdd(ctx_, model, T));
     }
     void clearModel() { check(icpb_model_clear(ctx_)); }
 
@@ -184,11 +225,11 @@ private:
         for (int c = 0; c < 4; ++c)
             for (int r = 0; r < 4; ++r) T[c * 4 + r] = m(r, c);
     }
-    void upload(const PointcloudAdapter &meas)
+    void upload(const _Adapter &meas)
     {
         double T[16];
         toColMajor(meas.local2global(), T);
-        check(icpb_source_upload(ctx_, meas.vertexData(), meas.vertexCount(), T, meas.density()));
+        check(detail::sourceUpload(ctx_, meas, T));
     }
     Result alignResident(size_t max_iter, double min_mse, double min_mse_diff, double overlap, bool eager_pairs)
     {
@@ -226,9 +267,13 @@ private:
     }
 };
 
+typedef TrimmedGPUT<PointcloudAdapter> TrimmedGPU;                   // counterpart of TrimmedKD    (icp/icp.hpp:522)
+typedef TrimmedGPUT<PointcloudEdgeAndNormalAdapter> TrimmedGPUEAN;   // counterpart of TrimmedKDEAN (icp/icp.hpp:521)
+
 #ifdef ICP_B200_REPLACE_TRIMMEDKD
 /** drop-in: existing callers of envire::icp::TrimmedKD (icp/icpLocalization.hpp, viz/enview/ICPHandler) pick up the GPU path */
 typedef TrimmedGPU TrimmedKD;
+typedef TrimmedGPUEAN TrimmedKDEAN;
 #endif
 
 } // namespace icp

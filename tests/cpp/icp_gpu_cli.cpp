@@ -52,6 +52,43 @@ int main(int argc, char **argv)
     fm2->setTransform(Eigen::Affine3d(Ts));
     const size_t modified_before = env->modifiedCount();
 
+    if (!strcmp(argv[20], "ean_sine")) {
+        // the reference's setSineWave fixture WITH normals and scan-edge attributes, through TrimmedGPUEAN
+        // (what the commented-out icp_test1 of test/unit/icp.cpp:132-145 drives through TrimmedKDEAN)
+        envire::Pointcloud *pcs[2] = {mesh, mesh2};
+        for (int k = 0; k < 2; ++k) {
+            envire::Pointcloud *pc = pcs[k];
+            pc->vertices.clear();
+            std::vector<envire::Pointcloud::vertex_attr> &attr = pc->getVertexData<envire::Pointcloud::vertex_attr>(envire::Pointcloud::VERTEX_ATTRIBUTES);
+            std::vector<Eigen::Vector3d> &normal = pc->getVertexData<Eigen::Vector3d>(envire::Pointcloud::VERTEX_NORMAL);
+            for (int i = -10; i <= 10; i++)
+                for (int j = -10; j <= 10; j++) {
+                    const bool edge = (i == -10 || j == -10 || i == 10 || j == 10);
+                    const double x = i * .1, y = j * .1, d = std::sqrt(x * x + y * y);
+                    const double zd = -.2 * 10.0 * std::sin(10.0 * d), nx = std::sqrt(1.0 / (1.0 + zd * zd)), ny = zd * nx;
+                    pc->vertices.push_back(Eigen::Vector3d(x, y, .2 * std::cos(10.0 * d)));
+                    attr.push_back(edge << 1);
+                    normal.push_back(Eigen::AngleAxisd(std::atan2(y, x), Eigen::Vector3d::UnitZ()) * Eigen::Vector3d(-ny, 0, nx));
+                }
+        }
+        try {
+            envire::icp::TrimmedGPUEAN icp;
+            icp.addToModel(envire::icp::PointcloudEdgeAndNormalAdapter(mesh, 1.0));
+            icp.align(envire::icp::PointcloudEdgeAndNormalAdapter(mesh2, density), max_iter, min_mse, min_mse_diff, atof(argv[24]));
+            const Eigen::Matrix4d M = fm2->getTransform().matrix();
+            const std::vector<double> pd = icp.getPairsDistance();
+            double pd_sum = 0;
+            for (size_t i = 0; i < pd.size(); ++i) pd_sum += pd[i];
+            printf("{\"fn_T\": [");
+            for (int r = 0; r < 4; ++r) printf("%s[%.17g, %.17g, %.17g, %.17g]", r ? ", " : "", M(r, 0), M(r, 1), M(r, 2), M(r, 3));
+            printf("], \"iter\": %zu, \"pairs\": %zu, \"mse\": %.17g, \"overlap\": %.17g, \"n_pairs_distance\": %zu, \"pd_sum\": %.17g}\n",
+                   icp.getNumIterations(), icp.getPairs(), icp.getMeanSquareError(), icp.getOverlap(), pd.size(), pd_sum);
+        } catch (const std::exception &e) {
+            printf("{\"error\": \"%s\"}\n", e.what());
+            return 1;
+        }
+        return 0;
+    }
     try {
         envire::icp::TrimmedGPU icp;
         icp.addToModel(envire::icp::PointcloudAdapter(mesh, 1.0));

@@ -17,6 +17,26 @@ def sine_wave():
     return np.array(pts)
 
 
+def sine_wave_ean():
+    """setSineWave incl. its normals and scan-edge attributes (test/unit/icp.cpp:52-91)."""
+    pts, nrm, att = [], [], []
+    for i in range(-10, 11):
+        for j in range(-10, 11):
+            edge = i in (-10, 10) or j in (-10, 10)
+            x, y = i * .1, j * .1
+            d = np.sqrt(x * x + y * y)
+            z = .2 * np.cos(10.0 * d)
+            zd = -.2 * 10.0 * np.sin(10.0 * d)
+            nx = np.sqrt(1.0 / (1.0 + zd * zd))
+            ny = zd * nx
+            a = np.arctan2(y, x)
+            Rz = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+            pts.append((x, y, z))
+            nrm.append(Rz @ np.array([-ny, 0.0, nx]))
+            att.append(int(edge) << 1)  # edge << TriMesh::SCAN_EDGE
+    return np.array(pts), np.array(nrm), np.array(att, dtype=np.int32)
+
+
 def half_cube():
     """test/unit/icp.cpp:23-50 (setHalfCube): 3 adjacent walls of a unit cube, 363 points."""
     pts = []
@@ -51,7 +71,27 @@ def cases():
                                         kind="fixed", params=dict(max_iter=40, min_mse=1e-12, min_mse_diff=1e-14, overlap=0.9))
     out["halfcube_golden_section"] = dict(model=[(hc, None, 1.0)], src=hc, T_src=small_transform(), density=1.0,
                                           kind="golden", params=dict(gui, alpha=0.4, beta=1.0, eps=0.05))
+    # TrimmedKDEAN: edge/normal pair filter (icp/icp.hpp:206-221, 513-521)
+    p_e, n_e, a_e = sine_wave_ean()
+    for ov in (0.8, 0.5):
+        out["ean_sine_overlap_%.1f" % ov] = dict(model=[(p_e, None, 1.0)], src=p_e, T_src=small_transform(), density=1.0,
+                                                 kind="ean", normals=n_e, attrs=a_e,
+                                                 params=dict(max_iter=10, min_mse=1e-9, min_mse_diff=1e-12, overlap=ov))
     m, s, T, prm = synth.config("cfg1", 0.1)
+    # a scene with analytic normals: ground normals from the height field, wall normals axis-aligned; 3 % edge flags
+    rng = np.random.default_rng(9)
+    nrm = np.zeros_like(m)
+    g = np.abs(m[:, 2] - 0.3 * np.sin(0.5 * m[:, 0]) * np.cos(0.4 * m[:, 1])) < 1e-12
+    gx = 0.15 * np.cos(0.5 * m[:, 0]) * np.cos(0.4 * m[:, 1])
+    gy = -0.12 * np.sin(0.5 * m[:, 0]) * np.sin(0.4 * m[:, 1])
+    nrm[g] = np.stack([-gx[g], -gy[g], np.ones(g.sum())], 1)
+    nrm[~g & (m[:, 1] == 10.0)] = (0, -1, 0)
+    nrm[~g & (m[:, 1] != 10.0)] = (1, 0, 0)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    att = (rng.random(len(m)) < 0.03).astype(np.int32) << 1
+    Rt = T[:3, :3]
+    out["ean_cfg1_scale0.1"] = dict(model=[(m, None, 1.0)], src=s, T_src=None, density=1.0, kind="ean", normals=nrm,
+                                    attrs=att, src_normals=nrm @ Rt, params=dict(prm, max_iter=25))
     out["cfg1_scale0.1"] = dict(model=[(m, None, 1.0)], src=s, T_src=None, density=1.0, kind="fixed", params=prm)
     out["cfg1_gui_defaults"] = dict(model=[(m, None, 1.0)], src=s, T_src=None, density=1.0, kind="fixed",
                                     params=dict(max_iter=5, min_mse=1e-5, min_mse_diff=1e-8, overlap=0.8))

@@ -20,9 +20,17 @@ def main():
            "cases": {}}
     for name, c in cases.cases().items():
         r = R.Ref()
-        for xyz, T, dens in c["model"]:
-            r.add_to_model(xyz, T=T, density=dens)
-        if c["kind"] == "golden":
+        if c["kind"] == "ean":
+            for xyz, T, dens in c["model"]:
+                r.add_to_model_ean(xyz, c["normals"], c["attrs"], T=T, density=dens)
+            g = r.align_ean(c["src"], c.get("src_normals", c["normals"]), c["attrs"], T=c["T_src"], density=c["density"],
+                            **c["params"])
+        else:
+            for xyz, T, dens in c["model"]:
+                r.add_to_model(xyz, T=T, density=dens)
+        if c["kind"] == "ean":
+            pass
+        elif c["kind"] == "golden":
             g = r.align_golden(c["src"], T=c["T_src"], density=c["density"], **c["params"])
         else:
             g = r.align(c["src"], T=c["T_src"], density=c["density"], **c["params"])

@@ -23,6 +23,30 @@ def test_c_abi_matches_reference_golden(icp, oracle, name):
     check_against_golden(name, r.matrix(), r.iter, r.pairs, r.mse, r.overlap, icp.pairs_distance(), oracle)
 
 
+@pytest.mark.parametrize("name", sorted(n for n in CASES if CASES[n]["kind"] == "ean"))
+def test_c_abi_ean_matches_reference_golden(icp, oracle, name):
+    """TrimmedKDEAN path: edge/normal pair filter after the NN search, against the reference's own TrimmedKDEAN."""
+    c = CASES[name]
+    icp.clear_model()
+    for xyz, T, dens in c["model"]:
+        icp.add_to_model_ean(xyz, c["normals"], c["attrs"], T=T, density=dens)
+    icp.upload_source_ean(c["src"], c.get("src_normals", c["normals"]), c["attrs"], T=c["T_src"], density=c["density"])
+    r = icp.align_resident(**c["params"])
+    check_against_golden(name, r.matrix(), r.iter, r.pairs, r.mse, r.overlap, icp.pairs_distance(), oracle)
+    # per-iteration pair counts equal the oracle's (the filter rejects the same vertices)
+    M = oracle.Model()
+    for xyz, T, dens in c["model"]:
+        M.add_ean(xyz, c["normals"], c["attrs"], T=T, density=dens)
+    run = oracle.Run()
+    M.align_ean(c["src"], c.get("src_normals", c["normals"]), c["attrs"], T=c["T_src"], density=c["density"], run=run,
+                **c["params"])
+    assert [t["found"] for t in icp.trace()] == [t["found"] for t in run.trace()]
+    # mixing plain and edge-and-normal clouds in one model is refused
+    with pytest.raises(Exception):
+        icp.add_to_model(c["src"])
+    icp.clear_model()
+
+
 @pytest.fixture(scope="module")
 def cli():
     src = os.path.join(ROOT, "tests", "cpp", "icp_gpu_cli.cpp")
@@ -36,7 +60,7 @@ def cli():
     return exe
 
 
-@pytest.mark.parametrize("name", sorted(n for n in CASES if len(CASES[n]["model"]) == 1))
+@pytest.mark.parametrize("name", sorted(n for n in CASES if len(CASES[n]["model"]) == 1 and CASES[n]["kind"] != "ean"))
 def test_host_mirror_matches_reference_golden(cli, tmp_path, name):
     """TrimmedGPU: addToModel / align (fixed and golden-section) / applyTransform -> FrameNode::setTransform / getters."""
     c, g = CASES[name], GOLDEN[name]
@@ -59,3 +83,21 @@ def test_host_mirror_matches_reference_golden(cli, tmp_path, name):
     assert out["n_pairs_distance"] == g["n_pairs_distance"] and out["pd_sorted"]
     assert abs(out["pd_sum"] - g["pd_sum"]) <= 1e-7 * abs(g["pd_sum"]) + 1e-12
     assert out["set_transform_events"] == 1  # applyTransform fires FrameNode::setTransform exactly once
+
+
+@pytest.mark.parametrize("name", ["ean_sine_overlap_0.8", "ean_sine_overlap_0.5"])
+def test_host_mirror_ean_matches_reference_golden(cli, tmp_path, name):
+    """TrimmedGPUEAN + PointcloudEdgeAndNormalAdapter on the reference's sine-wave fixture (normals + edge flags)."""
+    c, g = CASES[name], GOLDEN[name]
+    dummy = str(tmp_path / "d.bin")
+    np.zeros(3).tofile(dummy)
+    p = c["params"]
+    args = [cli, dummy, dummy] + ["%.17g" % v for v in np.asarray(c["T_src"]).T.reshape(16)] + [
+        "%.17g" % c["density"], "ean_sine", str(p["max_iter"]), "%.17g" % p["min_mse"], "%.17g" % p["min_mse_diff"],
+        "%.17g" % p["overlap"]]
+    out = json.loads(subprocess.check_output(args).decode())
+    assert "error" not in out, out
+    assert out["iter"] == g["iter"] and out["pairs"] == g["pairs"] and out["n_pairs_distance"] == g["n_pairs_distance"]
+    assert_transform_close(np.array(out["fn_T"]), np.array(g["fn_T"]), 2.0)
+    assert abs(out["mse"] - g["mse"]) <= 1e-5 * abs(g["mse"])
+    assert abs(out["pd_sum"] - g["pd_sum"]) <= 1e-7 * abs(g["pd_sum"]) + 1e-12
