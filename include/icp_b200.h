@@ -66,7 +66,10 @@ const char *icpb_version(void);
 /* ---- tunables (GPU-only knobs; ICPConfiguration stays untouched) ------ */
 /* keys: "cell_size" (m, 0 = auto), "target_pts_per_cell", "max_cells",
  *       "poll_every" (iterations between host polls of the done flag),
- *       "warm_start" (0/1: seed the search with the previous iteration's pair) */
+ *       "warm_start" (0/1: seed the search with the previous iteration's pair),
+ *       "sort_source" (0/1), "run_ahead", "profile" (0/1),
+ *       "growth_margin" (fraction of the model extent left free around it at a full build, so that later
+ *       addToModel calls inside that box are merged in without a rebuild; default 0), "merge_append" (0/1) */
 int icpb_set_option(icpb_ctx *, const char *key, double value);
 int icpb_get_option(const icpb_ctx *, const char *key, double *value);
 
@@ -91,6 +94,7 @@ typedef struct {
     uint32_t dims[3], levels;
     uint64_t n_cells, n_points, n_occupied;
     double build_ms;
+    uint64_t merges; /* addToModel calls served by a streaming merge into the existing grid instead of a rebuild */
 } icpb_grid_info;
 int icpb_model_build(icpb_ctx *, icpb_grid_info *info /* may be NULL */);
 

@@ -46,7 +46,7 @@ class Result(C.Structure):
 class GridInfo(C.Structure):
     _fields_ = [("origin", C.c_double * 3), ("cell_size", C.c_double), ("dims", C.c_uint32 * 3),
                 ("levels", C.c_uint32), ("n_cells", C.c_uint64), ("n_points", C.c_uint64),
-                ("n_occupied", C.c_uint64), ("build_ms", C.c_double)]
+                ("n_occupied", C.c_uint64), ("build_ms", C.c_double), ("merges", C.c_uint64)]
 
 
 class Timing(C.Structure):

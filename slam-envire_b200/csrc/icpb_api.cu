@@ -171,7 +171,7 @@ struct icpb_ctx {
     std::string err;
     // options
     double opt_cell_size = 0.0, opt_target = 4.0, opt_max_cells = 64.0 * 1024 * 1024, opt_run_ahead = 2.0,
-           opt_warm = 1.0, opt_profile = 1.0, opt_sort = 1.0;
+           opt_warm = 1.0, opt_profile = 1.0, opt_sort = 1.0, opt_margin = 0.0, opt_merge = 1.0;
     // model
     DevBuf<double> model_raw, model_nrm;
     DevBuf<uint8_t> model_edge;
@@ -180,8 +180,12 @@ struct icpb_ctx {
     DevBuf<int> stage_i;
     size_t model_n = 0;
     bool grid_dirty = true;
-    DevBuf<MPoint> pts;
-    DevBuf<FPoint> ptsf;
+    DevBuf<MPoint> pts, pts2;
+    DevBuf<FPoint> ptsf, ptsf2;
+    DevBuf<uint32_t> pkey, pkey2, newpref;
+    DevBuf<NPoint> npts2;
+    GridDims gdims;
+    unsigned long long merges = 0;
     DevBuf<uint32_t> cell_start;
     DevBuf<uint8_t> masks;
     DevBuf<uint32_t> keys0, keys1, vals0, vals1, sort_scratch;
@@ -331,6 +335,12 @@ void icpb_destroy(icpb_ctx *ctx)
     ctx->sedge_tmp.release();
     ctx->pts.release();
     ctx->ptsf.release();
+    ctx->pts2.release();
+    ctx->ptsf2.release();
+    ctx->pkey.release();
+    ctx->pkey2.release();
+    ctx->newpref.release();
+    ctx->npts2.release();
     ctx->cell_start.release();
     ctx->masks.release();
     ctx->keys0.release();
@@ -377,6 +387,8 @@ static double *opt_slot(icpb_ctx *ctx, const char *key)
     if (!strcmp(key, "warm_start")) return &ctx->opt_warm;
     if (!strcmp(key, "profile")) return &ctx->opt_profile;
     if (!strcmp(key, "sort_source")) return &ctx->opt_sort;
+    if (!strcmp(key, "growth_margin")) return &ctx->opt_margin;
+    if (!strcmp(key, "merge_append")) return &ctx->opt_merge;
     return nullptr;
 }
 int icpb_set_option(icpb_ctx *ctx, const char *key, double value)
@@ -400,6 +412,98 @@ int icpb_get_option(const icpb_ctx *ctx, const char *key, double *value)
 // ---------------------------------------------------------------------------
 // model
 // ---------------------------------------------------------------------------
+static int build_masks(icpb_ctx *ctx);
+
+// Growing model: merge a freshly appended batch (model_raw[n_old, n_old + k)) into the existing index in one
+// streaming pass instead of re-sorting everything.  Falls back (returns with *done == false) when there is no
+// built grid or the batch does not fit inside the grid box.
+static int try_merge_append(icpb_ctx *ctx, size_t n_old, size_t k, bool *done)
+{
+    *done = false;
+    if (ctx->opt_merge == 0.0 || ctx->grid_dirty || n_old == 0 || ctx->gv.n != n_old || k == 0) return ICPB_OK;
+    if (n_old + k >= 0xFFFFFFF0ull) return ICPB_OK;
+    cudaStream_t s = ctx->stream;
+    const GridView &g = ctx->gv;
+    const unsigned nbb = std::min<unsigned>(1024u, grid_for(k, 256));
+    CK(ctx->bbox_part.ensure((size_t)nbb * 6));
+    bbox_kernel<<<nbb, 256, 0, s>>>(ctx->model_raw.p + 3 * n_old, k, ctx->bbox_part.p);
+    CKL();
+    std::vector<double> hb((size_t)nbb * 6);
+    CK(cudaMemcpyAsync(hb.data(), ctx->bbox_part.p, hb.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (int a = 0; a < 3; ++a) {
+        double lo = INFINITY, hi = -INFINITY;
+        for (unsigned b = 0; b < nbb; ++b) {
+            lo = fmin(lo, hb[(size_t)b * 6 + a]);
+            hi = fmax(hi, hb[(size_t)b * 6 + 3 + a]);
+        }
+        // same arithmetic as icpb_cell_coord, but without clamping: the cell must exist
+        if (!(floor((lo - g.o[a]) * g.inv_h) >= 0.0) || !(floor((hi - g.o[a]) * g.inv_h) <= (double)(g.dim[0][a] - 1)))
+            return ICPB_OK;
+    }
+    const size_t ncell = (size_t)g.dim[0][0] * g.dim[0][1] * g.dim[0][2];
+    cudaEvent_t e0 = ctx->ev_up0, e1 = ctx->ev_up1;
+    CK(cudaEventRecord(e0, s));
+    CK(ctx->keys0.ensure(k));
+    CK(ctx->keys1.ensure(k));
+    CK(ctx->vals0.ensure(k));
+    CK(ctx->vals1.ensure(k));
+    CK(ctx->sort_scratch.ensure(rs_scratch_elems(k)));
+    CK(ctx->newpref.ensure(ncell + 1 + scan_scratch_elems(ncell + 1)));
+    CK(ctx->pts2.ensure(n_old + k));
+    CK(ctx->ptsf2.ensure(n_old + k));
+    CK(ctx->pkey2.ensure(n_old + k));
+    if (ctx->model_ean) CK(ctx->npts2.ensure(n_old + k));
+    cell_keys_kernel<<<grid_for(k, 256), 256, 0, s>>>(ctx->model_raw.p + 3 * n_old, (uint32_t)k, ctx->gdims, ctx->keys0.p,
+                                                      ctx->vals0.p, (uint32_t)n_old);
+    CKL();
+    int bits = 1;
+    while (((size_t)1 << bits) < ncell) ++bits;
+    const int w = radix_sort<uint32_t, true>(ctx->keys0.p, ctx->vals0.p, ctx->keys1.p, ctx->vals1.p, k, bits,
+                                             ctx->sort_scratch.p, s, &ctx->launches);
+    CKL();
+    const uint32_t *ks = w ? ctx->keys1.p : ctx->keys0.p, *vs = w ? ctx->vals1.p : ctx->vals0.p;
+    CK(cudaMemsetAsync(ctx->newpref.p, 0, (ncell + 1) * sizeof(uint32_t), s));
+    key_hist_kernel<<<grid_for(k, 256), 256, 0, s>>>(ks, (uint32_t)k, ctx->newpref.p);
+    CKL();
+    exclusive_scan_u32(ctx->newpref.p, ctx->newpref.p, ncell + 1, ctx->newpref.p + ncell + 1, s, &ctx->launches);
+    CKL();
+    merge_move_old_kernel<<<grid_for(n_old, 256), 256, 0, s>>>(ctx->pts.p, ctx->ptsf.p, ctx->pkey.p,
+                                                               ctx->model_ean ? ctx->npts.p : nullptr, (uint32_t)n_old,
+                                                               ctx->newpref.p, ctx->pts2.p, ctx->ptsf2.p, ctx->pkey2.p,
+                                                               ctx->model_ean ? ctx->npts2.p : nullptr);
+    merge_place_new_kernel<<<grid_for(k, 256), 256, 0, s>>>(ctx->model_raw.p, ctx->model_ean ? ctx->model_nrm.p : nullptr,
+                                                            ctx->model_ean ? ctx->model_edge.p : nullptr, ks, vs,
+                                                            (uint32_t)k, ctx->gdims, ctx->cell_start.p, ctx->pts2.p,
+                                                            ctx->ptsf2.p, ctx->pkey2.p,
+                                                            ctx->model_ean ? ctx->npts2.p : nullptr);
+    add_prefix_kernel<<<grid_for(ncell + 1, 256), 256, 0, s>>>(ctx->cell_start.p, ctx->newpref.p, ncell + 1);
+    CKL();
+    ctx->launches += 5;
+    std::swap(ctx->pts, ctx->pts2);
+    std::swap(ctx->ptsf, ctx->ptsf2);
+    std::swap(ctx->pkey, ctx->pkey2);
+    if (ctx->model_ean) std::swap(ctx->npts, ctx->npts2);
+    ctx->gv.pts = ctx->pts.p;
+    ctx->gv.ptsf = ctx->ptsf.p;
+    ctx->gv.n = (uint32_t)(n_old + k);
+    {
+        int rc = build_masks(ctx);
+        if (rc != ICPB_OK) return rc;
+    }
+    CK(cudaEventRecord(e1, s));
+    CK(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    ctx->merges += 1;
+    ctx->ginfo.n_points = n_old + k;
+    ctx->ginfo.merges = ctx->merges;
+    ctx->ginfo.build_ms = ms;
+    ctx->last_valid = false;
+    *done = true;
+    return ICPB_OK;
+}
+
 static int model_add(icpb_ctx *ctx, const double *xyz, const double *normals, const int32_t *attrs, size_t n,
                      const double T[16], double density)
 {
@@ -438,8 +542,14 @@ static int model_add(icpb_ctx *ctx, const double *xyz, const double *normals, co
         CK(cudaStreamSynchronize(ctx->stream));
     }
     ctx->model_ean = ean;
+    const size_t n_old = ctx->model_n;
     ctx->model_n += m;
-    ctx->grid_dirty = true;
+    bool merged = false;
+    {
+        int rc = try_merge_append(ctx, n_old, m, &merged);
+        if (rc != ICPB_OK) return rc;
+    }
+    if (!merged) ctx->grid_dirty = true;
     return ICPB_OK;
 }
 
@@ -480,6 +590,39 @@ static void dims_for(const double ext[3], double h, int d[3])
     }
 }
 
+// occupancy pyramid from the level-0 prefix array (also after a merge-append)
+static int build_masks(icpb_ctx *ctx)
+{
+    cudaStream_t s = ctx->stream;
+    GridView &g = ctx->gv;
+    int L = 0;
+    size_t mask_total = 0;
+    size_t mask_off[ICPB_MAX_LEVELS] = {0};
+    while (g.dim[L][0] > 1 || g.dim[L][1] > 1 || g.dim[L][2] > 1) {
+        for (int a = 0; a < 3; ++a) g.dim[L + 1][a] = (g.dim[L][a] + 1) >> 1;
+        ++L;
+        mask_off[L] = mask_total;
+        mask_total += (size_t)g.dim[L][0] * g.dim[L][1] * g.dim[L][2];
+    }
+    g.L = L;
+    CK(ctx->masks.ensure(mask_total + 16));
+    for (int l = 1; l <= L; ++l) {
+        uint8_t *ml = ctx->masks.p + mask_off[l];
+        g.mask[l] = ml;
+        const size_t cells = (size_t)g.dim[l][0] * g.dim[l][1] * g.dim[l][2];
+        if (l == 1)
+            mask_level1_kernel<<<grid_for(cells, 256), 256, 0, s>>>(ctx->cell_start.p, g.dim[0][0], g.dim[0][1],
+                                                                    g.dim[0][2], g.dim[1][0], g.dim[1][1],
+                                                                    g.dim[1][2], ml);
+        else
+            mask_levelN_kernel<<<grid_for(cells, 256), 256, 0, s>>>(g.mask[l - 1], g.dim[l - 1][0], g.dim[l - 1][1],
+                                                                    g.dim[l - 1][2], g.dim[l][0], g.dim[l][1],
+                                                                    g.dim[l][2], ml);
+        CKL();
+    }
+    return ICPB_OK;
+}
+
 static int build_grid(icpb_ctx *ctx)
 {
     const size_t n = ctx->model_n;
@@ -511,7 +654,15 @@ static int build_grid(icpb_ctx *ctx)
     }
     double se[3] = {ext[0], ext[1], ext[2]};
     std::sort(se, se + 3);
-    const double emax = se[2];
+    // growth margin: the grid box is the data box widened on every side, so that clouds added later (a growing
+    // map) fall inside it and can be merged in without a rebuild
+    const double margin = fmax(0.0, fmin(ctx->opt_margin, 8.0));
+    const double dext[3] = {ext[0], ext[1], ext[2]};
+    for (int a = 0; a < 3; ++a) {
+        mn[a] -= margin * dext[a];
+        ext[a] = dext[a] * (1.0 + 2.0 * margin);
+    }
+    const double emax = se[2] * (1.0 + 2.0 * margin);
     // smallest admissible cell edge: <= MAX_DIM cells per axis, <= max_cells cells in total
     auto h_floor = [&](double h) {
         if (emax > 0.0) h = fmax(h, emax / (double)(MAX_DIM - 1));
@@ -576,7 +727,10 @@ static int build_grid(icpb_ctx *ctx)
         if (fabs(h_new - h) <= 1e-3 * h) break; // clamped by the cell budget
         h = h_new;
     }
+    ctx->gdims = gd;
     const uint32_t *keys_sorted = sorted_in ? ctx->keys1.p : ctx->keys0.p;
+    CK(ctx->pkey.ensure(n));
+    CK(cudaMemcpyAsync(ctx->pkey.p, keys_sorted, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
     const uint32_t *perm = sorted_in ? ctx->vals1.p : ctx->vals0.p;
     const size_t ncell = (size_t)dim0[0] * dim0[1] * dim0[2];
 
@@ -606,31 +760,11 @@ static int build_grid(icpb_ctx *ctx)
     g.h = h;
     g.inv_h = 1.0 / h;
     g.eps = 1e-9 * h;
-    int L = 0;
-    size_t mask_total = 0;
-    size_t mask_off[ICPB_MAX_LEVELS] = {0};
-    while (g.dim[L][0] > 1 || g.dim[L][1] > 1 || g.dim[L][2] > 1) {
-        for (int a = 0; a < 3; ++a) g.dim[L + 1][a] = (g.dim[L][a] + 1) >> 1;
-        ++L;
-        mask_off[L] = mask_total;
-        mask_total += (size_t)g.dim[L][0] * g.dim[L][1] * g.dim[L][2];
+    {
+        int rc = build_masks(ctx);
+        if (rc != ICPB_OK) return rc;
     }
-    g.L = L;
-    CK(ctx->masks.ensure(mask_total + 16));
-    for (int l = 1; l <= L; ++l) {
-        uint8_t *ml = ctx->masks.p + mask_off[l];
-        g.mask[l] = ml;
-        const size_t cells = (size_t)g.dim[l][0] * g.dim[l][1] * g.dim[l][2];
-        if (l == 1)
-            mask_level1_kernel<<<grid_for(cells, 256), 256, 0, s>>>(ctx->cell_start.p, g.dim[0][0], g.dim[0][1],
-                                                                    g.dim[0][2], g.dim[1][0], g.dim[1][1],
-                                                                    g.dim[1][2], ml);
-        else
-            mask_levelN_kernel<<<grid_for(cells, 256), 256, 0, s>>>(g.mask[l - 1], g.dim[l - 1][0], g.dim[l - 1][1],
-                                                                    g.dim[l - 1][2], g.dim[l][0], g.dim[l][1],
-                                                                    g.dim[l][2], ml);
-        CKL();
-    }
+    const int L = g.L;
     g.cell_start = ctx->cell_start.p;
     g.pts = ctx->pts.p;
     g.ptsf = ctx->ptsf.p;
@@ -650,6 +784,7 @@ static int build_grid(icpb_ctx *ctx)
     gi.n_points = n;
     gi.n_occupied = occupied;
     gi.build_ms = ms;
+    gi.merges = ctx->merges;
     ctx->last_valid = false; // nn_pos of an earlier align refers to the old layout
     return ICPB_OK;
 }

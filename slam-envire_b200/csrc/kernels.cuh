@@ -15,6 +15,18 @@
 
 namespace icpb {
 
+// model normal + edge flag in the sorted order of pts[] (FindPairsKDEAN nodes, icp/icp.hpp:91-97)
+struct __align__(32) NPoint {
+    double nx, ny, nz;
+    unsigned long long edge;
+};
+// the edge/normal pair filter inputs of one align (all null/0 for the plain TrimmedKD path)
+struct EanView {
+    const NPoint *mn;                // model, sorted like GridView::pts
+    const double *snx, *sny, *snz;   // source normals (local frame), in the order of sx/sy/sz
+    const uint8_t *sedge;
+    int on;
+};
 // ---------------------------------------------------------------------------
 // K0: p = T * v  appended to the model (fp64 AoS in, AoS out)
 // ---------------------------------------------------------------------------
@@ -50,18 +62,6 @@ __global__ void edge_flags_kernel(const int *__restrict__ attrs, size_t n, uint8
     if (i < n) out[i] = (attrs[i] & (1 << 0x01)) ? 1 : 0;
 }
 
-// model normal + edge flag in the sorted order of pts[] (FindPairsKDEAN nodes, icp/icp.hpp:91-97)
-struct __align__(32) NPoint {
-    double nx, ny, nz;
-    unsigned long long edge;
-};
-// the edge/normal pair filter inputs of one align (all null/0 for the plain TrimmedKD path)
-struct EanView {
-    const NPoint *mn;                // model, sorted like GridView::pts
-    const double *snx, *sny, *snz;   // source normals (local frame), in the order of sx/sy/sz
-    const uint8_t *sedge;
-    int on;
-};
 __global__ void gather_ean_kernel(const double *__restrict__ nrm, const uint8_t *__restrict__ edge,
                                   const uint32_t *__restrict__ perm, uint32_t n, NPoint *__restrict__ out)
 {
@@ -132,7 +132,7 @@ struct GridDims {
 };
 
 __global__ void cell_keys_kernel(const double *__restrict__ pts, uint32_t n, GridDims g, uint32_t *__restrict__ keys,
-                                 uint32_t *__restrict__ vals)
+                                 uint32_t *__restrict__ vals, uint32_t base = 0)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -140,7 +140,7 @@ __global__ void cell_keys_kernel(const double *__restrict__ pts, uint32_t n, Gri
     const int cy = icpb_cell_coord(pts[3 * (size_t)i + 1], g.o[1], g.inv_h, g.ny);
     const int cz = icpb_cell_coord(pts[3 * (size_t)i + 2], g.o[2], g.inv_h, g.nz);
     keys[i] = (uint32_t)(((size_t)cz * g.ny + cy) * g.nx + cx);
-    vals[i] = i;
+    vals[i] = base + i; // insertion index
 }
 
 // number of distinct keys in a sorted key array (occupied cells)
@@ -176,6 +176,68 @@ __global__ void gather_points_kernel(const double *__restrict__ raw, const uint3
     f.w = 0.0f;
     outf[j] = f;
     atomicAdd(&cell_count[keys[j]], 1u);
+}
+
+// ---------------------------------------------------------------------------
+// K1b: append a batch to an existing index without re-sorting the model (growing model).
+// The new batch is sorted by cell key on its own; old and new points are then merged in one streaming pass:
+// an old point of cell c moves up by the number of new points in cells < c, the new points of cell c follow it.
+// ---------------------------------------------------------------------------
+__global__ void key_hist_kernel(const uint32_t *__restrict__ keys, uint32_t n, uint32_t *__restrict__ cnt)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(&cnt[keys[i]], 1u);
+}
+__global__ void merge_move_old_kernel(const MPoint *__restrict__ pts, const FPoint *__restrict__ ptsf,
+                                      const uint32_t *__restrict__ pkey, const NPoint *__restrict__ npts, uint32_t n,
+                                      const uint32_t *__restrict__ newpref, MPoint *__restrict__ pts2,
+                                      FPoint *__restrict__ ptsf2, uint32_t *__restrict__ pkey2, NPoint *__restrict__ npts2)
+{
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint32_t c = pkey[p];
+    const uint32_t q = p + newpref[c];
+    pts2[q] = pts[p];
+    ptsf2[q] = ptsf[p];
+    pkey2[q] = c;
+    if (npts) npts2[q] = npts[p];
+}
+__global__ void merge_place_new_kernel(const double *__restrict__ raw, const double *__restrict__ raw_nrm,
+                                       const uint8_t *__restrict__ raw_edge, const uint32_t *__restrict__ keys,
+                                       const uint32_t *__restrict__ vals, uint32_t k, GridDims g,
+                                       const uint32_t *__restrict__ cell_start_old, MPoint *__restrict__ pts2,
+                                       FPoint *__restrict__ ptsf2, uint32_t *__restrict__ pkey2, NPoint *__restrict__ npts2)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= k) return;
+    const uint32_t c = keys[j], src = vals[j];
+    const uint32_t q = cell_start_old[c + 1] + j; // old points of cells <= c, plus the new ones sorted before j
+    MPoint m;
+    m.x = raw[3 * (size_t)src];
+    m.y = raw[3 * (size_t)src + 1];
+    m.z = raw[3 * (size_t)src + 2];
+    m.idx = src;
+    pts2[q] = m;
+    FPoint f;
+    f.x = (float)((m.x - g.o[0]) * g.inv_h);
+    f.y = (float)((m.y - g.o[1]) * g.inv_h);
+    f.z = (float)((m.z - g.o[2]) * g.inv_h);
+    f.w = 0.0f;
+    ptsf2[q] = f;
+    pkey2[q] = c;
+    if (npts2) {
+        NPoint np;
+        np.nx = raw_nrm[3 * (size_t)src];
+        np.ny = raw_nrm[3 * (size_t)src + 1];
+        np.nz = raw_nrm[3 * (size_t)src + 2];
+        np.edge = raw_edge[src];
+        npts2[q] = np;
+    }
+}
+__global__ void add_prefix_kernel(uint32_t *__restrict__ cell_start, const uint32_t *__restrict__ newpref, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) cell_start[i] += newpref[i];
 }
 
 // level-1 occupancy masks from the level-0 prefix array

@@ -4,6 +4,7 @@
 // aligned against the model built from scans < i (TrimmedGPU::align), its FrameNode is updated by applyTransform, and it
 // is then added to the model (addToModel accumulates, like FindPairsKDTree::addModel, icp/icp.hpp:231-240).
 // usage: env_slam6d <dir> <n_scans> [--density d] [--overlap o] [--max-iter n] [--min-mse x] [--min-mse-diff x]
+//                   [--growth-margin f]
 //   <dir>/scanNNN.ply   scan in its sensor frame        <dir>/scanNNN.pose   initial sensor pose: 16 numbers, row-major 4x4
 // writes <dir>/scanNNN.frames (refined 4x4, row-major) and prints one JSON summary.
 #include <chrono>
@@ -22,7 +23,7 @@ int main(int argc, char **argv)
     if (argc < 3) { fprintf(stderr, "usage: env_slam6d <dir> <n_scans> [options]\n"); return 2; }
     const std::string dir = argv[1];
     const int n_scans = atoi(argv[2]);
-    double density = 1.0, overlap = 0.8, min_mse = 1e-6, min_mse_diff = 1e-9;
+    double density = 1.0, overlap = 0.8, min_mse = 1e-6, min_mse_diff = 1e-9, growth_margin = 1.0;
     size_t max_iter = 30;
     for (int i = 3; i < argc; ++i) {
         if (!strcmp(argv[i], "--density")) density = atof(argv[++i]);
@@ -30,10 +31,13 @@ int main(int argc, char **argv)
         else if (!strcmp(argv[i], "--max-iter")) max_iter = (size_t)atoll(argv[++i]);
         else if (!strcmp(argv[i], "--min-mse")) min_mse = atof(argv[++i]);
         else if (!strcmp(argv[i], "--min-mse-diff")) min_mse_diff = atof(argv[++i]);
+        else if (!strcmp(argv[i], "--growth-margin")) growth_margin = atof(argv[++i]);
     }
     try {
         std::unique_ptr<envire::Environment> env(new envire::Environment());
         envire::icp::TrimmedGPU icp;
+        // leave room around the first scans so that later scans are merged into the index instead of rebuilding it
+        icp.setOption("growth_margin", growth_margin);
         double align_ms = 0, add_ms = 0;
         size_t total_iter = 0, model_points = 0;
         for (int s = 0; s < n_scans; ++s) {

@@ -257,3 +257,49 @@ def test_full_size_properties_1m(icp, synth):
     assert_transform_close(r.matrix(), T, 100.0, rot_tol=1e-5, trans_tol_rel=1e-5)
     pd = icp.pairs_distance()
     assert len(pd) == 800000 and np.all(np.diff(pd) >= 0) and pd[-1] * 2.0 == r.d_box
+
+
+def test_growing_model_merge_append(pkg, oracle, synth):
+    """SURVEY 8f row f2: addToModel on a built index merges the new cloud in (no rebuild) when it fits the grid box;
+    the result must be indistinguishable from a model built in one go -- and from the oracle's accumulated kd-tree."""
+    m = synth.scene(90000, 30.0, 12)
+    order = np.argsort(m[:, 0], kind="stable")  # feed the map strip by strip, like a robot exploring along x
+    parts = np.array_split(m[order], 6)
+    q = synth.perturbed_copy(m, 2.0, 0.2, 0.01, seed=13)[0][:30000]
+    grow = pkg.Icp(0)
+    grow.set_option("growth_margin", 0.0)
+    # first two strips define the box only partly: the third lies outside -> rebuild; with a margin they all fit
+    M = oracle.Model()
+    for k, p in enumerate(parts):
+        grow.add_to_model(p)
+        M.add(p)
+        gi = grow.build()
+        assert gi.n_points == sum(len(x) for x in parts[:k + 1])
+    assert gi.merges == 0  # every strip extends the bounding box in x: all rebuilds
+    i_ref, d_ref = M.find_pairs(q)
+    i0, d0 = grow.find_pairs(q)
+    assert np.array_equal(i0, i_ref) and np.array_equal(d0, d_ref)
+    grow.close()
+
+    grow = pkg.Icp(0)
+    grow.set_option("growth_margin", 3.0)
+    M = oracle.Model()
+    for k, p in enumerate(parts):
+        grow.add_to_model(p)
+        M.add(p)
+        gi = grow.build()
+    # strip 1 spans 5 m in x; a 3x margin covers the next three strips (merged in), the last two force one rebuild
+    assert 3 <= gi.merges <= 5 and gi.n_points == len(m)
+    for d_box in (np.inf, 0.3):
+        i_ref, d_ref = M.find_pairs(q, d_box=d_box)
+        i1, d1 = grow.find_pairs(q, d_box=d_box)
+        d_ref = np.where(i_ref == 0xFFFFFFFF, d_box, d_ref)
+        assert np.array_equal(i1, i_ref) and np.array_equal(d1, d_ref)
+    # a full align on the merged index equals the oracle's
+    s, T = synth.perturbed_copy(m, 3.0, 0.2, 0.0, seed=14)
+    prm = dict(max_iter=12, min_mse=1e-10, min_mse_diff=1e-12, overlap=0.85)
+    r = grow.align(s[:20000], **prm)
+    r_ref = M.align(s[:20000], **prm)
+    assert r.iter == r_ref.iter and r.pairs == r_ref.pairs
+    assert_transform_close(r.matrix(), r_ref.matrix(), 30.0)
+    grow.close()
