@@ -175,12 +175,10 @@ def run_b200(args):
     model, src, T_true = workload(rank)
     n_s = len(src)
     icp = pkg.Icp(local)
+    comm_mode = os.environ.get("ICPB_COMM", "p2p")
     if world > 1:
-        uid = torch.zeros(pkg.NCCL_ID_BYTES, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid.copy_(torch.frombuffer(bytearray(pkg.nccl_unique_id()), dtype=torch.uint8))
-        dist.broadcast(uid, 0)
-        icp.comm_init(world, rank, bytes(uid.cpu().numpy().tobytes()))
+        sharding = importlib.import_module("slam-envire_b200.sharding")
+        sharding.init_comm(icp, dist, torch.device("cuda", local), mode=comm_mode)
     icp.add_to_model(model)
     gi = icp.build()
 
@@ -268,6 +266,8 @@ def run_b200(args):
                                    "overlap 0.8", "align": ALIGN, "iterations_per_align": n_iter_per_step,
                        "ms_per_iteration": step_ms / args.steps / max(n_iter_per_step, 1),
                        "sharding": "source sharded x%d, model grid replicated" % world,
+                       "collectives": ("none" if world == 1 else ("fused into the select/moments kernels over NVLink peer memory"
+                                                                   if comm_mode == "p2p" else "NCCL all-reduce / all-gather")),
                        "l2": "256 MB buffer written between steps (L2 flush)",
                        "grid": {"cell_size": gi.cell_size, "dims": list(gi.dims), "levels": gi.levels,
                                 "occupied_cells": gi.n_occupied, "build_ms": gi.build_ms},

@@ -36,6 +36,7 @@ extern "C" {
 
 #define ICPB_NO_PAIR 0xFFFFFFFFu
 #define ICPB_NCCL_ID_BYTES 128
+#define ICPB_IPC_HANDLE_BYTES 64
 #define ICPB_TRACE_COLS 24
 
 typedef struct icpb_ctx icpb_ctx;
@@ -157,6 +158,11 @@ int icpb_trim(icpb_ctx *, const double *dist, size_t n, size_t n_po, double *tau
  * 17 moment sums) over NCCL. */
 int icpb_nccl_unique_id(uint8_t id_out[ICPB_NCCL_ID_BYTES]);
 int icpb_comm_init(icpb_ctx *, int n_ranks, int rank, const uint8_t id[ICPB_NCCL_ID_BYTES]);
+/* Preferred on one NVLink/NVSwitch box: the per-iteration collectives are FUSED into the producing kernels and run
+ * over peer memory instead of NCCL.  Every rank exports the IPC handle of its exchange buffer, the handles are
+ * all-gathered by any channel, then every rank connects (n_ranks <= 8).  Results are identical to the NCCL path. */
+int icpb_p2p_export(icpb_ctx *, uint8_t handle_out[ICPB_IPC_HANDLE_BYTES]);
+int icpb_p2p_connect(icpb_ctx *, int n_ranks, int rank, const uint8_t *handles /* n_ranks * ICPB_IPC_HANDLE_BYTES */);
 /* shard upload: vertices already density-stepped by the caller, plus the
  * GLOBAL PointcloudAdapter::size() (icp/icp.hpp:143-146) that n_po is derived from */
 int icpb_source_upload_shard(icpb_ctx *, const double *xyz_aos_local, size_t n_local, size_t adapter_size_global,

@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libicp_b200.so")
 NO_PAIR = 0xFFFFFFFF
 TRACE_COLS = 24
 NCCL_ID_BYTES = 128
+IPC_HANDLE_BYTES = 64
 
 OK, ERR_CUDA, ERR_ARG, ERR_NO_MODEL, ERR_NO_SOURCE, ERR_NCCL, ERR_CAPACITY, ERR_NOT_ENOUGH_PAIRS = range(8)
 
@@ -26,7 +27,7 @@ SYMBOLS = [
     "icpb_get_option", "icpb_model_add", "icpb_model_add_ean", "icpb_source_upload_ean", "icpb_model_clear", "icpb_model_size", "icpb_model_build",
     "icpb_source_upload", "icpb_align_resident", "icpb_align", "icpb_pairs_distance", "icpb_debug_pairs",
     "icpb_trace", "icpb_last_timing", "icpb_iteration_times", "icpb_find_pairs", "icpb_trim", "icpb_nccl_unique_id", "icpb_comm_init",
-    "icpb_source_upload_shard",
+    "icpb_source_upload_shard", "icpb_p2p_export", "icpb_p2p_connect",
 ]
 
 
@@ -102,6 +103,8 @@ def load_library():
     L.icpb_trim.argtypes = [vp, dp, C.c_size_t, C.c_size_t, dp, sp, sp]
     L.icpb_nccl_unique_id.argtypes = [C.POINTER(C.c_uint8)]
     L.icpb_comm_init.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_uint8)]
+    L.icpb_p2p_export.argtypes = [vp, C.POINTER(C.c_uint8)]
+    L.icpb_p2p_connect.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_uint8)]
     L.icpb_source_upload_shard.argtypes = [vp, dp, C.c_size_t, C.c_size_t, dp]
     _lib = L
     return L
@@ -283,6 +286,15 @@ class Icp:
         return tau.value, kept.value, ties.value
 
     # -- multi-GPU ----------------------------------------------------------
+    def p2p_export(self):
+        buf = (C.c_uint8 * IPC_HANDLE_BYTES)()
+        self._ck(self._L.icpb_p2p_export(self._h, buf))
+        return bytes(buf)
+
+    def p2p_connect(self, n_ranks, rank, handles):
+        buf = (C.c_uint8 * (IPC_HANDLE_BYTES * n_ranks)).from_buffer_copy(handles)
+        self._ck(self._L.icpb_p2p_connect(self._h, n_ranks, rank, buf))
+
     def comm_init(self, n_ranks, rank, unique_id):
         buf = (C.c_uint8 * NCCL_ID_BYTES).from_buffer_copy(unique_id)
         self._ck(self._L.icpb_comm_init(self._h, n_ranks, rank, buf))

@@ -228,6 +228,11 @@ struct icpb_ctx {
     nccl_comm_t comm = nullptr;
     int n_ranks = 1, rank = 0;
     unsigned long long *d_gather = nullptr;
+    // peer-memory collectives
+    uint32_t *p2p_local = nullptr;
+    void *p2p_mapped[P2P_MAX_RANKS] = {nullptr};
+    P2PView p2p;
+    bool use_p2p = false;
 
     int fail(cudaError_t e, const char *what, int line)
     {
@@ -297,6 +302,8 @@ int icpb_create(icpb_ctx **out, int device_id)
     memset(&ctx->gv, 0, sizeof(ctx->gv));
     memset(&ctx->ginfo, 0, sizeof(ctx->ginfo));
     memset(&ctx->timing, 0, sizeof(ctx->timing));
+    memset(&ctx->p2p, 0, sizeof(ctx->p2p));
+    ctx->p2p.world = 1;
     *out = ctx;
     CK(cudaSetDevice(device_id));
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -323,6 +330,9 @@ void icpb_destroy(icpb_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
+    for (int r = 0; r < P2P_MAX_RANKS; ++r)
+        if (ctx->p2p_mapped[r]) cudaIpcCloseMemHandle(ctx->p2p_mapped[r]);
+    if (ctx->p2p_local) cudaFree(ctx->p2p_local);
     ctx->model_raw.release();
     ctx->model_nrm.release();
     ctx->model_edge.release();
@@ -969,12 +979,12 @@ static int launch_trim(icpb_ctx *ctx, uint32_t n)
 {
     cudaStream_t s = ctx->stream;
     const unsigned blocks = std::max(1u, std::min(grid_for(n, SEL_THREADS * 4), 148u * 4u));
-    const int fused = ctx->n_ranks == 1 ? 1 : 0;
+    const int fused = (ctx->n_ranks == 1 || ctx->use_p2p) ? 1 : 0;
     if (!fused) // pairs found on all ranks
         NK(g_nccl.AllReduce(&ctx->d_state->found, &ctx->d_state->found, 1, NCCL_UINT64, NCCL_SUM, ctx->comm, s));
     for (int p = 0; p < SEL_D_PASSES; ++p) {
         select_kernel<<<blocks, SEL_THREADS, 0, s>>>(ctx->nn_d.p, ctx->src_perm.p, n, ctx->d_state, ctx->d_ghist, p, 0,
-                                                     fused, p);
+                                                     fused, p, ctx->p2p);
         CKL();
         ++ctx->launches;
         if (!fused) {
@@ -1037,7 +1047,7 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
         ctx->events.resize((size_t)EVENT_ITERS * 4);
         for (auto &e : ctx->events) CK(cudaEventCreate(&e));
     }
-    const int fused = ctx->n_ranks == 1 ? 1 : 0;
+    const int fused = (ctx->n_ranks == 1 || ctx->use_p2p) ? 1 : 0;
     const int run_ahead = (int)std::max(1.0, std::min(ctx->opt_run_ahead, 32.0));
     const unsigned long long launches0 = ctx->launches;
 
@@ -1085,7 +1095,7 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
         if (timed) CK(cudaEventRecord(ev[2], s));
         moments_kernel<<<mom_blocks, MOM_THREADS, 0, s>>>(ctx->gv, ctx->sx.p, ctx->sy.p, ctx->sz.p, n, ctx->d_state,
                                                           ctx->nn_pos.p, ctx->nn_d.p, ctx->src_perm.p, ctx->partials.p,
-                                                          ctx->trace.p, ctx->trace_cap, fused);
+                                                          ctx->trace.p, ctx->trace_cap, fused, ctx->p2p);
         CKL();
         ++ctx->launches;
         if (!fused) {
@@ -1107,6 +1117,10 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
     CK(cudaStreamSynchronize(s));
 
     const IcpState &hs = *ctx->h_state;
+    if (hs.comm_error) {
+        ctx->err = "peer-memory collective timed out (a rank is missing)";
+        return ICPB_ERR_NCCL;
+    }
     aff12_to_cm(hs.C, out->C_global2globalnew);
     out->iter = (size_t)hs.iter;
     out->pairs = (size_t)hs.pairs;
@@ -1303,9 +1317,12 @@ int icpb_trim(icpb_ctx *ctx, const double *dist, size_t n, size_t n_po, double *
     trim_setup_kernel<<<1, 1, 0, s>>>(ctx->d_state, n_po, found);
     CKL();
     const int saved_ranks = ctx->n_ranks;
+    const P2PView saved_p2p = ctx->p2p;
     ctx->n_ranks = 1; // stand-alone trim is always rank-local
+    ctx->p2p.world = 1;
     int rc = launch_trim(ctx, (uint32_t)n);
     ctx->n_ranks = saved_ranks;
+    ctx->p2p = saved_p2p;
     if (rc != ICPB_OK) return rc;
     CK(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(IcpState), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -1327,6 +1344,49 @@ int icpb_nccl_unique_id(uint8_t id_out[ICPB_NCCL_ID_BYTES])
     nccl_uid_t id;
     if (g_nccl.GetUniqueId(&id) != 0) return ICPB_ERR_NCCL;
     memcpy(id_out, &id, ICPB_NCCL_ID_BYTES);
+    return ICPB_OK;
+}
+
+int icpb_p2p_export(icpb_ctx *ctx, uint8_t handle_out[ICPB_IPC_HANDLE_BYTES])
+{
+    if (!ctx || !handle_out) return ICPB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == ICPB_IPC_HANDLE_BYTES, "IPC handle size");
+    if (!ctx->p2p_local) {
+        CK(cudaMalloc((void **)&ctx->p2p_local, P2P_BUFFER_WORDS * sizeof(uint32_t)));
+        CK(cudaMemset(ctx->p2p_local, 0, P2P_BUFFER_WORDS * sizeof(uint32_t)));
+        CK(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, ctx->p2p_local));
+    memcpy(handle_out, &h, ICPB_IPC_HANDLE_BYTES);
+    return ICPB_OK;
+}
+
+int icpb_p2p_connect(icpb_ctx *ctx, int n_ranks, int rank, const uint8_t *handles)
+{
+    if (!ctx || n_ranks < 1 || n_ranks > P2P_MAX_RANKS || rank < 0 || rank >= n_ranks || !handles) return ICPB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->p2p_local) return ICPB_ERR_ARG; // icpb_p2p_export first
+    memset(&ctx->p2p, 0, sizeof(ctx->p2p));
+    ctx->p2p.world = n_ranks;
+    ctx->p2p.rank = rank;
+    for (int r = 0; r < n_ranks; ++r) {
+        if (r == rank) {
+            ctx->p2p.peer[r] = ctx->p2p_local;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * ICPB_IPC_HANDLE_BYTES, ICPB_IPC_HANDLE_BYTES);
+        void *p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->p2p_mapped[r] = p;
+        ctx->p2p.peer[r] = (uint32_t *)p;
+    }
+    ctx->n_ranks = n_ranks;
+    ctx->rank = rank;
+    ctx->use_p2p = n_ranks > 1;
+    if (n_ranks == 1) ctx->p2p.world = 1;
     return ICPB_OK;
 }
 

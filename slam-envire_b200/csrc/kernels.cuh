@@ -344,6 +344,58 @@ __global__ void __launch_bounds__(SEARCH_THREADS)
 }
 
 // ---------------------------------------------------------------------------
+// Fused collectives over NVLink peer memory (multi-GPU, one process per GPU).
+// Every rank owns an exchange buffer that its peers map through CUDA IPC.  A collective is "one-shot": the LAST
+// block of the producing kernel stores this rank's small vector into its row of EVERY peer's buffer (plain stores
+// over NVLink), raises a sequence flag there, waits until all rows of its own buffer carry the same sequence number
+// and sums the rows in rank order -- identical arithmetic, hence identical results, on every rank.  No separate
+// collective launch, no host involvement; two buffer halves alternate (a rank can be at most one collective ahead
+// of a peer, because it needs that peer's contribution to finish).
+// ---------------------------------------------------------------------------
+constexpr int P2P_MAX_RANKS = 8;
+constexpr int P2P_ROW_WORDS = 2112; // 2048 histogram bins + 64 spare words (found count, ...)
+constexpr size_t P2P_DATA_WORDS = 2ull * P2P_MAX_RANKS * P2P_ROW_WORDS;
+constexpr size_t P2P_BUFFER_WORDS = P2P_DATA_WORDS + 2 * P2P_MAX_RANKS + 64;
+struct P2PView {
+    int world, rank;
+    uint32_t *peer[P2P_MAX_RANKS]; // base of every rank's exchange buffer (peer[rank] is the local one)
+};
+__device__ __forceinline__ uint32_t *p2p_flags(uint32_t *base) { return base + P2P_DATA_WORDS; }
+
+// Called by all threads of ONE block per rank.  src: nwords 32-bit words in local global memory.
+// Returns the local rows of this collective: row q (from rank q) starts at ret + q * P2P_ROW_WORDS; read with __ldcv.
+__device__ const uint32_t *p2p_exchange(const P2PView &v, IcpState *st, const uint32_t *src, int nwords)
+{
+    const uint32_t seq = st->comm_seq + 1u;
+    const int par = (int)(seq & 1u);
+    __syncthreads(); // everyone has read comm_seq
+    for (int p = 0; p < v.world; ++p) {
+        uint32_t *dst = v.peer[p] + ((size_t)par * P2P_MAX_RANKS + v.rank) * P2P_ROW_WORDS;
+        for (int i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < v.world) {
+        __threadfence_system();
+        volatile uint32_t *f = p2p_flags(v.peer[threadIdx.x]) + par * P2P_MAX_RANKS + v.rank;
+        *f = seq; // my row has landed in peer threadIdx.x
+        volatile uint32_t *mine = p2p_flags(v.peer[v.rank]) + par * P2P_MAX_RANKS + threadIdx.x;
+        const long long t0 = clock64();
+        while ((int)(*mine - seq) < 0) {
+            if (clock64() - t0 > 20000000000ll) { // ~10 s: a peer is gone; give up instead of hanging the GPU
+                st->comm_error = 1u;
+                st->done = 1; // every later launch of this align becomes a no-op
+                break;
+            }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) st->comm_seq = seq;
+    return v.peer[v.rank] + (size_t)par * P2P_MAX_RANKS * P2P_ROW_WORDS;
+}
+
+// ---------------------------------------------------------------------------
 // K4: radix select.  Distances are non-negative doubles (or +inf = no pair),
 // so their bit patterns order like unsigned integers.
 // ---------------------------------------------------------------------------
@@ -358,7 +410,8 @@ __constant__ int c_sel_t_bits[SEL_T_PASSES] = {11, 11, 10};
 
 // the last block of a pass (or a stand-alone 1-block launch after the histogram
 // all-reduce) picks the bucket holding the k-th smallest key and narrows the prefix
-__device__ void select_pick(IcpState *st, uint32_t *ghist, int pass, bool tie_mode, uint32_t *smem /* >= 34 */)
+__device__ void select_pick(IcpState *st, uint32_t *ghist, int pass, bool tie_mode, uint32_t *smem /* >= 34 */,
+                            const uint32_t *rows = nullptr, int world = 1, int rank = 0)
 {
     const int bits = tie_mode ? c_sel_t_bits[pass] : c_sel_d_bits[pass];
     const int shift = tie_mode ? c_sel_t_shift[pass] : c_sel_d_shift[pass];
@@ -419,10 +472,20 @@ __device__ void select_pick(IcpState *st, uint32_t *ghist, int pass, bool tie_mo
                 st->sel_krem = krem - run;
                 if (pass == SEL_D_PASSES - 1) {
                     st->tau = __longlong_as_double((long long)prefix);
-                    st->cnt_eq = c[j];
-                    st->quota = krem - run;
-                    st->need_tie = (krem - run) < (unsigned long long)c[j] ? 1u : 0u;
-                    st->p_cut = 0x100000000ll;
+                    unsigned long long cnt = c[j], quota = krem - run;
+                    if (rows && quota < cnt) {
+                        // ties are kept in global pair order = lower ranks first: this rank's share of the quota
+                        unsigned long long before = 0;
+                        for (int q = 0; q < rank; ++q) before += __ldcv(rows + (size_t)q * P2P_ROW_WORDS + b);
+                        const unsigned long long local = __ldcv(rows + (size_t)rank * P2P_ROW_WORDS + b);
+                        quota = quota > before ? quota - before : 0ull;
+                        if (quota > local) quota = local;
+                        cnt = local;
+                    }
+                    st->cnt_eq = cnt;
+                    st->quota = quota;
+                    st->need_tie = (quota > 0 && quota < cnt) ? 1u : 0u;
+                    st->p_cut = (rows && quota == 0 && cnt > 0 && (krem - run) < (unsigned long long)c[j]) ? -1ll : 0x100000000ll;
                 }
             } else {
                 const unsigned prefix = (pass == 0 ? 0u : st->tie_prefix) | ((unsigned)b << shift);
@@ -441,7 +504,7 @@ __device__ void select_pick(IcpState *st, uint32_t *ghist, int pass, bool tie_mo
 __global__ void __launch_bounds__(SEL_THREADS)
     select_kernel(const double *__restrict__ nn_d, const uint32_t *__restrict__ perm, uint32_t n,
                   IcpState *__restrict__ st, uint32_t *__restrict__ ghist, int pass, int tie_mode, int fused_pick,
-                  int ticket_slot)
+                  int ticket_slot, const P2PView p2p)
 {
     if (st->done) return;
     if (tie_mode && !st->need_tie) return;
@@ -496,6 +559,25 @@ __global__ void __launch_bounds__(SEL_THREADS)
     if (!is_last) return;
     __threadfence();
     if (threadIdx.x == 0) st->tickets[ticket_slot] = 0;
+    if (p2p.world > 1 && !tie_mode) {
+        // fused all-reduce of the digit histogram (+ the found count in pass 0) over peer memory
+        if (pass == 0 && threadIdx.x == 0) ghist[SEL_MAX_BINS] = (uint32_t)st->found;
+        __syncthreads();
+        const uint32_t *rows = p2p_exchange(p2p, st, ghist, bins + (pass == 0 ? 1 : 0) * (SEL_MAX_BINS - bins + 1));
+        for (int b = threadIdx.x; b < bins; b += SEL_THREADS) {
+            uint32_t v = 0;
+            for (int q = 0; q < p2p.world; ++q) v += __ldcv(rows + (size_t)q * P2P_ROW_WORDS + b);
+            ghist[b] = v;
+        }
+        if (pass == 0 && threadIdx.x == 0) {
+            unsigned long long f = 0;
+            for (int q = 0; q < p2p.world; ++q) f += __ldcv(rows + (size_t)q * P2P_ROW_WORDS + SEL_MAX_BINS);
+            st->found = f;
+        }
+        __syncthreads();
+        select_pick(st, ghist, pass, false, scan_smem, rows, p2p.world, p2p.rank);
+        return;
+    }
     select_pick(st, ghist, pass, tie_mode != 0, scan_smem);
 }
 
@@ -557,7 +639,7 @@ __global__ void __launch_bounds__(MOM_THREADS, 3)
                    const double *__restrict__ sz, uint32_t n, IcpState *__restrict__ st,
                    const uint32_t *__restrict__ nn_pos, const double *__restrict__ nn_d,
                    const uint32_t *__restrict__ perm, double *__restrict__ partials, double *__restrict__ trace,
-                   int trace_cap, int fused_pose)
+                   int trace_cap, int fused_pose, const P2PView p2p)
 {
     if (st->done) return;
     __shared__ double sm[MOM_THREADS / 32][ICPB_NSUMS];
@@ -624,6 +706,20 @@ __global__ void __launch_bounds__(MOM_THREADS, 3)
         if (lane == 0) st->sums[k] = v;
     }
     __syncthreads();
+    if (p2p.world > 1) {
+        // fused all-reduce of the 17 moment sums over peer memory; rows are summed in rank order on every rank
+        const uint32_t *rows = p2p_exchange(p2p, st, reinterpret_cast<const uint32_t *>(st->sums), 2 * ICPB_NSUMS);
+        if (threadIdx.x < ICPB_NSUMS) {
+            double v = 0.0;
+            for (int q = 0; q < p2p.world; ++q) {
+                const uint32_t *r = rows + (size_t)q * P2P_ROW_WORDS + 2 * threadIdx.x;
+                const unsigned long long bits = (unsigned long long)__ldcv(r) | ((unsigned long long)__ldcv(r + 1) << 32);
+                v += __longlong_as_double((long long)bits);
+            }
+            st->sums[threadIdx.x] = v;
+        }
+        __syncthreads();
+    }
     if (threadIdx.x == 0) {
         st->tickets[15] = 0;
         if (fused_pose) {

@@ -47,6 +47,8 @@ struct IcpState {
     int executed; // loop bodies executed so far (== trace rows)
     int warm;     // nn_pos[] of the previous iteration is valid
     unsigned int tickets[16];
+    unsigned int comm_seq;   // collectives completed on the peer-memory path (same on every rank)
+    unsigned int comm_error; // a peer did not show up within the spin budget
 };
 
 ICPB_HD void icpb_aff_identity(double *a)
@@ -180,6 +182,7 @@ ICPB_HD void icpb_state_init(IcpState &s, const double *Cl2g, unsigned long long
     s.p_cut = 0x100000000ll;
     s.need_tie = 0;
     for (int i = 0; i < 16; ++i) s.tickets[i] = 0;
+    s.comm_error = 0; // comm_seq keeps counting across aligns
     s.done = icpb_loop_continues(s) ? 0 : 1;
 }
 

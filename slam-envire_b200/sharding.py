@@ -38,13 +38,23 @@ def shard_source(xyz, density, world, rank):
     return np.ascontiguousarray(xyz[sel[lo:hi]]), adapter_size(len(xyz), density)
 
 
-def init_comm(icp, dist, device):
-    """Bootstrap the library's NCCL communicator through an existing torch.distributed process group."""
+def init_comm(icp, dist, device, mode="p2p"):
+    """Connect the ranks' contexts through an existing torch.distributed process group.
+
+    mode "p2p": exchange CUDA-IPC handles; the per-iteration collectives then run fused inside the kernels over NVLink
+    peer memory (<= 8 ranks on one box).  mode "nccl": the library opens its own NCCL communicator instead."""
     import importlib
     import torch
     pkg = importlib.import_module("slam-envire_b200")
     world, rank = dist.get_world_size(), dist.get_rank()
     if world == 1:
+        return
+    if mode == "p2p":
+        mine = torch.frombuffer(bytearray(icp.p2p_export()), dtype=torch.uint8).to(device)
+        allh = [torch.zeros(pkg.IPC_HANDLE_BYTES, dtype=torch.uint8, device=device) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        icp.p2p_connect(world, rank, b"".join(h.cpu().numpy().tobytes() for h in allh))
+        dist.barrier()
         return
     uid = torch.zeros(pkg.NCCL_ID_BYTES, dtype=torch.uint8, device=device)
     if rank == 0:

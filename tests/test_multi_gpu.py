@@ -13,13 +13,17 @@ from conftest import ROOT
 
 
 @pytest.mark.gpu
-def test_sharded_align_matches_single_gpu():
+@pytest.mark.parametrize("mode", ["p2p", "nccl"])
+def test_sharded_align_matches_single_gpu(mode):
+    """p2p: collectives fused into the kernels over NVLink peer memory (CUDA IPC); nccl: the library's own communicator."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, ICPB_COMM=mode)
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                          "--master-addr", "127.0.0.1", "--master-port", "29533",
-                          os.path.join(ROOT, "tools", "multi_gpu_check.py")], capture_output=True, text=True, timeout=600)
+                          "--master-addr", "127.0.0.1", "--master-port", "29533" if mode == "p2p" else "29534",
+                          os.path.join(ROOT, "tools", "multi_gpu_check.py")], capture_output=True, text=True, timeout=600,
+                         env=env)
     assert "MULTI_GPU_CHECK PASS" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
 
 
