@@ -166,18 +166,35 @@ ICPB_HD void icpb_scan_cell(const GridView &g, int cx, int cy, int cz, double qx
     const uint32_t c = ((uint32_t)cz * (uint32_t)g.dim[0][1] + (uint32_t)cy) * (uint32_t)g.dim[0][0] + (uint32_t)cx;
     const uint32_t s = g.cell_start[c], e = g.cell_start[c + 1];
     ICPB_COUNT(cells);
-    for (uint32_t p = s; p < e; ++p) {
-        ICPB_COUNT(cands);
-        const FPoint f = g.ptsf[p];
-        const float dx = ux - f.x, dy = uy - f.y, dz = uz - f.z;
-        const float d2f = dx * dx + dy * dy + dz * dz;
-        if (d2f > candf) continue; // cannot be nearer than the best so far (nor tie with it)
-        ICPB_COUNT(exact);
-        const double before = bd2;
-        icpb_nn_eval(g.pts[p], p, qx, qy, qz, bd2, bidx, bpos);
-        if (bd2 < before) {
-            boundf = icpb_bound_cells((dbox2s < bd2) ? dbox2s : bd2, inv_h2);
-            candf = icpb_cand_radius2(boundf, slack);
+    // four candidates per step: the loads are issued together (memory-level parallelism), the tail repeats the last one
+    for (uint32_t p = s; p < e; p += 4) {
+        const uint32_t last = e - 1;
+        const uint32_t p1 = p + 1 < e ? p + 1 : last, p2 = p + 2 < e ? p + 2 : last, p3 = p + 3 < e ? p + 3 : last;
+        const FPoint f0 = g.ptsf[p], f1 = g.ptsf[p1], f2 = g.ptsf[p2], f3 = g.ptsf[p3];
+        float dx, dy, dz;
+        dx = ux - f0.x, dy = uy - f0.y, dz = uz - f0.z;
+        const float d0 = dx * dx + dy * dy + dz * dz;
+        dx = ux - f1.x, dy = uy - f1.y, dz = uz - f1.z;
+        const float d1 = dx * dx + dy * dy + dz * dz;
+        dx = ux - f2.x, dy = uy - f2.y, dz = uz - f2.z;
+        const float d2 = dx * dx + dy * dy + dz * dz;
+        dx = ux - f3.x, dy = uy - f3.y, dz = uz - f3.z;
+        const float d3 = dx * dx + dy * dy + dz * dz;
+        if (fminf(fminf(d0, d1), fminf(d2, d3)) > candf) continue; // none can be nearer than the best so far (nor tie)
+#ifdef __CUDACC__
+#pragma unroll
+#endif
+        for (int k = 0; k < 4; ++k) {
+            const float dk = k == 0 ? d0 : (k == 1 ? d1 : (k == 2 ? d2 : d3));
+            const uint32_t pk = k == 0 ? p : (k == 1 ? p1 : (k == 2 ? p2 : p3));
+            if (dk > candf || (k > 0 && pk != p + (uint32_t)k)) continue; // filtered, or a repeated tail slot
+            ICPB_COUNT(exact);
+            const double before = bd2;
+            icpb_nn_eval(g.pts[pk], pk, qx, qy, qz, bd2, bidx, bpos);
+            if (bd2 < before) {
+                boundf = icpb_bound_cells((dbox2s < bd2) ? dbox2s : bd2, inv_h2);
+                candf = icpb_cand_radius2(boundf, slack);
+            }
         }
     }
 }
