@@ -303,3 +303,39 @@ def test_growing_model_merge_append(pkg, oracle, synth):
     assert r.iter == r_ref.iter and r.pairs == r_ref.pairs
     assert_transform_close(r.matrix(), r_ref.matrix(), 30.0)
     grow.close()
+
+
+def test_c_abi_error_paths(pkg):
+    """Status codes instead of exceptions across the boundary; ICPConfiguration-independent GPU knobs."""
+    import ctypes as C
+    L = pkg.load_library()
+    icp = pkg.Icp(0)
+    h = icp._h
+    dp = C.POINTER(C.c_double)
+    assert L.icpb_set_option(h, b"no_such_option", 1.0) == pkg.ERR_ARG
+    for key in (b"cell_size", b"target_pts_per_cell", b"max_cells", b"warm_start", b"sort_source", b"run_ahead", b"profile",
+                b"growth_margin", b"merge_append"):
+        v = C.c_double()
+        assert L.icpb_get_option(h, key, C.byref(v)) == pkg.OK
+        assert L.icpb_set_option(h, key, v.value) == pkg.OK
+    prm, res = pkg.Params(5, 1e-4, 1e-5, 0.9), pkg.Result()
+    assert L.icpb_align_resident(h, C.byref(prm), C.byref(res)) == pkg.ERR_NO_SOURCE
+    pts = np.random.default_rng(0).normal(size=(100, 3))
+    T = np.eye(4).reshape(16)
+    assert L.icpb_model_add(h, pts.ctypes.data_as(dp), 100, T.ctypes.data_as(dp), 0.0) == pkg.ERR_ARG  # density <= 0
+    assert L.icpb_model_add(h, None, 100, T.ctypes.data_as(dp), 1.0) == pkg.ERR_ARG
+    icp.add_to_model(pts)
+    r = icp.align(pts + 0.01, max_iter=3)
+    n = C.c_size_t()
+    buf = np.zeros(10)
+    assert L.icpb_pairs_distance(h, buf.ctypes.data_as(dp), 10, C.byref(n)) == pkg.ERR_CAPACITY and n.value == r.pairs
+    assert L.icpb_trace(h, buf.ctypes.data_as(dp), 0, C.byref(n)) == pkg.ERR_CAPACITY
+    assert L.icpb_strerror(pkg.ERR_NOT_ENOUGH_PAIRS) == b"not enough pairs to get transform"
+    assert L.icpb_create(C.byref(C.c_void_p()), 10 ** 6) == pkg.ERR_ARG  # no such device
+    # options that change the schedule never change the result
+    base = icp.align(pts + 0.01, max_iter=6, min_mse=0, min_mse_diff=-1).matrix()
+    for key, val in (("warm_start", 0), ("sort_source", 0), ("run_ahead", 8), ("profile", 0), ("cell_size", 0.5)):
+        icp.set_option(key, val)
+        again = icp.align(pts + 0.01, max_iter=6, min_mse=0, min_mse_diff=-1).matrix()
+        assert np.abs(again - base).max() < 1e-12, key
+    icp.close()
