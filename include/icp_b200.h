@@ -150,6 +150,13 @@ int icpb_find_pairs(icpb_ctx *, const double *q_xyz_aos, size_t n, double d_box,
  * *n_ties_kept = how many entries equal to tau are kept */
 int icpb_trim(icpb_ctx *, const double *dist, size_t n, size_t n_po, double *tau, size_t *kept, size_t *n_ties_kept);
 
+/* K4+K5+K6 on caller-supplied pairs: Pairs::add xN, Pairs::trim(n_po), Pairs::getTransform (icp/icp.cpp:12-102).
+ * x = model points, p = source points (fp64 AoS), dist = their distances.  Outputs the transform that moves p onto x
+ * (col-major 4x4), the mean square distance over the kept pairs, tau = largest kept distance and the kept count.
+ * Returns ICPB_ERR_NOT_ENOUGH_PAIRS when fewer than 3 pairs are left (where the reference throws). */
+int icpb_pairs_transform(icpb_ctx *, const double *x_aos, const double *p_aos, const double *dist, size_t n, size_t n_po,
+                         double T_out[16], double *mse, double *tau, size_t *kept);
+
 /* ---- multi-GPU (one process per GPU; source sharded, model replicated) - */
 /* rank 0 creates the id and ships the ICPB_NCCL_ID_BYTES to its peers by any
  * channel (torch.distributed broadcast in bench.py), then every rank calls

@@ -26,7 +26,7 @@ SYMBOLS = [
     "icpb_create", "icpb_destroy", "icpb_strerror", "icpb_last_error", "icpb_version", "icpb_set_option",
     "icpb_get_option", "icpb_model_add", "icpb_model_add_ean", "icpb_source_upload_ean", "icpb_model_clear", "icpb_model_size", "icpb_model_build",
     "icpb_source_upload", "icpb_align_resident", "icpb_align", "icpb_pairs_distance", "icpb_debug_pairs",
-    "icpb_trace", "icpb_last_timing", "icpb_iteration_times", "icpb_find_pairs", "icpb_trim", "icpb_nccl_unique_id", "icpb_comm_init",
+    "icpb_trace", "icpb_last_timing", "icpb_iteration_times", "icpb_find_pairs", "icpb_trim", "icpb_pairs_transform", "icpb_nccl_unique_id", "icpb_comm_init",
     "icpb_source_upload_shard", "icpb_p2p_export", "icpb_p2p_connect",
 ]
 
@@ -101,6 +101,7 @@ def load_library():
     L.icpb_iteration_times.argtypes = [vp, dp, C.c_size_t, sp]
     L.icpb_find_pairs.argtypes = [vp, dp, C.c_size_t, C.c_double, up, dp]
     L.icpb_trim.argtypes = [vp, dp, C.c_size_t, C.c_size_t, dp, sp, sp]
+    L.icpb_pairs_transform.argtypes = [vp, dp, dp, dp, C.c_size_t, C.c_size_t, dp, dp, dp, sp]
     L.icpb_nccl_unique_id.argtypes = [C.POINTER(C.c_uint8)]
     L.icpb_comm_init.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_uint8)]
     L.icpb_p2p_export.argtypes = [vp, C.POINTER(C.c_uint8)]
@@ -284,6 +285,20 @@ class Icp:
         kept, ties = C.c_size_t(), C.c_size_t()
         self._ck(self._L.icpb_trim(self._h, ap, a.shape[0], n_po, C.byref(tau), C.byref(kept), C.byref(ties)))
         return tau.value, kept.value, ties.value
+
+    def pairs_transform(self, x, p, dist, n_po):
+        """Pairs::add xN + trim(n_po) + getTransform on the device.  Returns (T 4x4, mse, tau, kept)."""
+        x_, xp = _d(x)
+        p_, pp = _d(p)
+        d_, dp_ = _d(dist)
+        T = np.zeros(16)
+        mse, tau, kept = C.c_double(), C.c_double(), C.c_size_t()
+        rc = self._L.icpb_pairs_transform(self._h, xp, pp, dp_, len(d_), n_po, T.ctypes.data_as(C.POINTER(C.c_double)),
+                                          C.byref(mse), C.byref(tau), C.byref(kept))
+        if rc == ERR_NOT_ENOUGH_PAIRS:
+            raise IcpError(rc, "not enough pairs to get transform")
+        self._ck(rc)
+        return T.reshape(4, 4).T.copy(), mse.value, tau.value, kept.value
 
     # -- multi-GPU ----------------------------------------------------------
     def p2p_export(self):

@@ -983,8 +983,7 @@ static int launch_trim(icpb_ctx *ctx, uint32_t n)
     if (!fused) // pairs found on all ranks
         NK(g_nccl.AllReduce(&ctx->d_state->found, &ctx->d_state->found, 1, NCCL_UINT64, NCCL_SUM, ctx->comm, s));
     for (int p = 0; p < SEL_D_PASSES; ++p) {
-        select_kernel<<<blocks, SEL_THREADS, 0, s>>>(ctx->nn_d.p, ctx->src_perm.p, n, ctx->d_state, ctx->d_ghist, p, 0,
-                                                     fused, p, ctx->p2p);
+        select_kernel<<<blocks, SEL_THREADS, 0, s>>>(ctx->nn_d.p, n, ctx->d_state, ctx->d_ghist, p, fused, ctx->p2p);
         CKL();
         ++ctx->launches;
         if (!fused) {
@@ -1332,6 +1331,79 @@ int icpb_trim(icpb_ctx *ctx, const double *dist, size_t n, size_t n_po, double *
     ctx->have_source = false;
     ctx->last_valid = false;
     return ICPB_OK;
+}
+
+__global__ void pairs_setup_kernel(IcpState *st, unsigned long long n_po, unsigned long long found)
+{
+    double I[12];
+    icpb_aff_identity(I);
+    icpb_state_init(*st, I, 1, -1.0, -1.0, 1.0, n_po); // one loop body, identity source transform
+    st->found = found;
+    st->tie_local = 0;
+}
+
+int icpb_pairs_transform(icpb_ctx *ctx, const double *x, const double *p, const double *dist, size_t n, size_t n_po,
+                         double T_out[16], double *mse, double *tau, size_t *kept)
+{
+    if (!ctx || ((!x || !p || !dist) && n) || !T_out || !mse || !tau || !kept) return ICPB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (n >= 0xFFFFFFF0ull) return ICPB_ERR_ARG;
+    cudaStream_t s = ctx->stream;
+    const size_t m = std::max<size_t>(n, 1);
+    CK(ctx->stage.ensure(3 * m));
+    CK(ctx->sx.ensure(m));
+    CK(ctx->sy.ensure(m));
+    CK(ctx->sz.ensure(m));
+    CK(ctx->nn_pos.ensure(m));
+    CK(ctx->nn_d.ensure(m));
+    CK(ctx->src_perm.ensure(m));
+    CK(ctx->pts2.ensure(m));
+    const unsigned mom_blocks = std::max(1u, std::min(grid_for(n, MOM_THREADS), 148u * 6u));
+    CK(ctx->partials.ensure((size_t)mom_blocks * ICPB_NSUMS));
+    if (n) {
+        CK(cudaMemcpyAsync(ctx->stage.p, p, 3 * n * sizeof(double), cudaMemcpyHostToDevice, s));
+        aos_to_soa_kernel<<<grid_for(n, 256), 256, 0, s>>>(ctx->stage.p, n, ctx->sx.p, ctx->sy.p, ctx->sz.p);
+        CK(cudaStreamSynchronize(s)); // stage is reused below
+        CK(cudaMemcpyAsync(ctx->stage.p, x, 3 * n * sizeof(double), cudaMemcpyHostToDevice, s));
+        pack_points_kernel<<<grid_for(n, 256), 256, 0, s>>>(ctx->stage.p, (uint32_t)n, ctx->pts2.p);
+        iota_kernel<<<grid_for(n, 256), 256, 0, s>>>(ctx->nn_pos.p, (uint32_t)n);
+        iota_kernel<<<grid_for(n, 256), 256, 0, s>>>(ctx->src_perm.p, (uint32_t)n);
+        CK(cudaMemcpyAsync(ctx->nn_d.p, dist, n * sizeof(double), cudaMemcpyHostToDevice, s));
+        CKL();
+    }
+    size_t found = 0;
+    for (size_t i = 0; i < n; ++i) found += isfinite(dist[i]) ? 1 : 0;
+    pairs_setup_kernel<<<1, 1, 0, s>>>(ctx->d_state, n_po, found);
+    CKL();
+    const int saved_ranks = ctx->n_ranks;
+    const P2PView saved_p2p = ctx->p2p;
+    ctx->n_ranks = 1;
+    ctx->p2p.world = 1;
+    int rc = launch_trim(ctx, (uint32_t)n);
+    GridView gv;
+    memset(&gv, 0, sizeof(gv));
+    gv.pts = ctx->pts2.p;
+    gv.n = (uint32_t)n;
+    if (rc == ICPB_OK) {
+        moments_kernel<<<mom_blocks, MOM_THREADS, 0, s>>>(gv, ctx->sx.p, ctx->sy.p, ctx->sz.p, (uint32_t)n, ctx->d_state,
+                                                          ctx->nn_pos.p, ctx->nn_d.p, ctx->src_perm.p, ctx->partials.p,
+                                                          nullptr, 0, 1, ctx->p2p);
+        ctx->launches += 1;
+    }
+    ctx->n_ranks = saved_ranks;
+    ctx->p2p = saved_p2p;
+    if (rc != ICPB_OK) return rc;
+    CKL();
+    CK(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(IcpState), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const IcpState &hs = *ctx->h_state;
+    aff12_to_cm(hs.C, T_out);
+    *mse = hs.mse;
+    *tau = hs.pairs > 0 ? hs.tau : NAN;
+    *kept = (size_t)hs.pairs;
+    ctx->have_source = false;
+    ctx->last_valid = false;
+    return hs.early ? ICPB_ERR_NOT_ENOUGH_PAIRS : ICPB_OK;
 }
 
 // ---------------------------------------------------------------------------

@@ -498,27 +498,25 @@ __device__ void select_pick(IcpState *st, uint32_t *ghist, int pass, bool tie_mo
     }
 }
 
-// One histogram pass.  tie_mode == 0: key = bits(nn_d[i]).  tie_mode == 1: key = perm[i] (the pair index)
-// restricted to entries with nn_d[i] == tau (decides WHICH equidistant pairs survive:
-// those at the lowest positions, i.e. a stable sort by (distance, pair index)).
+// One histogram pass over the distance bits (key = bits(nn_d[i]); digit `pass` of c_sel_d_*).  The last block to finish
+// (ticket) narrows the prefix: locally, or after the fused peer-memory all-reduce, or -- NCCL mode -- not at all
+// (fused_pick == 0: select_pick_kernel runs after ncclAllReduce).
 __global__ void __launch_bounds__(SEL_THREADS)
-    select_kernel(const double *__restrict__ nn_d, const uint32_t *__restrict__ perm, uint32_t n,
-                  IcpState *__restrict__ st, uint32_t *__restrict__ ghist, int pass, int tie_mode, int fused_pick,
-                  int ticket_slot, const P2PView p2p)
+    select_kernel(const double *__restrict__ nn_d, uint32_t n, IcpState *__restrict__ st, uint32_t *__restrict__ ghist,
+                  int pass, int fused_pick, const P2PView p2p)
 {
     if (st->done) return;
-    if (tie_mode && !st->need_tie) return;
-    if (!tie_mode && pass > 0 && st->sel_krem == 0) return; // nothing to select this iteration
+    if (pass > 0 && st->sel_krem == 0) return; // nothing to select this iteration
     __shared__ uint32_t hist[SEL_MAX_BINS];
     __shared__ uint32_t scan_smem[34];
     __shared__ int is_last;
-    const int bits = tie_mode ? c_sel_t_bits[pass] : c_sel_d_bits[pass];
-    const int shift = tie_mode ? c_sel_t_shift[pass] : c_sel_d_shift[pass];
+    const int bits = c_sel_d_bits[pass];
+    const int shift = c_sel_d_shift[pass];
     const int bins = 1 << bits;
     for (int b = threadIdx.x; b < bins; b += SEL_THREADS) hist[b] = 0;
     __syncthreads();
     const unsigned bin_mask = (unsigned)bins - 1u;
-    if (!tie_mode) {
+    {
         const unsigned long long prefix = pass == 0 ? 0ull : st->sel_prefix;
         const int hs = shift + bits; // bits above the current digit must match the prefix
         // four independent loads in flight per thread before the (dependent) shared-memory atomics
@@ -537,16 +535,6 @@ __global__ void __launch_bounds__(SEL_THREADS)
                     atomicAdd(&hist[(unsigned)(key[u] >> shift) & bin_mask], 1u);
             }
         }
-    } else {
-        const unsigned long long tau_bits = (unsigned long long)__double_as_longlong(st->tau);
-        const unsigned prefix = pass == 0 ? 0u : st->tie_prefix;
-        const int hs = shift + bits;
-        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-            const unsigned long long key = (unsigned long long)__double_as_longlong(nn_d[i]);
-            if (key != tau_bits) continue;
-            const uint32_t pi = perm[i]; // pair index in the adapter's visiting order
-            if (pass == 0 || hs >= 32 || (pi >> hs) == (prefix >> hs)) atomicAdd(&hist[(pi >> shift) & bin_mask], 1u);
-        }
     }
     __syncthreads();
     for (int b = threadIdx.x; b < bins; b += SEL_THREADS)
@@ -554,16 +542,16 @@ __global__ void __launch_bounds__(SEL_THREADS)
     if (!fused_pick) return;
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicAdd(&st->tickets[ticket_slot], 1u) == gridDim.x - 1) ? 1 : 0;
+    if (threadIdx.x == 0) is_last = (atomicAdd(&st->tickets[pass], 1u) == gridDim.x - 1) ? 1 : 0;
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    if (threadIdx.x == 0) st->tickets[ticket_slot] = 0;
-    if (p2p.world > 1 && !tie_mode) {
+    if (threadIdx.x == 0) st->tickets[pass] = 0;
+    if (p2p.world > 1) {
         // fused all-reduce of the digit histogram (+ the found count in pass 0) over peer memory
         if (pass == 0 && threadIdx.x == 0) ghist[SEL_MAX_BINS] = (uint32_t)st->found;
         __syncthreads();
-        const uint32_t *rows = p2p_exchange(p2p, st, ghist, bins + (pass == 0 ? 1 : 0) * (SEL_MAX_BINS - bins + 1));
+        const uint32_t *rows = p2p_exchange(p2p, st, ghist, pass == 0 ? SEL_MAX_BINS + 1 : bins);
         for (int b = threadIdx.x; b < bins; b += SEL_THREADS) {
             uint32_t v = 0;
             for (int q = 0; q < p2p.world; ++q) v += __ldcv(rows + (size_t)q * P2P_ROW_WORDS + b);
@@ -578,7 +566,7 @@ __global__ void __launch_bounds__(SEL_THREADS)
         select_pick(st, ghist, pass, false, scan_smem, rows, p2p.world, p2p.rank);
         return;
     }
-    select_pick(st, ghist, pass, tie_mode != 0, scan_smem);
+    select_pick(st, ghist, pass, false, scan_smem);
 }
 
 // stand-alone pick (multi-GPU: runs after the histogram all-reduce)
@@ -821,6 +809,18 @@ __global__ void gather_soa_kernel(const double *__restrict__ aos, const uint32_t
     x[j] = aos[3 * s];
     y[j] = aos[3 * s + 1];
     z[j] = aos[3 * s + 2];
+}
+// stand-alone Pairs::getTransform entry: model points of the pairs as an MPoint array (pair i <-> position i)
+__global__ void pack_points_kernel(const double *__restrict__ aos, uint32_t n, MPoint *__restrict__ out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    MPoint m;
+    m.x = aos[3 * (size_t)i];
+    m.y = aos[3 * (size_t)i + 1];
+    m.z = aos[3 * (size_t)i + 2];
+    m.idx = i;
+    out[i] = m;
 }
 __global__ void iota_kernel(uint32_t *__restrict__ v, uint32_t n)
 {

@@ -32,6 +32,62 @@
 namespace envire {
 namespace icp {
 
+/** envire::icp::Pairs (icp/icp.hpp:32-76, icp/icp.cpp:12-119): a set of point pairs with their distances; trim() keeps the
+ * n_po closest and returns the largest kept distance, getTransform() returns the reference's (non-Horn) rigid fit of p onto
+ * x.  Same public members (x, p, mse) and methods; the sort / sums / pose solve run on the device through
+ * icpb_trim / icpb_pairs_transform (used e.g. by icp/ransac.hpp:40-50 on 3-point samples). */
+class Pairs {
+public:
+    const static unsigned int MIN_PAIRS = 3;
+    explicit Pairs(icpb_ctx *ctx) : mse(0), ctx_(ctx), n_po_(static_cast<size_t>(-1)) {}
+    void add(const Eigen::Vector3d &a, const Eigen::Vector3d &b, double dist)
+    {
+        x.push_back(a);
+        p.push_back(b);
+        dist_.push_back(dist);
+    }
+    double trim(size_t n_po)
+    {
+        n_po_ = n_po;
+        double tau = std::numeric_limits<double>::quiet_NaN();
+        size_t kept = 0, ties = 0;
+        if (icpb_trim(ctx_, dist_.data(), dist_.size(), n_po, &tau, &kept, &ties) != ICPB_OK) throw std::runtime_error(icpb_last_error(ctx_));
+        kept_ = kept;
+        return tau;
+    }
+    Eigen::Affine3d getTransform()
+    {
+        if (size() < MIN_PAIRS) throw std::runtime_error("not enough pairs to get transform");
+        double T[16], tau;
+        size_t kept;
+        const int rc = icpb_pairs_transform(ctx_, x.empty() ? 0 : x[0].data(), p.empty() ? 0 : p[0].data(), dist_.data(), dist_.size(),
+                                            n_po_ < dist_.size() ? n_po_ : dist_.size(), T, &mse, &tau, &kept);
+        if (rc == ICPB_ERR_NOT_ENOUGH_PAIRS) throw std::runtime_error("not enough pairs to get transform");
+        if (rc != ICPB_OK) throw std::runtime_error(icpb_last_error(ctx_));
+        Eigen::Matrix4d m;
+        for (int c = 0; c < 4; ++c)
+            for (int r = 0; r < 4; ++r) m(r, c) = T[c * 4 + r];
+        return Eigen::Affine3d(m);
+    }
+    double getMeanSquareError() const { return mse; }
+    size_t size() const { return n_po_ < dist_.size() ? kept_ : dist_.size(); }
+    void clear()
+    {
+        x.clear();
+        p.clear();
+        dist_.clear();
+        n_po_ = static_cast<size_t>(-1);
+    }
+
+    std::vector<Eigen::Vector3d> x, p;
+    double mse;
+
+private:
+    icpb_ctx *ctx_;
+    std::vector<double> dist_;
+    size_t n_po_, kept_ = 0;
+};
+
 /** Adapter concept of Trimmed<_Adapter,_FindPairs> (icp/icp.hpp:99-171) for envire::Pointcloud.  The iteration
  * interface (reset/hasNext/next/size) is kept for code that walks an adapter itself; TrimmedGPU hands the whole
  * vertex array, the density and C_local2global to the device instead of pulling points one by one. */

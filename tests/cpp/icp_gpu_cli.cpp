@@ -4,6 +4,7 @@
 //   icp_gpu_cli <model.bin> <src.bin> <T_src 16 col-major numbers> <density> fixed <max_iter> <min_mse> <min_mse_diff> <overlap>
 //   icp_gpu_cli <model.bin> <src.bin> <T_src ...>                  <density> golden <max_iter> <min_mse> <min_mse_diff> <alpha> <beta> <eps>
 // .bin = raw little-endian doubles, xyz triples.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -52,6 +53,25 @@ int main(int argc, char **argv)
     fm2->setTransform(Eigen::Affine3d(Ts));
     const size_t modified_before = env->modifiedCount();
 
+    if (!strcmp(argv[20], "pairs")) {
+        // envire::icp::Pairs mirror: add / trim / getTransform on the (model, source) points taken as pairs
+        try {
+            envire::icp::TrimmedGPU owner;
+            envire::icp::Pairs pairs(owner.handle());
+            const size_t n = std::min(mesh->vertices.size(), mesh2->vertices.size());
+            for (size_t i = 0; i < n; ++i)
+                pairs.add(mesh->vertices[i], mesh2->vertices[i], (mesh->vertices[i] - mesh2->vertices[i]).norm());
+            const double tau = pairs.trim((size_t)atoll(argv[21]));
+            const Eigen::Matrix4d M = pairs.getTransform().matrix();
+            printf("{\"T\": [");
+            for (int r = 0; r < 4; ++r) printf("%s[%.17g, %.17g, %.17g, %.17g]", r ? ", " : "", M(r, 0), M(r, 1), M(r, 2), M(r, 3));
+            printf("], \"tau\": %.17g, \"mse\": %.17g, \"size\": %zu}\n", tau, pairs.getMeanSquareError(), pairs.size());
+        } catch (const std::exception &e) {
+            printf("{\"error\": \"%s\"}\n", e.what());
+            return 1;
+        }
+        return 0;
+    }
     if (!strcmp(argv[20], "ean_sine")) {
         // the reference's setSineWave fixture WITH normals and scan-edge attributes, through TrimmedGPUEAN
         // (what the commented-out icp_test1 of test/unit/icp.cpp:132-145 drives through TrimmedKDEAN)

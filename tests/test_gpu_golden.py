@@ -101,3 +101,22 @@ def test_host_mirror_ean_matches_reference_golden(cli, tmp_path, name):
     assert_transform_close(np.array(out["fn_T"]), np.array(g["fn_T"]), 2.0)
     assert abs(out["mse"] - g["mse"]) <= 1e-5 * abs(g["mse"])
     assert abs(out["pd_sum"] - g["pd_sum"]) <= 1e-7 * abs(g["pd_sum"]) + 1e-12
+
+
+def test_host_mirror_pairs_class(cli, tmp_path, oracle):
+    """envire::icp::Pairs (add / trim / getTransform / getMeanSquareError / size) over the device stages."""
+    rng = np.random.default_rng(3)
+    x = rng.normal(size=(700, 3)) * [5, 3, 1]
+    p = x @ np.array([[0.995, -0.0998, 0], [0.0998, 0.995, 0], [0, 0, 1.0]]) + [0.2, -0.1, 0.05] + 0.01 * rng.normal(size=(700, 3))
+    mp, sp = str(tmp_path / "x.bin"), str(tmp_path / "p.bin")
+    x.tofile(mp)
+    p.tofile(sp)
+    n_po = 500
+    args = [cli, mp, sp] + ["%.17g" % v for v in np.eye(4).reshape(16)] + ["1", "pairs", str(n_po), "0", "0"]
+    out = json.loads(subprocess.check_output(args).decode())
+    assert "error" not in out, out
+    d = np.linalg.norm(x - p, axis=1)
+    order, tau = oracle.trim(d, n_po)
+    T, mse = oracle.get_transform(p, x, d, order)
+    assert out["size"] == n_po and out["tau"] == tau
+    assert np.allclose(np.array(out["T"]), T, atol=1e-10) and abs(out["mse"] - mse) <= 1e-12 * mse

@@ -339,3 +339,33 @@ def test_c_abi_error_paths(pkg):
         again = icp.align(pts + 0.01, max_iter=6, min_mse=0, min_mse_diff=-1).matrix()
         assert np.abs(again - base).max() < 1e-12, key
     icp.close()
+
+
+def test_pairs_transform_stage(icp, oracle, pkg):
+    """K4+K5+K6 in isolation against Pairs::trim + Pairs::getTransform of the oracle (and, in the dev container, of the
+    reference itself): the non-Horn pose solve, the moments, the trim threshold."""
+    rng = np.random.default_rng(0)
+    try:
+        from oracle import ref as R
+        have_ref = R.available()
+    except Exception:
+        have_ref = False
+    for trial in range(12):
+        n = int(rng.integers(3, 5000))
+        x = rng.normal(size=(n, 3)) * rng.uniform(0.1, 30) + rng.normal(size=3) * 10
+        ang = rng.uniform(-1.5, 1.5)
+        A = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]])
+        p = x @ A + rng.normal(size=3) + 0.01 * rng.normal(size=(n, 3))
+        d = np.linalg.norm(p - x, axis=1)
+        n_po = int(rng.integers(3, n + 5))
+        order, tau_ref = oracle.trim(d, n_po)
+        T_ref, mse_ref = oracle.get_transform(p, x, d, order)
+        T, mse, tau, kept = icp.pairs_transform(x, p, d, n_po)
+        assert kept == len(order) and tau == tau_ref
+        assert np.allclose(T, T_ref, rtol=0, atol=1e-10 * (1 + np.abs(x).max()))
+        assert abs(mse - mse_ref) <= 1e-12 * mse_ref
+        if have_ref:
+            k2, T2, mse2, tau2 = R.pairs_transform(x, p, d, n_po)
+            assert k2 == kept and tau2 == tau and np.allclose(T, T2, rtol=0, atol=1e-10 * (1 + np.abs(x).max()))
+    with pytest.raises(pkg.IcpError):
+        icp.pairs_transform(x[:2], p[:2], d[:2], 5)  # Pairs::getTransform throws below MIN_PAIRS
