@@ -214,7 +214,8 @@ struct icpb_ctx {
     int last_executed = 0;
     bool last_valid = false, last_early = false;
     // K7 / debug scratch
-    DevBuf<unsigned long long> kd0, kd1;
+    DevBuf<unsigned long long> kd0, kd1, cand_key;
+    DevBuf<uint32_t> cand_idx;
     DevBuf<uint32_t> dbg_idx;
     DevBuf<uint8_t> dbg_kept;
     // timing
@@ -314,6 +315,7 @@ int icpb_create(icpb_ctx **out, int device_id)
     CK(cudaMalloc((void **)&ctx->d_ghist, (SEL_MAX_BINS + 64) * sizeof(uint32_t)));
     CK(cudaMemset(ctx->d_ghist, 0, (SEL_MAX_BINS + 64) * sizeof(uint32_t)));
     CK(cudaMalloc((void **)&ctx->d_counter, 8 * sizeof(unsigned long long)));
+    CK(cudaMemset(ctx->d_counter, 0, 8 * sizeof(unsigned long long)));
     CK(cudaMalloc((void **)&ctx->d_gather, 64 * sizeof(unsigned long long)));
     CK(cudaEventCreate(&ctx->ev_begin));
     CK(cudaEventCreate(&ctx->ev_end));
@@ -369,6 +371,8 @@ void icpb_destroy(icpb_ctx *ctx)
     ctx->partials.release();
     ctx->trace.release();
     ctx->kd0.release();
+    ctx->cand_key.release();
+    ctx->cand_idx.release();
     ctx->kd1.release();
     ctx->dbg_idx.release();
     ctx->dbg_kept.release();
@@ -980,6 +984,21 @@ static int launch_trim(icpb_ctx *ctx, uint32_t n)
     cudaStream_t s = ctx->stream;
     const unsigned blocks = std::max(1u, std::min(grid_for(n, SEL_THREADS * 4), 148u * 4u));
     const int fused = (ctx->n_ranks == 1 || ctx->use_p2p) ? 1 : 0;
+    if (fused) {
+        // two grid-wide digit passes, then collect the few remaining candidates and finish on them in one block
+        CK(ctx->cand_key.ensure(std::max<size_t>(n, 1)));
+        CK(ctx->cand_idx.ensure(std::max<size_t>(n, 1)));
+        for (int p = 0; p < 2; ++p) {
+            select_kernel<<<blocks, SEL_THREADS, 0, s>>>(ctx->nn_d.p, n, ctx->d_state, ctx->d_ghist, p, 1, ctx->p2p);
+            CKL();
+        }
+        select_collect_kernel<<<blocks, SEL_THREADS, 0, s>>>(ctx->nn_d.p, ctx->src_perm.p, n, ctx->d_state, ctx->d_ghist,
+                                                             ctx->cand_key.p, ctx->cand_idx.p,
+                                                             (unsigned int *)(ctx->d_counter + 2), ctx->p2p);
+        CKL();
+        ctx->launches += 3;
+        return ICPB_OK;
+    }
     if (!fused) // pairs found on all ranks
         NK(g_nccl.AllReduce(&ctx->d_state->found, &ctx->d_state->found, 1, NCCL_UINT64, NCCL_SUM, ctx->comm, s));
     for (int p = 0; p < SEL_D_PASSES; ++p) {

@@ -281,7 +281,7 @@ constexpr int SEARCH_THREADS = 128;
 template <bool EAN>
 __global__ void __launch_bounds__(SEARCH_THREADS)
     search_kernel(const GridView g, const double *__restrict__ sx, const double *__restrict__ sy,
-                  const double *__restrict__ sz, uint32_t n, IcpState *__restrict__ st, uint32_t *__restrict__ nn_pos,
+                  const double *__restrict__ sz, uint32_t n, IcpState *st, uint32_t *__restrict__ nn_pos,
                   double *__restrict__ nn_d, int use_warm, const EanView ean)
 {
     if (st->done) return;
@@ -396,6 +396,9 @@ __device__ const uint32_t *p2p_exchange(const P2PView &v, IcpState *st, const ui
 }
 
 // ---------------------------------------------------------------------------
+// NOTE: IcpState pointers are deliberately NOT __restrict__: the last block of a kernel re-reads fields that another
+// thread of the same block has just written (behind __syncthreads); with a noalias pointer the compiler may keep the
+// stale value in a register.
 // K4: radix select.  Distances are non-negative doubles (or +inf = no pair),
 // so their bit patterns order like unsigned integers.
 // ---------------------------------------------------------------------------
@@ -502,7 +505,7 @@ __device__ void select_pick(IcpState *st, uint32_t *ghist, int pass, bool tie_mo
 // (ticket) narrows the prefix: locally, or after the fused peer-memory all-reduce, or -- NCCL mode -- not at all
 // (fused_pick == 0: select_pick_kernel runs after ncclAllReduce).
 __global__ void __launch_bounds__(SEL_THREADS)
-    select_kernel(const double *__restrict__ nn_d, uint32_t n, IcpState *__restrict__ st, uint32_t *__restrict__ ghist,
+    select_kernel(const double *__restrict__ nn_d, uint32_t n, IcpState *st, uint32_t *__restrict__ ghist,
                   int pass, int fused_pick, const P2PView p2p)
 {
     if (st->done) return;
@@ -606,6 +609,104 @@ __global__ void __launch_bounds__(1024)
     }
 }
 
+// Third and last launch of the trim (single GPU and peer-memory mode).  After two grid-wide digit passes the 22-bit
+// prefix (exponent + 11 mantissa bits) of the n_po-th smallest distance is known and only a handful of distances
+// still match it.  This kernel collects those candidates (warp-aggregated append) and its last block finishes the
+// selection on them alone: the remaining four digits (with the fused peer-memory all-reduce per digit when there are
+// several ranks) and, if fewer equidistant pairs are kept than exist, the three pair-index digits of the tie-break.
+__global__ void __launch_bounds__(SEL_THREADS)
+    select_collect_kernel(const double *__restrict__ nn_d, const uint32_t *__restrict__ perm, uint32_t n,
+                          IcpState *st, uint32_t *__restrict__ ghist, unsigned long long *__restrict__ cand_key,
+                          uint32_t *__restrict__ cand_idx, unsigned int *__restrict__ cand_count, const P2PView p2p)
+{
+    if (st->done) return;
+    if (st->sel_krem == 0) return; // nothing to select this iteration
+    __shared__ uint32_t scan_smem[34];
+    __shared__ int is_last;
+    const int hs = c_sel_d_shift[1]; // bits >= hs are fixed by the first two passes
+    const unsigned long long want = st->sel_prefix >> hs;
+    const int lane = threadIdx.x & 31;
+    const uint32_t T = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += 4u * T) { // warp-uniform trip count
+        unsigned long long key[4];
+        uint32_t idx[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            idx[u] = base + (uint32_t)u * T + threadIdx.x;
+            key[u] = (idx[u] < n && idx[u] >= base) ? (unsigned long long)__double_as_longlong(nn_d[idx[u]]) : ~0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const bool hit = key[u] != ~0ull && (key[u] >> hs) == want;
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
+            if (!m) continue;
+            unsigned pos = 0;
+            if (lane == __ffs(m) - 1) pos = atomicAdd(cand_count, (unsigned)__popc(m));
+            pos = __shfl_sync(0xFFFFFFFFu, pos, __ffs(m) - 1) + __popc(m & ((1u << lane) - 1u));
+            if (hit) {
+                cand_key[pos] = key[u];
+                cand_idx[pos] = idx[u];
+            }
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(&st->tickets[6], 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const unsigned cnt = *((volatile unsigned int *)cand_count);
+    for (int pass = 2; pass < SEL_D_PASSES; ++pass) {
+        const int bits = c_sel_d_bits[pass], shift = c_sel_d_shift[pass], hsp = shift + bits;
+        const unsigned bin_mask = (1u << bits) - 1u;
+        const unsigned long long prefix = st->sel_prefix;
+        if (st->sel_krem == 0) break;
+        for (unsigned j = threadIdx.x; j < cnt; j += blockDim.x) {
+            const unsigned long long k = __ldcg(cand_key + j);
+            if ((k >> hsp) == (prefix >> hsp)) atomicAdd(&ghist[(unsigned)(k >> shift) & bin_mask], 1u);
+        }
+        __threadfence();
+        __syncthreads();
+        if (p2p.world > 1) {
+            const int bins = 1 << bits;
+            const uint32_t *rows = p2p_exchange(p2p, st, ghist, bins);
+            for (int b = threadIdx.x; b < bins; b += blockDim.x) {
+                uint32_t v = 0;
+                for (int q = 0; q < p2p.world; ++q) v += __ldcv(rows + (size_t)q * P2P_ROW_WORDS + b);
+                ghist[b] = v;
+            }
+            __syncthreads();
+            select_pick(st, ghist, pass, false, scan_smem, rows, p2p.world, p2p.rank);
+        } else {
+            select_pick(st, ghist, pass, false, scan_smem);
+        }
+        __threadfence();
+        __syncthreads();
+    }
+    if (st->need_tie) { // which of the equidistant pairs survive: the lowest pair indices (rank-local quota)
+        const unsigned long long tau_bits = (unsigned long long)__double_as_longlong(st->tau);
+        for (int pass = 0; pass < SEL_T_PASSES; ++pass) {
+            const int bits = c_sel_t_bits[pass], shift = c_sel_t_shift[pass], hst = shift + bits;
+            const unsigned bin_mask = (1u << bits) - 1u;
+            const unsigned prefix = pass == 0 ? 0u : st->tie_prefix;
+            for (unsigned j = threadIdx.x; j < cnt; j += blockDim.x) {
+                if (__ldcg(cand_key + j) != tau_bits) continue;
+                const uint32_t pi = perm[__ldcg(cand_idx + j)];
+                if (pass == 0 || hst >= 32 || (pi >> hst) == (prefix >> hst)) atomicAdd(&ghist[(pi >> shift) & bin_mask], 1u);
+            }
+            __threadfence();
+            __syncthreads();
+            select_pick(st, ghist, pass, true, scan_smem);
+            __threadfence();
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) {
+        *cand_count = 0;
+        st->tickets[6] = 0;
+    }
+}
+
 __device__ __forceinline__ bool pair_kept(double d, uint32_t i, double tau, long long p_cut)
 {
     return d < tau || (d == tau && (long long)i <= p_cut);
@@ -624,7 +725,7 @@ __device__ __forceinline__ double shfl_xor_double(double v, int o)
 
 __global__ void __launch_bounds__(MOM_THREADS, 3)
     moments_kernel(const GridView g, const double *__restrict__ sx, const double *__restrict__ sy,
-                   const double *__restrict__ sz, uint32_t n, IcpState *__restrict__ st,
+                   const double *__restrict__ sz, uint32_t n, IcpState *st,
                    const uint32_t *__restrict__ nn_pos, const double *__restrict__ nn_d,
                    const uint32_t *__restrict__ perm, double *__restrict__ partials, double *__restrict__ trace,
                    int trace_cap, int fused_pose, const P2PView p2p)
@@ -744,7 +845,7 @@ __global__ void init_state_kernel(IcpState *st, Aff12 Cl2g, unsigned long long m
 // K7 + debug: kept distances / correspondences of the last executed iteration
 // ---------------------------------------------------------------------------
 __global__ void compact_kept_kernel(const double *__restrict__ nn_d, const uint32_t *__restrict__ perm, uint32_t n,
-                                    const IcpState *__restrict__ st,
+                                    const IcpState *st,
                                     unsigned long long *__restrict__ out_keys, unsigned int *__restrict__ counter)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -765,7 +866,7 @@ __global__ void compact_kept_kernel(const double *__restrict__ nn_d, const uint3
 
 __global__ void debug_pairs_kernel(const GridView g, const uint32_t *__restrict__ nn_pos,
                                    const double *__restrict__ nn_d, const uint32_t *__restrict__ perm, uint32_t n,
-                                   const IcpState *__restrict__ st, uint32_t *__restrict__ idx_out,
+                                   const IcpState *st, uint32_t *__restrict__ idx_out,
                                    double *__restrict__ d_out, uint8_t *__restrict__ kept_out)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
