@@ -71,14 +71,22 @@ template <typename T>
 struct DevBuf {
     T *p = nullptr;
     size_t cap = 0;
+    // contents are NOT kept; capacity grows geometrically so a growing model does not pay cudaFree/cudaMalloc per add
     cudaError_t ensure(size_t n)
     {
         if (n <= cap) return cudaSuccess;
+        const size_t want = cap ? std::max(n, cap + cap / 2) : n;
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
-        cudaError_t e = cudaMalloc((void **)&p, n * sizeof(T));
-        if (e == cudaSuccess) cap = n;
+        cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+        if (e != cudaSuccess && want > n) { // tight on memory: fall back to the exact size
+            cudaGetLastError();
+            e = cudaMalloc((void **)&p, n * sizeof(T));
+            if (e == cudaSuccess) cap = n;
+            return e;
+        }
+        if (e == cudaSuccess) cap = want;
         return e;
     }
     // grow, keeping the first `used` elements

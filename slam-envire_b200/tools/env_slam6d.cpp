@@ -23,7 +23,7 @@ int main(int argc, char **argv)
     if (argc < 3) { fprintf(stderr, "usage: env_slam6d <dir> <n_scans> [options]\n"); return 2; }
     const std::string dir = argv[1];
     const int n_scans = atoi(argv[2]);
-    double density = 1.0, overlap = 0.8, min_mse = 1e-6, min_mse_diff = 1e-9, growth_margin = 1.0;
+    double density = 1.0, overlap = 0.8, min_mse = 1e-6, min_mse_diff = 1e-9, growth_margin = 0.0;
     size_t max_iter = 30;
     for (int i = 3; i < argc; ++i) {
         if (!strcmp(argv[i], "--density")) density = atof(argv[++i]);
