@@ -68,7 +68,10 @@ const char *icpb_version(void);
 /* keys: "cell_size" (m, 0 = auto), "target_pts_per_cell", "max_cells",
  *       "poll_every" (iterations between host polls of the done flag),
  *       "warm_start" (0/1: seed the search with the previous iteration's pair),
- *       "sort_source" (0/1), "run_ahead", "profile" (0/1),
+ *       "sort_source" (0/1), "graph" (0/1, default 1: the whole _align loop is ONE CUDA-graph launch whose WHILE
+ *       node is driven by the device-side loop condition), "profile" (0/1, default 0: 1 enqueues the loop kernel by
+ *       kernel on the stream with CUDA events around every phase -- icpb_last_timing / icpb_iteration_times --
+ *       and the host peeking at a pinned flag at most "run_ahead" iterations behind),
  *       "growth_margin" (fraction of the model extent left free around it at a full build, so that later
  *       addToModel calls inside that box are merged in without a rebuild; default 0), "merge_append" (0/1) */
 int icpb_set_option(icpb_ctx *, const char *key, double value);

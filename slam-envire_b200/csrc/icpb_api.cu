@@ -179,7 +179,7 @@ struct icpb_ctx {
     std::string err;
     // options
     double opt_cell_size = 0.0, opt_target = 4.0, opt_max_cells = 64.0 * 1024 * 1024, opt_run_ahead = 2.0,
-           opt_warm = 1.0, opt_profile = 1.0, opt_sort = 1.0, opt_margin = 0.0, opt_merge = 1.0;
+           opt_warm = 1.0, opt_profile = 0.0, opt_sort = 1.0, opt_margin = 0.0, opt_merge = 1.0, opt_graph = 1.0;
     // model
     DevBuf<double> model_raw, model_nrm;
     DevBuf<uint8_t> model_edge;
@@ -237,6 +237,12 @@ struct icpb_ctx {
     nccl_comm_t comm = nullptr;
     int n_ranks = 1, rank = 0;
     unsigned long long *d_gather = nullptr;
+    // CUDA-graph form of the align loop (WHILE conditional node), rebuilt when any captured argument changes
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    cudaGraphNode_t graph_init_node = nullptr;
+    cudaGraphConditionalHandle graph_cond = 0;
+    std::vector<unsigned char> graph_key;
     // peer-memory collectives
     uint32_t *p2p_local = nullptr;
     void *p2p_mapped[P2P_MAX_RANKS] = {nullptr};
@@ -339,6 +345,8 @@ void icpb_destroy(icpb_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+    if (ctx->graph) cudaGraphDestroy(ctx->graph);
     if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
     for (int r = 0; r < P2P_MAX_RANKS; ++r)
         if (ctx->p2p_mapped[r]) cudaIpcCloseMemHandle(ctx->p2p_mapped[r]);
@@ -411,6 +419,7 @@ static double *opt_slot(icpb_ctx *ctx, const char *key)
     if (!strcmp(key, "sort_source")) return &ctx->opt_sort;
     if (!strcmp(key, "growth_margin")) return &ctx->opt_margin;
     if (!strcmp(key, "merge_append")) return &ctx->opt_merge;
+    if (!strcmp(key, "graph")) return &ctx->opt_graph;
     return nullptr;
 }
 int icpb_set_option(icpb_ctx *ctx, const char *key, double value)
@@ -1077,16 +1086,109 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
     const int run_ahead = (int)std::max(1.0, std::min(ctx->opt_run_ahead, 32.0));
     const unsigned long long launches0 = ctx->launches;
 
-    CK(cudaEventRecord(ctx->ev_begin, s));
     Aff12 A;
     memcpy(A.a, ctx->Cl2g, sizeof(A.a));
+    cudaGraphConditionalHandle cond = 0;
+    int use_cond = 0;
+    const int use_warm = ctx->opt_warm != 0.0 ? 1 : 0;
+    // one loop body of Trimmed::_align: search, trim, moments + pose
+    auto enqueue_iteration = [&]() -> int {
+        if (ean.on)
+            search_kernel<true><<<grid_for(std::max<uint32_t>(n, 1), SEARCH_THREADS), SEARCH_THREADS, 0, s>>>(
+                ctx->gv, ctx->sx.p, ctx->sy.p, ctx->sz.p, n, ctx->d_state, ctx->nn_pos.p, ctx->nn_d.p, use_warm, ean);
+        else
+            search_kernel<false><<<grid_for(std::max<uint32_t>(n, 1), SEARCH_THREADS), SEARCH_THREADS, 0, s>>>(
+                ctx->gv, ctx->sx.p, ctx->sy.p, ctx->sz.p, n, ctx->d_state, ctx->nn_pos.p, ctx->nn_d.p, use_warm, ean);
+        CKL();
+        ++ctx->launches;
+        return ICPB_OK;
+    };
+    size_t it = 0, checked = 0, timed_iters = 0;
+    const bool use_graph = ctx->opt_graph != 0.0 && !profile && fused;
+    if (use_graph) {
+        // ---- the whole loop as ONE graph launch: init -> WHILE(!done){search, trim, moments+pose} ----
+        CK(ctx->cand_key.ensure(std::max<size_t>(n, 1)));
+        CK(ctx->cand_idx.ensure(std::max<size_t>(n, 1)));
+        std::vector<unsigned char> key;
+        auto add_key = [&](const void *p, size_t bytes) { key.insert(key.end(), (const unsigned char *)p, (const unsigned char *)p + bytes); };
+        const void *ptrs[] = {ctx->sx.p, ctx->sy.p, ctx->sz.p, ctx->nn_pos.p, ctx->nn_d.p, ctx->src_perm.p, ctx->partials.p,
+                              ctx->trace.p, ctx->cand_key.p, ctx->cand_idx.p, ctx->d_state, ctx->d_ghist};
+        add_key(&n, sizeof(n));
+        add_key(&ctx->gv, sizeof(ctx->gv));
+        add_key(ptrs, sizeof(ptrs));
+        add_key(&ean, sizeof(ean));
+        add_key(&ctx->p2p, sizeof(ctx->p2p));
+        add_key(&ctx->trace_cap, sizeof(ctx->trace_cap));
+        add_key(&use_warm, sizeof(use_warm));
+        void *init_args[11];
+        unsigned long long a_max_iter = max_iter, a_n_po = n_po, a_n = n, a_off = 0;
+        double a_mse = prm->min_mse, a_diff = prm->min_mse_diff, a_ov = prm->overlap;
+        int one = 1;
+        if (key != ctx->graph_key || !ctx->graph_exec) {
+            if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+            if (ctx->graph) cudaGraphDestroy(ctx->graph);
+            ctx->graph_exec = nullptr;
+            ctx->graph = nullptr;
+            ctx->graph_key.clear();
+            CK(cudaGraphCreate(&ctx->graph, 0));
+            CK(cudaGraphConditionalHandleCreate(&ctx->graph_cond, ctx->graph, 1, cudaGraphCondAssignDefault));
+            init_args[0] = &ctx->d_state; init_args[1] = &A; init_args[2] = &a_max_iter; init_args[3] = &a_mse;
+            init_args[4] = &a_diff; init_args[5] = &a_ov; init_args[6] = &a_n_po; init_args[7] = &a_n; init_args[8] = &a_off;
+            init_args[9] = &ctx->graph_cond; init_args[10] = &one;
+            cudaKernelNodeParams kp;
+            memset(&kp, 0, sizeof(kp));
+            kp.func = (void *)init_state_kernel;
+            kp.gridDim = dim3(1);
+            kp.blockDim = dim3(1);
+            kp.kernelParams = init_args;
+            CK(cudaGraphAddKernelNode(&ctx->graph_init_node, ctx->graph, nullptr, 0, &kp));
+            cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
+            cp.type = cudaGraphNodeTypeConditional;
+            cp.conditional.handle = ctx->graph_cond;
+            cp.conditional.type = cudaGraphCondTypeWhile;
+            cp.conditional.size = 1;
+            cudaGraphNode_t cond_node;
+            CK(cudaGraphAddNode(&cond_node, ctx->graph, &ctx->graph_init_node, 1, &cp));
+            cudaGraph_t body = cp.conditional.phGraph_out[0];
+            CK(cudaStreamBeginCaptureToGraph(s, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+            cond = ctx->graph_cond;
+            use_cond = 1;
+            int rc = enqueue_iteration();
+            if (rc == ICPB_OK) rc = launch_trim(ctx, n);
+            if (rc == ICPB_OK) {
+                moments_kernel<<<mom_blocks, MOM_THREADS, 0, s>>>(ctx->gv, ctx->sx.p, ctx->sy.p, ctx->sz.p, n, ctx->d_state,
+                                                                  ctx->nn_pos.p, ctx->nn_d.p, ctx->src_perm.p,
+                                                                  ctx->partials.p, ctx->trace.p, ctx->trace_cap, fused,
+                                                                  ctx->p2p, cond, use_cond);
+            }
+            cudaGraph_t captured = nullptr;
+            cudaError_t ce = cudaStreamEndCapture(s, &captured);
+            if (rc != ICPB_OK) return rc;
+            if (ce != cudaSuccess) return ctx->fail(ce, "cudaStreamEndCapture", __LINE__);
+            CK(cudaGraphInstantiate(&ctx->graph_exec, ctx->graph, 0));
+            ctx->graph_key = key;
+        }
+        // this align's parameters go into the init node
+        init_args[0] = &ctx->d_state; init_args[1] = &A; init_args[2] = &a_max_iter; init_args[3] = &a_mse;
+        init_args[4] = &a_diff; init_args[5] = &a_ov; init_args[6] = &a_n_po; init_args[7] = &a_n; init_args[8] = &a_off;
+        init_args[9] = &ctx->graph_cond; init_args[10] = &one;
+        cudaKernelNodeParams kp;
+        memset(&kp, 0, sizeof(kp));
+        kp.func = (void *)init_state_kernel;
+        kp.gridDim = dim3(1);
+        kp.blockDim = dim3(1);
+        kp.kernelParams = init_args;
+        CK(cudaGraphExecKernelNodeSetParams(ctx->graph_exec, ctx->graph_init_node, &kp));
+        CK(cudaEventRecord(ctx->ev_begin, s));
+        CK(cudaGraphLaunch(ctx->graph_exec, s));
+    } else {
+    CK(cudaEventRecord(ctx->ev_begin, s));
     init_state_kernel<<<1, 1, 0, s>>>(ctx->d_state, A, max_iter, prm->min_mse, prm->min_mse_diff, prm->overlap, n_po,
-                                      n, 0ull);
+                                      n, 0ull, 0, 0);
     CKL();
     ++ctx->launches;
     for (int k = 0; k < FLAG_RING; ++k) ctx->h_flags[k] = -1;
 
-    size_t it = 0, checked = 0, timed_iters = 0;
     bool stop = false;
     for (; it < max_iter && !stop; ++it) {
         // never run more than run_ahead iterations ahead of the device-side loop condition
@@ -1103,16 +1205,10 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
         const bool timed = profile && it < (size_t)EVENT_ITERS;
         cudaEvent_t *ev = timed ? &ctx->events[it * 4] : nullptr;
         if (timed) CK(cudaEventRecord(ev[0], s));
-        if (ean.on)
-            search_kernel<true><<<grid_for(std::max<uint32_t>(n, 1), SEARCH_THREADS), SEARCH_THREADS, 0, s>>>(
-                ctx->gv, ctx->sx.p, ctx->sy.p, ctx->sz.p, n, ctx->d_state, ctx->nn_pos.p, ctx->nn_d.p,
-                ctx->opt_warm != 0.0 ? 1 : 0, ean);
-        else
-            search_kernel<false><<<grid_for(std::max<uint32_t>(n, 1), SEARCH_THREADS), SEARCH_THREADS, 0, s>>>(
-                ctx->gv, ctx->sx.p, ctx->sy.p, ctx->sz.p, n, ctx->d_state, ctx->nn_pos.p, ctx->nn_d.p,
-                ctx->opt_warm != 0.0 ? 1 : 0, ean);
-        CKL();
-        ++ctx->launches;
+        {
+            int rc = enqueue_iteration();
+            if (rc != ICPB_OK) return rc;
+        }
         if (timed) CK(cudaEventRecord(ev[1], s));
         {
             int rc = launch_trim(ctx, n);
@@ -1121,7 +1217,7 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
         if (timed) CK(cudaEventRecord(ev[2], s));
         moments_kernel<<<mom_blocks, MOM_THREADS, 0, s>>>(ctx->gv, ctx->sx.p, ctx->sy.p, ctx->sz.p, n, ctx->d_state,
                                                           ctx->nn_pos.p, ctx->nn_d.p, ctx->src_perm.p, ctx->partials.p,
-                                                          ctx->trace.p, ctx->trace_cap, fused, ctx->p2p);
+                                                          ctx->trace.p, ctx->trace_cap, fused, ctx->p2p, cond, use_cond);
         CKL();
         ++ctx->launches;
         if (!fused) {
@@ -1137,6 +1233,7 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
         }
         CK(cudaMemcpyAsync(&ctx->h_flags[it % FLAG_RING], &ctx->d_state->done, sizeof(int), cudaMemcpyDeviceToHost, s));
         CK(cudaEventRecord(ctx->ring[it % ctx->ring.size()], s));
+    }
     }
     CK(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(IcpState), cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(ctx->ev_end, s));
@@ -1177,7 +1274,8 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
         ctx->iter_ms[k * 3 + 1] = b;
         ctx->iter_ms[k * 3 + 2] = c;
     }
-    ctx->timing.iterations = exec_timed;
+    ctx->timing.iterations = use_graph ? (unsigned long long)hs.executed : exec_timed;
+    if (use_graph) ctx->launches = launches0 + 1ull + 5ull * (unsigned long long)hs.executed; // init + 5 kernels per executed body
     ctx->timing.kernels_launched = ctx->launches - launches0;
     return ICPB_OK;
 }
@@ -1414,7 +1512,7 @@ int icpb_pairs_transform(icpb_ctx *ctx, const double *x, const double *p, const 
     if (rc == ICPB_OK) {
         moments_kernel<<<mom_blocks, MOM_THREADS, 0, s>>>(gv, ctx->sx.p, ctx->sy.p, ctx->sz.p, (uint32_t)n, ctx->d_state,
                                                           ctx->nn_pos.p, ctx->nn_d.p, ctx->src_perm.p, ctx->partials.p,
-                                                          nullptr, 0, 1, ctx->p2p);
+                                                          nullptr, 0, 1, ctx->p2p, 0, 0);
         ctx->launches += 1;
     }
     ctx->n_ranks = saved_ranks;

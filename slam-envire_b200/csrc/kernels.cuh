@@ -277,9 +277,12 @@ __global__ void mask_levelN_kernel(const uint8_t *__restrict__ below, int nx, in
 // K2 + K3: transform the source vertex and find its exact nearest model point
 // ---------------------------------------------------------------------------
 constexpr int SEARCH_THREADS = 128;
+#ifndef ICPB_SEARCH_MIN_BLOCKS
+#define ICPB_SEARCH_MIN_BLOCKS 8
+#endif
 
 template <bool EAN>
-__global__ void __launch_bounds__(SEARCH_THREADS)
+__global__ void __launch_bounds__(SEARCH_THREADS, ICPB_SEARCH_MIN_BLOCKS)
     search_kernel(const GridView g, const double *__restrict__ sx, const double *__restrict__ sy,
                   const double *__restrict__ sz, uint32_t n, IcpState *st, uint32_t *__restrict__ nn_pos,
                   double *__restrict__ nn_d, int use_warm, const EanView ean)
@@ -728,7 +731,7 @@ __global__ void __launch_bounds__(MOM_THREADS, 3)
                    const double *__restrict__ sz, uint32_t n, IcpState *st,
                    const uint32_t *__restrict__ nn_pos, const double *__restrict__ nn_d,
                    const uint32_t *__restrict__ perm, double *__restrict__ partials, double *__restrict__ trace,
-                   int trace_cap, int fused_pose, const P2PView p2p)
+                   int trace_cap, int fused_pose, const P2PView p2p, cudaGraphConditionalHandle cond, int use_cond)
 {
     if (st->done) return;
     __shared__ double sm[MOM_THREADS / 32][ICPB_NSUMS];
@@ -815,6 +818,8 @@ __global__ void __launch_bounds__(MOM_THREADS, 3)
             const int row = st->executed;
             icpb_iteration_finish(*st, row < trace_cap ? trace + (size_t)row * ICPB_TRACE_COLS_DEV : nullptr);
         }
+        // CUDA-graph mode: the loop condition of Trimmed::_align drives the WHILE node this kernel lives in
+        if (use_cond) cudaGraphSetConditional(cond, st->done ? 0u : 1u);
     }
 }
 
@@ -828,7 +833,8 @@ __global__ void pose_kernel(IcpState *st, double *trace, int trace_cap)
 
 __global__ void init_state_kernel(IcpState *st, Aff12 Cl2g, unsigned long long max_iter, double min_mse,
                                   double min_mse_diff, double overlap, unsigned long long n_po,
-                                  unsigned long long n_local, unsigned long long n_offset)
+                                  unsigned long long n_local, unsigned long long n_offset,
+                                  cudaGraphConditionalHandle cond, int use_cond)
 {
     icpb_state_init(*st, Cl2g.a, max_iter, min_mse, min_mse_diff, overlap, n_po);
     st->n_local = n_local;
@@ -839,6 +845,7 @@ __global__ void init_state_kernel(IcpState *st, Aff12 Cl2g, unsigned long long m
     st->tie_krem = 0;
     st->tie_local = 0;
     for (int k = 0; k < ICPB_NSUMS; ++k) st->sums[k] = 0.0;
+    if (use_cond) cudaGraphSetConditional(cond, st->done ? 0u : 1u); // max_iter == 0 etc.: the body never runs
 }
 
 // ---------------------------------------------------------------------------

@@ -369,3 +369,29 @@ def test_pairs_transform_stage(icp, oracle, pkg):
             assert k2 == kept and tau2 == tau and np.allclose(T, T2, rtol=0, atol=1e-10 * (1 + np.abs(x).max()))
     with pytest.raises(pkg.IcpError):
         icp.pairs_transform(x[:2], p[:2], d[:2], 5)  # Pairs::getTransform throws below MIN_PAIRS
+
+
+def test_graph_loop_equals_stream_loop(pkg, oracle, synth):
+    """profile=0 runs the whole _align as ONE CUDA-graph launch (WHILE conditional node driven by the device-side loop
+    condition); it must give exactly what the stream-enqueued loop gives, incl. early exits and edge cases."""
+    m, s, T, prm = synth.config("cfg1", 0.2)
+    a, b = pkg.Icp(0), pkg.Icp(0)
+    a.set_option("profile", 1)  # stream-enqueued loop with per-phase events; b keeps the default: one graph launch
+    for c in (a, b):
+        c.add_to_model(m)
+    cases = [dict(prm), dict(prm, max_iter=7), dict(prm, max_iter=0), dict(prm, overlap=0.0001), dict(prm, max_iter=3, overlap=0.5)]
+    for p in cases:
+        ra, rb = a.align(s, **p), b.align(s, **p)
+        assert ra.iter == rb.iter and ra.pairs == rb.pairs and ra.status == rb.status
+        assert np.array_equal(ra.matrix(), rb.matrix())
+        assert (ra.mse == rb.mse) or (np.isinf(ra.mse) and np.isinf(rb.mse))
+        assert len(a.trace()) == len(b.trace())
+        assert np.array_equal(a.pairs_distance(), b.pairs_distance())
+    # a different source size re-captures the graph; same size re-uses it
+    for n in (5000, 5000, 2000, 2):
+        ra, rb = a.align(s[:n], **prm), b.align(s[:n], **prm)
+        assert ra.iter == rb.iter and np.array_equal(ra.matrix(), rb.matrix())
+    t = b.timing()
+    assert t["kernels_launched"] >= 1
+    a.close()
+    b.close()

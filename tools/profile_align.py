@@ -13,6 +13,7 @@ for k in list(opts):
     if k in prm:
         prm[k] = type(prm[k])(float(opts.pop(k)))
 icp = pkg.Icp(0)
+icp.set_option("profile", 1)  # per-phase CUDA events (the default is the single-graph-launch loop)
 for k, v in opts.items():
     icp.set_option(k, float(v))
 icp.add_to_model(m)

@@ -38,6 +38,7 @@ else:
 gen_s = time.time() - t0
 
 icp = pkg.Icp(local)
+icp.set_option("profile", 1)
 if world > 1:
     sharding.init_comm(icp, dist, torch.device("cuda", local), mode=os.environ.get("ICPB_COMM", "p2p"))
 t0 = time.time()
