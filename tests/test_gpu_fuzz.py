@@ -1,0 +1,111 @@
+"""Randomised parity sweep: many small, oddly shaped problems through the C ABI against the oracle.  Covers what the
+fixed cases do not: degenerate clouds (planes, lines, duplicates, lattices with massive ties), queries far outside
+the grid, forced cell sizes (different pyramid depths), tiny and empty inputs, random d_box / overlap / density."""
+import numpy as np
+import pytest
+
+from conftest import assert_transform_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _cloud(rng, kind, n):
+    if kind == "volume":
+        return rng.uniform(-5, 5, (n, 3)) * rng.uniform(0.1, 10, 3)
+    if kind == "plane":
+        p = rng.uniform(-8, 8, (n, 3))
+        p[:, rng.integers(0, 3)] = rng.normal()
+        return p
+    if kind == "line":
+        t = rng.uniform(-20, 20, (n, 1))
+        return t * rng.normal(size=(1, 3)) + rng.normal(size=3)
+    if kind == "lattice":
+        k = max(2, int(round(n ** (1 / 3))))
+        g = np.arange(k, dtype=np.float64) * rng.choice([0.25, 1.0, 3.0])
+        return np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    if kind == "clusters":
+        c = rng.uniform(-50, 50, (max(1, n // 50), 3))
+        return c[rng.integers(0, len(c), n)] + rng.normal(0, 0.05, (n, 3))
+    if kind == "duplicates":
+        p = rng.uniform(-3, 3, (max(1, n // 4), 3))
+        return p[rng.integers(0, len(p), n)]
+    raise ValueError(kind)
+
+
+KINDS = ["volume", "plane", "line", "lattice", "clusters", "duplicates"]
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_find_pairs_fuzz(pkg, oracle, seed):
+    rng = np.random.default_rng(1000 + seed)
+    kind = KINDS[seed % len(KINDS)]
+    n = int(rng.choice([1, 2, 7, 60, 700, 5000]))
+    m = _cloud(rng, kind, n)
+    nq = int(rng.choice([1, 33, 500, 3000]))
+    span = np.ptp(m, axis=0).max() + 1.0
+    q = m[rng.integers(0, len(m), nq)] + rng.normal(0, 1, (nq, 3)) * rng.choice([1e-9, 0.01, 0.3, 2.0]) * span * 0.1
+    if seed % 5 == 0:
+        q[: nq // 3] += rng.normal(size=3) * span * 50  # far outside the grid
+    if kind == "lattice" and seed % 2 == 0:
+        q = m[rng.integers(0, len(m), nq)] + 0.5 * (m[1, 2] - m[0, 2] if len(m) > 1 else 1.0)  # equidistant ties
+    d_box = float(rng.choice([np.inf, np.inf, span * 0.02, span * 0.5, 0.0]))
+    icp = pkg.Icp(0)
+    if seed % 3 == 0:
+        icp.set_option("cell_size", float(span * rng.choice([0.002, 0.05, 0.7])))
+    icp.add_to_model(m)
+    M = oracle.Model()
+    M.add(m)
+    i_ref, d_ref = M.find_pairs(q, d_box=d_box, brute=True)
+    i_gpu, d_gpu = icp.find_pairs(q, d_box=d_box)
+    d_ref = np.where(i_ref == 0xFFFFFFFF, d_box, d_ref)
+    assert np.array_equal(d_gpu, d_ref), (kind, n, nq, d_box)
+    assert np.array_equal(i_gpu, i_ref), (kind, n, nq, d_box)  # ties -> lowest insertion index on both sides
+    icp.close()
+
+
+@pytest.mark.parametrize("seed", range(30))
+def test_align_fuzz(pkg, oracle, synth, seed):
+    rng = np.random.default_rng(5000 + seed)
+    kind = ["volume", "plane", "clusters", "lattice"][seed % 4]
+    n = int(rng.choice([3, 40, 900, 6000]))
+    m = _cloud(rng, kind, n)
+    span = float(np.ptp(m, axis=0).max() + 1e-3)
+    ns = int(rng.choice([1, 3, 50, 2000, 7000]))
+    T = synth.rigid(rng.normal(size=3), float(rng.uniform(0, 0.15)), rng.normal(size=3) * span * 0.02)
+    s = m[rng.integers(0, len(m), ns)] + rng.normal(0, span * 1e-3, (ns, 3))
+    s = (s - T[:3, 3]) @ T[:3, :3]
+    T_src = synth.rigid(rng.normal(size=3), float(rng.uniform(0, 0.5)), rng.normal(size=3)) if seed % 3 == 0 else None
+    density = float(rng.choice([1.0, 1.0, 0.5, 0.31]))
+    prm = dict(max_iter=int(rng.integers(0, 25)), min_mse=float(rng.choice([1e-4, 1e-12])),
+               min_mse_diff=float(rng.choice([1e-5, 1e-14])), overlap=float(rng.choice([1.0, 0.9, 0.6, 0.2, 0.01])))
+    icp = pkg.Icp(0)
+    if seed % 2 == 0:
+        icp.set_option("profile", 1)  # stream loop; the others use the single-graph-launch loop
+    icp.add_to_model(m)
+    M = oracle.Model()
+    M.add(m)
+    run = oracle.Run()
+    r_ref = M.align(s, T=T_src, density=density, run=run, **prm)
+    r = icp.align(s, T=T_src, density=density, **prm)
+    tr, tr_ref = icp.trace(), run.trace()
+    # the first loop body does not depend on any pose solve: always identical
+    assert (len(tr) > 0) == (len(tr_ref) > 0)
+    if tr_ref:
+        assert tr[0]["found"] == tr_ref[0]["found"] and tr[0]["kept"] == tr_ref[0]["kept"]
+        assert tr[0]["tau"] == tr_ref[0]["tau"] or (np.isnan(tr[0]["tau"]) and np.isnan(tr_ref[0]["tau"]))
+    # Degenerate pairings (the kept pairs hit fewer than a handful of distinct model points, e.g. a far-away blob or a
+    # 3-point model): the cross-covariance is zero up to rounding, so the REFERENCE's own rotation is decided by the
+    # summation order -- nothing to compare beyond the first body.
+    idx_ref, _ = run.last_pairs() if tr_ref else (np.zeros(0, np.uint32), None)
+    distinct = len(np.unique(idx_ref[idx_ref != 0xFFFFFFFF])) if len(idx_ref) else 0
+    sv = np.linalg.svd(m - m.mean(0), compute_uv=False) if len(m) > 3 else np.zeros(3)
+    well_posed = distinct >= 12 and r_ref.pairs >= 12 and sv[1] > 1e-3 * sv[0]
+    if well_posed:
+        assert r.iter == r_ref.iter and r.pairs == r_ref.pairs, (kind, n, ns, prm)
+        assert [t["kept"] for t in tr] == [t["kept"] for t in tr_ref]
+        assert [t["found"] for t in tr] == [t["found"] for t in tr_ref]
+        assert_transform_close(r.matrix(), r_ref.matrix(), max(span, 1.0), rot_tol=1e-5, trans_tol_rel=1e-6)
+        if np.isfinite(r_ref.mse) and r_ref.mse > 1e-20:
+            assert abs(r.mse - r_ref.mse) <= 1e-5 * r_ref.mse
+        assert len(icp.pairs_distance()) == len(run.pairs_distance())
+    icp.close()
