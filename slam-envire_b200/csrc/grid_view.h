@@ -4,26 +4,32 @@
 // Replaces: FindPairsKDTree::findPairs -> kdtree.find_nearest(node, d_box)
 //           (reference icp/icp.hpp:242-252).
 //
-// Layout (all in HBM, built once per model by grid_build.cuh):
+// Layout (all in HBM, built once per model by the K1 kernels):
 //   pts[n]          model points sorted by level-0 cell key (x fastest), 32 B
 //                   each: fp64 x,y,z in the global frame + insertion index
+//   ptsf[n]         the same points as float4 in cell units relative to the grid origin (candidate pre-filter)
 //   cell_start[c]   exclusive prefix of points per level-0 cell, ncell+1 entries
 //                   (so x-adjacent cells form one contiguous run of pts)
-//   mask[l][c]      l >= 1: one byte per level-l cell, bit (dx|dy<<1|dz<<2) set
-//                   when that child cell of level l-1 holds at least one point.
-//                   Level l cells have edge h*2^l; the top level is one cell.
+//   node[l][c]      l >= 1: one 32-bit word per level-l cell.  Bits 0-7: child occupancy, bit (dx|dy<<1|dz<<2)
+//                   set when that child cell of level l-1 holds at least one point.  Bits 8-31: the TIGHT
+//                   bounding box of the points below the node, six nibbles lo x,y,z / hi x,y,z in sixteenths
+//                   of the node's edge (lo rounded down, hi up).  Scenes are surfaces: a node's points fill a
+//                   thin slab of its cube, and a query several cells off the surface prunes on the slab where
+//                   the cube alone would make it descend.  Level l cells have edge h*2^l; the top level is one
+//                   cell.
 //
-// Search: exact Euclidean NN inside the inclusive ball d_box.  The uniform grid
-// is searched as "rings" of cells around the query, but rings are expanded
-// hierarchically: the start level is the one whose cell edge covers the current
-// upper bound U (previous iteration's pair, or d_box), so the ball touches at
-// most 2x2x2 cells of that level; those cells are then descended depth-first,
-// nearest child first, skipping empty space through the occupancy masks and
-// pruning every cell whose box is farther than the best distance so far.
-// Pruning is conservative (eps slack, ">" not ">=") so the answer is the
-// lexicographic minimum over (d^2, insertion index) of ALL model points: the
-// same point a kd-tree returns, with equidistant ties resolved to the lowest
-// insertion index.  Distances are evaluated exactly like libkdtree++ does:
+// Search: exact Euclidean NN inside the inclusive ball d_box, one thread per query, no stack in memory.
+//   * The upper bound U is the previous iteration's pair (warm start) or d_box.  Everything that steers the walk
+//     is fp32 in cell units with a slack that keeps every bound provably <= the true distance; fp64 is spent only
+//     on the source transform, on the candidates that can still win, and on the final sqrt.
+//   * 2U <= one cell edge (the converged regime, most iterations): the ball touches at most 2x2x2 level-0
+//     cells; x-adjacent cells are one contiguous run of pts, so at most four runs are scanned, own column first.
+//   * otherwise: the start level is the one whose cell edge covers 2U (<= 2x2x2 roots); each root is walked
+//     depth-first, nearest child first, with the path kept as one byte of pending children per level in two
+//     registers ("trail"), skipping empty space through the occupancy bits and pruning on the tight boxes.
+// Pruning is conservative (slack, ">" not ">=") so the answer is the lexicographic minimum over
+// (d^2, insertion index) of ALL model points: the same point a kd-tree returns, with equidistant ties resolved
+// to the lowest insertion index.  Distances are evaluated exactly like libkdtree++ does:
 // sqrt((dx*dx + dy*dy) + dz*dz) in fp64 without FMA contraction.
 //
 // The functions are __host__ __device__ so tests/ can run the very same search
@@ -40,9 +46,15 @@
 
 #define ICPB_MAX_LEVELS 16
 #define ICPB_NONE 0xFFFFFFFFu
-#define ICPB_SEARCH_STACK 112
 #ifndef ICPB_COUNT
 #define ICPB_COUNT(what) // instrumentation hook (tests/harness defines it to count traversal work)
+#endif
+// fp32 bounds may use FMA (the library is built with -fmad=false for fp64 parity; the fp32 side only has to be
+// conservative, not reproducible)
+#ifdef __CUDA_ARCH__
+#define ICPB_FMAF(a, b, c) __fmaf_rn((a), (b), (c))
+#else
+#define ICPB_FMAF(a, b, c) ((a) * (b) + (c))
 #endif
 
 struct
@@ -72,11 +84,11 @@ struct GridView {
     double o[3];  // origin (min corner of the model bounding box)
     double h;     // level-0 cell edge
     double inv_h; // 1/h
-    double eps;   // geometric slack for pruning (1e-9 * h)
+    double eps;   // geometric slack of the cell assignment (1e-9 * h)
     int dim[ICPB_MAX_LEVELS][3];
     int L; // top level: dim[L] == {1,1,1}
     const uint32_t *cell_start;
-    const uint8_t *mask[ICPB_MAX_LEVELS];
+    const uint32_t *node[ICPB_MAX_LEVELS]; // see the layout comment
     const MPoint *pts;
     const FPoint *ptsf; // same order as pts
     uint32_t n;
@@ -93,42 +105,56 @@ ICPB_HD int icpb_cell_coord(double p, double o, double inv_h, int dim)
     return (int)t;
 }
 
-// squared distance from q to the box of cell (cx,cy,cz) at `level`, shrunk by eps
-ICPB_HD double icpb_cell_mindist2(const GridView &g, int level, int cx, int cy, int cz, double qx, double qy,
-                                  double qz)
+// ---- node words -----------------------------------------------------------------------------------------------
+ICPB_HD uint32_t icpb_node_word(unsigned mask, const int lo[3], const int hi[3])
 {
-    const double hl = g.h * (double)(1u << level);
-    double lo, gap, d2 = 0.0;
-    lo = g.o[0] + (double)cx * hl;
-    gap = fmax(fmax(lo - qx, qx - (lo + hl)) - g.eps, 0.0);
-    d2 += gap * gap;
-    lo = g.o[1] + (double)cy * hl;
-    gap = fmax(fmax(lo - qy, qy - (lo + hl)) - g.eps, 0.0);
-    d2 += gap * gap;
-    lo = g.o[2] + (double)cz * hl;
-    gap = fmax(fmax(lo - qz, qz - (lo + hl)) - g.eps, 0.0);
-    d2 += gap * gap;
-    return d2;
+    return (uint32_t)mask | ((uint32_t)lo[0] << 8) | ((uint32_t)lo[1] << 12) | ((uint32_t)lo[2] << 16) |
+           ((uint32_t)hi[0] << 20) | ((uint32_t)hi[1] << 24) | ((uint32_t)hi[2] << 28);
 }
+// nibble of a cell-unit coordinate u inside the level-`level` cube starting at cube_lo (sixteenths of the edge)
+ICPB_HD int icpb_node_nibble(double u, double cube_lo, int level)
+{
+    double t = floor((u - cube_lo) * (16.0 / (double)(1u << level)));
+    if (!(t > 0.0)) t = 0.0;
+    if (t > 15.0) t = 15.0;
+    return (int)t;
+}
+// the nibbles of a child's box seen from its parent (child code bit a selects the upper half on axis a)
+ICPB_HD int icpb_nibble_up(uint32_t child_word, int shift, int upper_half) { return 8 * upper_half + (int)((child_word >> shift) & 15u) / 2; }
 
-// The same lower bound in fp32 "cell units" (u = (q - o)/h), used by the traversal: cell corners are small
-// integers (exact in fp32), the query coordinate carries a conversion error that `slack` (>= that error plus
-// the cell-assignment slack, in cells) absorbs, and the sum is scaled down to stay below the true value.
-// Conservative by construction: never larger than the true squared distance (in cells^2) to any point filed
-// under the cell, so pruning with it cannot lose a candidate.
+// ---- fp32 bounds in cell units --------------------------------------------------------------------------------
+// Squared gap between the query coordinate u and the interval [lo, hi] along one axis.  u is the fp32 copy of the
+// exact cell-unit coordinate, off by at most `slack` (which also absorbs the cell-assignment slack and the fp32
+// rounding of the subtraction): the result never exceeds the true squared gap.
+ICPB_HD float icpb_gap2f(float lo, float hi, float u, float slack)
+{
+    const float gap = fmaxf(fmaxf(lo - u, u - hi) - slack, 0.0f);
+    return gap * gap;
+}
+// lower bound of the squared distance to the cube of cell (cx,cy,cz) at `level`
 ICPB_HD float icpb_cell_mindist2f(int level, int cx, int cy, int cz, float ux, float uy, float uz, float slack)
 {
     const float s = (float)(1u << level);
-    float lo, gap, d2;
+    float lo, d2;
     lo = (float)cx * s;
-    gap = fmaxf(fmaxf(lo - ux, ux - (lo + s)) - slack, 0.0f);
-    d2 = gap * gap;
+    d2 = icpb_gap2f(lo, lo + s, ux, slack);
     lo = (float)cy * s;
-    gap = fmaxf(fmaxf(lo - uy, uy - (lo + s)) - slack, 0.0f);
-    d2 += gap * gap;
+    d2 += icpb_gap2f(lo, lo + s, uy, slack);
     lo = (float)cz * s;
-    gap = fmaxf(fmaxf(lo - uz, uz - (lo + s)) - slack, 0.0f);
-    d2 += gap * gap;
+    d2 += icpb_gap2f(lo, lo + s, uz, slack);
+    return d2 * 0.999999f;
+}
+// lower bound of the squared distance to the tight box stored in node word w of cell (cx,cy,cz) at `level` >= 1
+ICPB_HD float icpb_node_mindist2f(uint32_t w, int level, int cx, int cy, int cz, float ux, float uy, float uz, float slack)
+{
+    const float s = (float)(1u << level), q = s * 0.0625f; // exact: small integers times powers of two
+    float lo, d2;
+    lo = (float)cx * s;
+    d2 = icpb_gap2f(ICPB_FMAF((float)((w >> 8) & 15u), q, lo), ICPB_FMAF((float)(((w >> 20) & 15u) + 1u), q, lo), ux, slack);
+    lo = (float)cy * s;
+    d2 += icpb_gap2f(ICPB_FMAF((float)((w >> 12) & 15u), q, lo), ICPB_FMAF((float)(((w >> 24) & 15u) + 1u), q, lo), uy, slack);
+    lo = (float)cz * s;
+    d2 += icpb_gap2f(ICPB_FMAF((float)((w >> 16) & 15u), q, lo), ICPB_FMAF((float)(((w >> 28) & 15u) + 1u), q, lo), uz, slack);
     return d2 * 0.999999f;
 }
 // upper bound of (bound * inv_h^2) in fp32
@@ -138,19 +164,6 @@ ICPB_HD float icpb_bound_cells(double bound, double inv_h2)
     if (!(b < 3.0e38)) return (float)icpb_inf();
     return (float)b * 1.000001f + 1e-30f;
 }
-
-ICPB_HD void icpb_nn_eval(const MPoint &m, uint32_t pos, double qx, double qy, double qz, double &bd2,
-                          unsigned long long &bidx, uint32_t &bpos)
-{
-    const double dx = qx - m.x, dy = qy - m.y, dz = qz - m.z;
-    const double d2 = (dx * dx + dy * dy) + dz * dz;
-    if (d2 < bd2 || (d2 == bd2 && m.idx < bidx)) {
-        bd2 = d2;
-        bidx = m.idx;
-        bpos = pos;
-    }
-}
-
 // squared fp32 radius (cell units) inside which a candidate must be re-evaluated exactly: the fp32 distance of a
 // point that can still beat (or tie) the best is at most sqrt(bound) + (conversion errors of query and point)
 ICPB_HD float icpb_cand_radius2(float boundf, float slack)
@@ -159,184 +172,218 @@ ICPB_HD float icpb_cand_radius2(float boundf, float slack)
     return r * r * 1.00001f;
 }
 
-ICPB_HD void icpb_scan_cell(const GridView &g, int cx, int cy, int cz, double qx, double qy, double qz, float ux, float uy,
-                            float uz, float slack, double dbox2s, double inv_h2, double &bd2, unsigned long long &bidx,
-                            uint32_t &bpos, float &boundf, float &candf)
+// ---- search state of one query ----------------------------------------------------------------------------------
+struct NNState {
+    double qx, qy, qz;  // query, global frame
+    double dbox2s;      // d_box^2 widened by a few ulps (+inf when unbounded)
+    double inv_h2;
+    double bd2;         // best exact squared distance so far
+    unsigned long long bidx;
+    uint32_t bpos;
+    float ux, uy, uz;   // query in cell units (fp32)
+    float slack;
+    float boundf;       // min(d_box^2, bd2) in cell units, rounded up
+    float candf;        // fp32 pre-filter radius^2
+};
+
+ICPB_HD void icpb_nn_refresh_bound(NNState &s)
 {
-    const uint32_t c = ((uint32_t)cz * (uint32_t)g.dim[0][1] + (uint32_t)cy) * (uint32_t)g.dim[0][0] + (uint32_t)cx;
-    const uint32_t s = g.cell_start[c], e = g.cell_start[c + 1];
+    s.boundf = icpb_bound_cells((s.dbox2s < s.bd2) ? s.dbox2s : s.bd2, s.inv_h2);
+    s.candf = icpb_cand_radius2(s.boundf, s.slack);
+}
+
+ICPB_HD void icpb_nn_eval(const MPoint &m, uint32_t pos, NNState &s)
+{
+    const double dx = s.qx - m.x, dy = s.qy - m.y, dz = s.qz - m.z;
+    const double d2 = (dx * dx + dy * dy) + dz * dz;
+    ICPB_COUNT(exact);
+    if (d2 < s.bd2 || (d2 == s.bd2 && m.idx < s.bidx)) {
+        const bool nearer = d2 < s.bd2;
+        s.bd2 = d2;
+        s.bidx = m.idx;
+        s.bpos = pos;
+        if (nearer) icpb_nn_refresh_bound(s);
+    }
+}
+
+ICPB_HD float icpb_dist2f(const FPoint &f, const NNState &s)
+{
+    const float dx = s.ux - f.x, dy = s.uy - f.y, dz = s.uz - f.z;
+    return ICPB_FMAF(dz, dz, ICPB_FMAF(dy, dy, dx * dx));
+}
+
+// scan the contiguous run [p, e) of pts: four candidates per step (the loads are issued together, the tail repeats
+// the last point), exact evaluation only for those inside the pre-filter radius
+ICPB_HD void icpb_scan_run(const GridView &g, uint32_t p, uint32_t e, NNState &s)
+{
     ICPB_COUNT(cells);
-    // four candidates per step: the loads are issued together (memory-level parallelism), the tail repeats the last one
-    for (uint32_t p = s; p < e; p += 4) {
+    for (; p < e; p += 4) {
         const uint32_t last = e - 1;
         const uint32_t p1 = p + 1 < e ? p + 1 : last, p2 = p + 2 < e ? p + 2 : last, p3 = p + 3 < e ? p + 3 : last;
         const FPoint f0 = g.ptsf[p], f1 = g.ptsf[p1], f2 = g.ptsf[p2], f3 = g.ptsf[p3];
-        float dx, dy, dz;
-        dx = ux - f0.x, dy = uy - f0.y, dz = uz - f0.z;
-        const float d0 = dx * dx + dy * dy + dz * dz;
-        dx = ux - f1.x, dy = uy - f1.y, dz = uz - f1.z;
-        const float d1 = dx * dx + dy * dy + dz * dz;
-        dx = ux - f2.x, dy = uy - f2.y, dz = uz - f2.z;
-        const float d2 = dx * dx + dy * dy + dz * dz;
-        dx = ux - f3.x, dy = uy - f3.y, dz = uz - f3.z;
-        const float d3 = dx * dx + dy * dy + dz * dz;
-        if (fminf(fminf(d0, d1), fminf(d2, d3)) > candf) continue; // none can be nearer than the best so far (nor tie)
+        const float d0 = icpb_dist2f(f0, s), d1 = icpb_dist2f(f1, s), d2 = icpb_dist2f(f2, s), d3 = icpb_dist2f(f3, s);
+        if (fminf(fminf(d0, d1), fminf(d2, d3)) > s.candf) continue; // none can be nearer than the best so far (nor tie)
+        if (d0 <= s.candf) icpb_nn_eval(g.pts[p], p, s);
+        if (p1 != p && d1 <= s.candf) icpb_nn_eval(g.pts[p1], p1, s);
+        if (p2 != p1 && d2 <= s.candf) icpb_nn_eval(g.pts[p2], p2, s);
+        if (p3 != p2 && d3 <= s.candf) icpb_nn_eval(g.pts[p3], p3, s);
+    }
+}
+
+// child visiting order as XOR codes relative to the child octant the query is in: 0,1,2,4,3,5,6,7
+#define ICPB_ORD 0x76534210u
+
+// Depth-first walk below node (cx,cy,cz) of level `top` >= 1 whose word is w (already known to be non-empty and
+// within the bound).  trail byte b holds the pending children of the current path's node at level b+1 in visiting
+// order (bit k <-> child near ^ ORD[k]).
+ICPB_HD void icpb_walk(const GridView &g, int top, int cx, int cy, int cz, uint32_t w, NNState &s)
+{
+    unsigned long long tr0 = 0;
+    unsigned int tr1 = 0;
+    int lev = top;
+    bool enter = true; // the current node was just entered: w is its word
+    for (;;) {
+        const float hc = (float)(1u << (lev - 1));
+        const unsigned near = (s.ux >= (float)(2 * cx + 1) * hc ? 1u : 0u) | (s.uy >= (float)(2 * cy + 1) * hc ? 2u : 0u) |
+                              (s.uz >= (float)(2 * cz + 1) * hc ? 4u : 0u);
+        const int b = lev - 1;
+        unsigned pend;
+        if (enter) {
+            // occupancy bits permuted into visiting order
+            pend = 0;
 #ifdef __CUDACC__
 #pragma unroll
 #endif
-        for (int k = 0; k < 4; ++k) {
-            const float dk = k == 0 ? d0 : (k == 1 ? d1 : (k == 2 ? d2 : d3));
-            const uint32_t pk = k == 0 ? p : (k == 1 ? p1 : (k == 2 ? p2 : p3));
-            if (dk > candf || (k > 0 && pk != p + (uint32_t)k)) continue; // filtered, or a repeated tail slot
-            ICPB_COUNT(exact);
-            const double before = bd2;
-            icpb_nn_eval(g.pts[pk], pk, qx, qy, qz, bd2, bidx, bpos);
-            if (bd2 < before) {
-                boundf = icpb_bound_cells((dbox2s < bd2) ? dbox2s : bd2, inv_h2);
-                candf = icpb_cand_radius2(boundf, slack);
-            }
+            for (int k = 0; k < 8; ++k) pend |= ((w >> (near ^ ((ICPB_ORD >> (4 * k)) & 7u))) & 1u) << k;
+            ICPB_COUNT(expands);
+            enter = false;
+        } else {
+            pend = b < 8 ? (unsigned)(tr0 >> (8 * b)) & 255u : (tr1 >> (8 * (b - 8))) & 255u;
         }
+        if (pend == 0) { // this node is finished: back to its parent
+            if (lev == top) return;
+            ++lev;
+            cx >>= 1, cy >>= 1, cz >>= 1;
+            continue;
+        }
+#ifdef __CUDA_ARCH__
+        const int k = __ffs((int)pend) - 1;
+#else
+        const int k = __builtin_ctz(pend);
+#endif
+        pend &= pend - 1u;
+        if (b < 8)
+            tr0 = (tr0 & ~(255ull << (8 * b))) | ((unsigned long long)pend << (8 * b));
+        else
+            tr1 = (tr1 & ~(255u << (8 * (b - 8)))) | (pend << (8 * (b - 8)));
+        const unsigned ch = near ^ ((ICPB_ORD >> (4 * k)) & 7u);
+        const int x = 2 * cx + (int)(ch & 1u), y = 2 * cy + (int)((ch >> 1) & 1u), z = 2 * cz + (int)((ch >> 2) & 1u);
+        ICPB_COUNT(pops);
+        if (icpb_cell_mindist2f(lev - 1, x, y, z, s.ux, s.uy, s.uz, s.slack) > s.boundf) continue;
+        if (lev == 1) {
+            const uint32_t c = ((uint32_t)z * (uint32_t)g.dim[0][1] + (uint32_t)y) * (uint32_t)g.dim[0][0] + (uint32_t)x;
+            icpb_scan_run(g, g.cell_start[c], g.cell_start[c + 1], s);
+            continue;
+        }
+        const size_t ci = ((size_t)z * g.dim[lev - 1][1] + y) * g.dim[lev - 1][0] + x;
+        const uint32_t cw = g.node[lev - 1][ci];
+        ICPB_COUNT(nodes);
+        if (icpb_node_mindist2f(cw, lev - 1, x, y, z, s.ux, s.uy, s.uz, s.slack) > s.boundf) continue; // tight box
+        --lev;
+        cx = x, cy = y, cz = z;
+        w = cw;
+        enter = true;
     }
 }
 
 // Exact NN of q.  dbox2s = d_box^2 widened by a few ulps (+inf when unbounded);
 // warm_pos = position in pts[] of a candidate to seed the bound (ICPB_NONE for none).
 // Returns the position in pts[] (ICPB_NONE if the model is empty or nothing lies
-// within the bound) and the exact squared distance.  *visited counts cells scanned.
+// within the bound) and the exact squared distance; start_level = level the search started at.
 ICPB_HD void icpb_nn_search(const GridView &g, double qx, double qy, double qz, double dbox2s, uint32_t warm_pos,
                             uint32_t &out_pos, double &out_d2, int &start_level)
 {
-    const double INF = icpb_inf();
-    double bd2 = INF;
-    unsigned long long bidx = ~0ull;
-    uint32_t bpos = ICPB_NONE;
+    NNState s;
+    s.qx = qx, s.qy = qy, s.qz = qz;
+    s.dbox2s = dbox2s;
+    s.inv_h2 = g.inv_h * g.inv_h;
+    s.bd2 = icpb_inf();
+    s.bidx = ~0ull;
+    s.bpos = ICPB_NONE;
     start_level = 0;
     out_pos = ICPB_NONE;
-    out_d2 = INF;
+    out_d2 = s.bd2;
     if (g.n == 0) return;
-    if (warm_pos < g.n) icpb_nn_eval(g.pts[warm_pos], warm_pos, qx, qy, qz, bd2, bidx, bpos);
+    s.ux = (float)((qx - g.o[0]) * g.inv_h);
+    s.uy = (float)((qy - g.o[1]) * g.inv_h);
+    s.uz = (float)((qz - g.o[2]) * g.inv_h);
+    s.slack = 1e-6f * (fmaxf(fmaxf(fabsf(s.ux), fabsf(s.uy)), fabsf(s.uz)) + 4096.0f);
+    s.boundf = s.candf = (float)icpb_inf();
+    if (warm_pos < g.n) icpb_nn_eval(g.pts[warm_pos], warm_pos, s);
+    if (!(s.boundf < (float)icpb_inf())) icpb_nn_refresh_bound(s); // no warm start: the bound is d_box
 
-    double bound = (dbox2s < bd2) ? dbox2s : bd2;
-    // start level: smallest l with h*2^l >= 2U, so the ball spans <= 2 cells per axis
+    // radius of the ball in cell units, rounded up: covers the fp32 copy's distance from the exact query coordinate
+    const float ru = sqrtf(s.boundf) * 1.000001f + s.slack;
+    // start level: smallest l with 2^l >= 2*(ru + slack), so the ball spans <= 2 cells per axis even after the fp32
+    // rounding of the range arithmetic below (which the extra slack dominates)
     int l = 0;
-    double U = INF;
-    if (bound < INF) {
-        U = sqrt(bound) * (1.0 + 1e-15) + g.eps;
-        const double ratio = 2.0 * U * g.inv_h;
-        while (l < g.L && (double)(1u << l) < ratio) ++l;
+    if (ru < 1.0e30f) {
+        while (l < g.L && (float)(1u << l) < 2.0f * (ru + s.slack)) ++l;
     } else {
         l = g.L;
     }
     start_level = l;
-
-    // traversal state in fp32 cell units
-    const double inv_h2 = g.inv_h * g.inv_h;
-    const double uxd = (qx - g.o[0]) * g.inv_h, uyd = (qy - g.o[1]) * g.inv_h, uzd = (qz - g.o[2]) * g.inv_h;
-    const float ux = (float)uxd, uy = (float)uyd, uz = (float)uzd;
-    const float slack = 1e-6f * (fmaxf(fmaxf(fabsf(ux), fabsf(uy)), fabsf(uz)) + 4096.0f);
-    float boundf = icpb_bound_cells(bound, inv_h2);
-    float candf = icpb_cand_radius2(boundf, slack);
-
-    unsigned long long stack[ICPB_SEARCH_STACK];
-    int sp = 0;
-    {
-        const double inv_hl = g.inv_h / (double)(1u << l);
-        int lo[3], hi[3];
-        const double q[3] = {qx, qy, qz};
-        for (int a = 0; a < 3; ++a) {
-            const double dm1 = (double)(g.dim[l][a] - 1);
-            double flo = floor((q[a] - U - g.o[a]) * inv_hl);
-            double fhi = floor((q[a] + U - g.o[a]) * inv_hl);
-            if (!(flo > 0.0)) flo = 0.0; // also catches -inf / NaN
-            if (!(fhi < dm1)) fhi = dm1;
-            if (flo > dm1 || fhi < 0.0) { // ball misses the grid on this axis
-                out_pos = bpos;
-                out_d2 = bd2;
-                return;
-            }
-            lo[a] = (int)flo;
-            hi[a] = (int)fhi;
+    // the <= 2 cells per axis the ball touches at level l: `near` holds the query (or is the closest), `far` the other
+    const float inv_s = 1.0f / (float)(1u << l);
+    int cn[3], cf[3];
+    const float u[3] = {s.ux, s.uy, s.uz};
+    for (int a = 0; a < 3; ++a) {
+        const float dm1 = (float)(g.dim[l][a] - 1);
+        float flo = floorf((u[a] - ru) * inv_s), fhi = floorf((u[a] + ru) * inv_s);
+        if (!(flo > 0.0f)) flo = 0.0f; // also -inf / NaN
+        if (!(fhi < dm1)) fhi = dm1;
+        if (flo > fhi) { // the ball misses the grid on this axis
+            out_pos = s.bpos;
+            out_d2 = s.bd2;
+            return;
         }
-        float best_md2 = (float)INF;
-        int best_at = -1;
-        for (int z = lo[2]; z <= hi[2]; ++z)
-            for (int y = lo[1]; y <= hi[1]; ++y)
-                for (int x = lo[0]; x <= hi[0]; ++x) {
-                    const float md2 = icpb_cell_mindist2f(l, x, y, z, ux, uy, uz, slack);
-                    if (md2 > boundf) continue;
-                    if (sp >= ICPB_SEARCH_STACK - 64) continue; // cannot happen (<= 27 roots)
-                    if (md2 < best_md2) {
-                        best_md2 = md2;
-                        best_at = sp;
-                    }
-                    stack[sp++] = ((unsigned long long)l << 60) | ((unsigned long long)z << 40) |
-                                  ((unsigned long long)y << 20) | (unsigned long long)x;
-                }
-        if (best_at >= 0) { // nearest root on top
-            const unsigned long long t = stack[best_at];
-            stack[best_at] = stack[sp - 1];
-            stack[sp - 1] = t;
-        }
+        float fc = floorf(u[a] * inv_s);
+        fc = fminf(fmaxf(fc, flo), fhi);
+        cn[a] = (int)fc;
+        cf[a] = (fc == flo) ? (int)fhi : (int)flo; // == cn[a] when the ball stays inside one cell
     }
 
-    // Two-phase ("while-while") traversal: every lane first walks the pyramid until it holds a cell group to scan
-    // (a level-1 node, or a level-0 root cell), then scans it -- lanes of a warp stay in the same code section
-    // instead of interleaving node expansion with candidate evaluation.
-    const unsigned ORD = 0x76534210u; // child visiting order as XOR codes: 0,1,2,4,3,5,6,7
-    for (;;) {
-        int have = 0, lx = 0, ly = 0, lz = 0;
-        unsigned lmask = 0;
-        while (sp > 0) {
-            const unsigned long long e = stack[--sp];
+    if (l == 0) {
+        // at most 2x2x2 level-0 cells; x-adjacent cells are contiguous in pts[]: <= 4 runs, the query's column first
+        const int x0 = cn[0] < cf[0] ? cn[0] : cf[0], x1 = cn[0] < cf[0] ? cf[0] : cn[0];
+        const float gx = fminf(icpb_gap2f((float)x0, (float)(x0 + 1), s.ux, s.slack), icpb_gap2f((float)x1, (float)(x1 + 1), s.ux, s.slack));
+#ifdef __CUDACC__
+#pragma unroll
+#endif
+        for (int k = 0; k < 4; ++k) {
+            const int y = (k & 1) ? cf[1] : cn[1], z = (k & 2) ? cf[2] : cn[2];
+            if (((k & 1) && cf[1] == cn[1]) || ((k & 2) && cf[2] == cn[2])) continue;
+            const float md = (gx + icpb_gap2f((float)y, (float)(y + 1), s.uy, s.slack) + icpb_gap2f((float)z, (float)(z + 1), s.uz, s.slack)) * 0.999999f;
             ICPB_COUNT(pops);
-            const int lev = (int)(e >> 60);
-            const int cx = (int)(e & 0xFFFFFu), cy = (int)((e >> 20) & 0xFFFFFu), cz = (int)((e >> 40) & 0xFFFFFu);
-            if (icpb_cell_mindist2f(lev, cx, cy, cz, ux, uy, uz, slack) > boundf) continue;
-            if (lev == 0) {
-                have = 1;
-                lx = cx, ly = cy, lz = cz;
-                break;
-            }
-            const size_t ci = ((size_t)cz * g.dim[lev][1] + cy) * g.dim[lev][0] + cx;
-            const unsigned m = g.mask[lev][ci];
-            ICPB_COUNT(nodes);
-            if (!m) continue;
-            if (lev == 1) {
-                have = 2;
-                lmask = m;
-                lx = cx, ly = cy, lz = cz;
-                break;
-            }
-            const float hc = (float)(1u << (lev - 1));
-            const unsigned near = (ux >= (float)(2 * cx + 1) * hc ? 1u : 0u) | (uy >= (float)(2 * cy + 1) * hc ? 2u : 0u) |
-                                  (uz >= (float)(2 * cz + 1) * hc ? 4u : 0u);
-            for (int k = 7; k >= 0; --k) {
-                const unsigned ch = near ^ ((ORD >> (4 * k)) & 7u);
-                if (!((m >> ch) & 1u)) continue;
-                const int x = 2 * cx + (int)(ch & 1u), y = 2 * cy + (int)((ch >> 1) & 1u),
-                          z = 2 * cz + (int)((ch >> 2) & 1u);
-                if (icpb_cell_mindist2f(lev - 1, x, y, z, ux, uy, uz, slack) > boundf) continue;
-                if (sp < ICPB_SEARCH_STACK)
-                    stack[sp++] = ((unsigned long long)(lev - 1) << 60) | ((unsigned long long)z << 40) |
-                                  ((unsigned long long)y << 20) | (unsigned long long)x;
-            }
+            if (md > s.boundf) continue;
+            const uint32_t c = ((uint32_t)z * (uint32_t)g.dim[0][1] + (uint32_t)y) * (uint32_t)g.dim[0][0];
+            icpb_scan_run(g, g.cell_start[c + (uint32_t)x0], g.cell_start[c + (uint32_t)x1 + 1u], s);
         }
-        if (!have) break;
-        if (have == 1) {
-            icpb_scan_cell(g, lx, ly, lz, qx, qy, qz, ux, uy, uz, slack, dbox2s, inv_h2, bd2, bidx, bpos, boundf, candf);
-        } else {
-            const unsigned near = (ux >= (float)(2 * lx + 1) ? 1u : 0u) | (uy >= (float)(2 * ly + 1) ? 2u : 0u) |
-                                  (uz >= (float)(2 * lz + 1) ? 4u : 0u);
-            for (int k = 0; k < 8; ++k) {
-                const unsigned ch = near ^ ((ORD >> (4 * k)) & 7u);
-                if (!((lmask >> ch) & 1u)) continue;
-                const int x = 2 * lx + (int)(ch & 1u), y = 2 * ly + (int)((ch >> 1) & 1u),
-                          z = 2 * lz + (int)((ch >> 2) & 1u);
-                if (icpb_cell_mindist2f(0, x, y, z, ux, uy, uz, slack) > boundf) continue;
-                icpb_scan_cell(g, x, y, z, qx, qy, qz, ux, uy, uz, slack, dbox2s, inv_h2, bd2, bidx, bpos, boundf, candf);
-            }
+    } else {
+        for (int k = 0; k < 8; ++k) {
+            const unsigned code = (ICPB_ORD >> (4 * k)) & 7u;
+            if (((code & 1u) && cf[0] == cn[0]) || ((code & 2u) && cf[1] == cn[1]) || ((code & 4u) && cf[2] == cn[2])) continue;
+            const int x = (code & 1u) ? cf[0] : cn[0], y = (code & 2u) ? cf[1] : cn[1], z = (code & 4u) ? cf[2] : cn[2];
+            ICPB_COUNT(pops);
+            if (icpb_cell_mindist2f(l, x, y, z, s.ux, s.uy, s.uz, s.slack) > s.boundf) continue;
+            const size_t ci = ((size_t)z * g.dim[l][1] + y) * g.dim[l][0] + x;
+            const uint32_t w = g.node[l][ci];
+            ICPB_COUNT(nodes);
+            if (!(w & 255u)) continue;
+            if (icpb_node_mindist2f(w, l, x, y, z, s.ux, s.uy, s.uz, s.slack) > s.boundf) continue;
+            icpb_walk(g, l, x, y, z, w, s);
         }
     }
-    out_pos = bpos;
-    out_d2 = bd2;
+    out_pos = s.bpos;
+    out_d2 = s.bd2;
 }

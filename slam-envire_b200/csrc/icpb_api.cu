@@ -195,7 +195,7 @@ struct icpb_ctx {
     GridDims gdims;
     unsigned long long merges = 0;
     DevBuf<uint32_t> cell_start;
-    DevBuf<uint8_t> masks;
+    DevBuf<uint32_t> masks;
     DevBuf<uint32_t> keys0, keys1, vals0, vals1, sort_scratch;
     DevBuf<double> bbox_part;
     GridView gv;
@@ -621,7 +621,7 @@ static void dims_for(const double ext[3], double h, int d[3])
     }
 }
 
-// occupancy pyramid from the level-0 prefix array (also after a merge-append)
+// pyramid of node words (occupancy + tight boxes) from the level-0 prefix array (also after a merge-append)
 static int build_masks(icpb_ctx *ctx)
 {
     cudaStream_t s = ctx->stream;
@@ -638,15 +638,14 @@ static int build_masks(icpb_ctx *ctx)
     g.L = L;
     CK(ctx->masks.ensure(mask_total + 16));
     for (int l = 1; l <= L; ++l) {
-        uint8_t *ml = ctx->masks.p + mask_off[l];
-        g.mask[l] = ml;
+        uint32_t *ml = ctx->masks.p + mask_off[l];
+        g.node[l] = ml;
         const size_t cells = (size_t)g.dim[l][0] * g.dim[l][1] * g.dim[l][2];
         if (l == 1)
-            mask_level1_kernel<<<grid_for(cells, 256), 256, 0, s>>>(ctx->cell_start.p, g.dim[0][0], g.dim[0][1],
-                                                                    g.dim[0][2], g.dim[1][0], g.dim[1][1],
-                                                                    g.dim[1][2], ml);
+            node_level1_kernel<<<grid_for(cells, 256), 256, 0, s>>>(ctx->cell_start.p, ctx->pts.p, ctx->gdims, g.dim[1][0],
+                                                                    g.dim[1][1], g.dim[1][2], ml);
         else
-            mask_levelN_kernel<<<grid_for(cells, 256), 256, 0, s>>>(g.mask[l - 1], g.dim[l - 1][0], g.dim[l - 1][1],
+            node_levelN_kernel<<<grid_for(cells, 256), 256, 0, s>>>(g.node[l - 1], g.dim[l - 1][0], g.dim[l - 1][1],
                                                                     g.dim[l - 1][2], g.dim[l][0], g.dim[l][1],
                                                                     g.dim[l][2], ml);
         CKL();

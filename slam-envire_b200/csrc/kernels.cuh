@@ -240,37 +240,57 @@ __global__ void add_prefix_kernel(uint32_t *__restrict__ cell_start, const uint3
     if (i < n) cell_start[i] += newpref[i];
 }
 
-// level-1 occupancy masks from the level-0 prefix array
-__global__ void mask_level1_kernel(const uint32_t *__restrict__ cell_start, int nx, int ny, int nz, int mx, int my,
-                                   int mz, uint8_t *__restrict__ mask)
+// level-1 node words (child occupancy + tight box of the points below, grid_view.h) from the level-0 prefix array
+__global__ void node_level1_kernel(const uint32_t *__restrict__ cell_start, const MPoint *__restrict__ pts, GridDims g,
+                                   int mx, int my, int mz, uint32_t *__restrict__ node)
 {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)mx * my * mz) return;
     const int cx = (int)(t % mx), cy = (int)((t / mx) % my), cz = (int)(t / ((size_t)mx * my));
     unsigned m = 0;
+    int lo[3] = {15, 15, 15}, hi[3] = {0, 0, 0};
+    const double cl[3] = {2.0 * cx, 2.0 * cy, 2.0 * cz};
     for (int ch = 0; ch < 8; ++ch) {
         const int x = 2 * cx + (ch & 1), y = 2 * cy + ((ch >> 1) & 1), z = 2 * cz + ((ch >> 2) & 1);
-        if (x >= nx || y >= ny || z >= nz) continue;
-        const size_t c = ((size_t)z * ny + y) * nx + x;
-        if (cell_start[c + 1] > cell_start[c]) m |= 1u << ch;
+        if (x >= g.nx || y >= g.ny || z >= g.nz) continue;
+        const size_t c = ((size_t)z * g.ny + y) * g.nx + x;
+        const uint32_t s = cell_start[c], e = cell_start[c + 1];
+        if (e == s) continue;
+        m |= 1u << ch;
+        for (uint32_t p = s; p < e; ++p) {
+            const MPoint q = pts[p];
+            const double u[3] = {(q.x - g.o[0]) * g.inv_h, (q.y - g.o[1]) * g.inv_h, (q.z - g.o[2]) * g.inv_h};
+            for (int a = 0; a < 3; ++a) {
+                const int nb = icpb_node_nibble(u[a], cl[a], 1);
+                lo[a] = min(lo[a], nb);
+                hi[a] = max(hi[a], nb);
+            }
+        }
     }
-    mask[t] = (uint8_t)m;
+    node[t] = m ? icpb_node_word(m, lo, hi) : 0u;
 }
 
-// level-l masks (l >= 2) from the masks one level below
-__global__ void mask_levelN_kernel(const uint8_t *__restrict__ below, int nx, int ny, int nz, int mx, int my, int mz,
-                                   uint8_t *__restrict__ mask)
+// level-l node words (l >= 2) from the words one level below
+__global__ void node_levelN_kernel(const uint32_t *__restrict__ below, int nx, int ny, int nz, int mx, int my, int mz,
+                                   uint32_t *__restrict__ node)
 {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)mx * my * mz) return;
     const int cx = (int)(t % mx), cy = (int)((t / mx) % my), cz = (int)(t / ((size_t)mx * my));
     unsigned m = 0;
+    int lo[3] = {15, 15, 15}, hi[3] = {0, 0, 0};
     for (int ch = 0; ch < 8; ++ch) {
         const int x = 2 * cx + (ch & 1), y = 2 * cy + ((ch >> 1) & 1), z = 2 * cz + ((ch >> 2) & 1);
         if (x >= nx || y >= ny || z >= nz) continue;
-        if (below[((size_t)z * ny + y) * nx + x]) m |= 1u << ch;
+        const uint32_t w = below[((size_t)z * ny + y) * nx + x];
+        if (!(w & 255u)) continue;
+        m |= 1u << ch;
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = min(lo[a], icpb_nibble_up(w, 8 + 4 * a, (ch >> a) & 1));
+            hi[a] = max(hi[a], icpb_nibble_up(w, 20 + 4 * a, (ch >> a) & 1));
+        }
     }
-    mask[t] = (uint8_t)m;
+    node[t] = m ? icpb_node_word(m, lo, hi) : 0u;
 }
 
 // ---------------------------------------------------------------------------
@@ -288,11 +308,17 @@ __global__ void __launch_bounds__(SEARCH_THREADS, ICPB_SEARCH_MIN_BLOCKS)
                   double *__restrict__ nn_d, int use_warm, const EanView ean)
 {
     if (st->done) return;
+    __shared__ double M[12]; // C_local2globalnew: broadcast reads instead of per-thread global loads
+    __shared__ unsigned int blk_found, blk_far;
+    if (threadIdx.x < 12) M[threadIdx.x] = st->M[threadIdx.x];
+    if (threadIdx.x == 12) blk_found = 0;
+    if (threadIdx.x == 13) blk_far = 0;
+    __syncthreads();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned found = 0, far = 0;
     if (i < n) {
         double qx, qy, qz;
-        icpb_aff_apply(st->M, sx[i], sy[i], sz[i], qx, qy, qz); // C_local2globalnew * v (icp/icp.hpp:130)
+        icpb_aff_apply(M, sx[i], sy[i], sz[i], qx, qy, qz); // C_local2globalnew * v (icp/icp.hpp:130)
         const double d_box = st->d_box;
         const double dbox2s = d_box * d_box * (1.0 + 1e-12);
         const uint32_t warm = (use_warm && st->warm) ? nn_pos[i] : ICPB_NONE;
@@ -306,9 +332,9 @@ __global__ void __launch_bounds__(SEARCH_THREADS, ICPB_SEARCH_MIN_BLOCKS)
             // EdgeAndNormalPairFilter (icp/icp.hpp:206-221) on the nearest neighbour: neither vertex on a scan edge,
             // normals (source normal mapped by C_local2globalnew.linear()) less than pi/8 apart
             const double ax = ean.snx[i], ay = ean.sny[i], az = ean.snz[i];
-            const double bx = (st->M[0] * ax + st->M[1] * ay) + st->M[2] * az;
-            const double by = (st->M[4] * ax + st->M[5] * ay) + st->M[6] * az;
-            const double bz = (st->M[8] * ax + st->M[9] * ay) + st->M[10] * az;
+            const double bx = (M[0] * ax + M[1] * ay) + M[2] * az;
+            const double by = (M[4] * ax + M[5] * ay) + M[6] * az;
+            const double bz = (M[8] * ax + M[9] * ay) + M[10] * az;
             const NPoint mn = ean.mn[pos];
             const double dot = (bx * mn.nx + by * mn.ny) + bz * mn.nz;
             const bool edge = ean.sedge[i] || mn.edge;
@@ -323,8 +349,13 @@ __global__ void __launch_bounds__(SEARCH_THREADS, ICPB_SEARCH_MIN_BLOCKS)
     found = __reduce_add_sync(0xFFFFFFFFu, found);
     far = __reduce_add_sync(0xFFFFFFFFu, far);
     if ((threadIdx.x & 31) == 0) {
-        if (found) atomicAdd(&st->found, (unsigned long long)found);
-        if (far) atomicAdd(&st->far, (unsigned long long)far);
+        if (found) atomicAdd(&blk_found, found);
+        if (far) atomicAdd(&blk_far, far);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (blk_found) atomicAdd(&st->found, (unsigned long long)blk_found);
+        if (blk_far) atomicAdd(&st->far, (unsigned long long)blk_far);
     }
 }
 

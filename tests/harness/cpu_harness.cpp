@@ -13,7 +13,7 @@
 #include <numeric>
 #include <vector>
 
-struct HsCounters { unsigned long long cells, cands, pops, nodes, exact; };
+struct HsCounters { unsigned long long cells, cands, pops, nodes, exact, expands; };
 static HsCounters g_cnt;
 #define ICPB_COUNT(what) (++g_cnt.what)
 #include "../../slam-envire_b200/csrc/grid_view.h"
@@ -25,7 +25,7 @@ struct HostGrid {
     std::vector<MPoint> pts;
     std::vector<FPoint> ptsf;
     std::vector<uint32_t> cell_start;
-    std::vector<std::vector<uint8_t>> masks;
+    std::vector<std::vector<uint32_t>> masks;
     std::vector<uint32_t> pos_of_idx;
 };
 
@@ -85,18 +85,39 @@ void build(HostGrid &G, const double *model, size_t n, double h)
             for (int cy = 0; cy < d[1]; ++cy)
                 for (int cx = 0; cx < d[0]; ++cx) {
                     unsigned m = 0;
+                    int lo[3] = {15, 15, 15}, hi[3] = {0, 0, 0};
                     for (int ch = 0; ch < 8; ++ch) {
                         const int x = 2 * cx + (ch & 1), y = 2 * cy + ((ch >> 1) & 1), z = 2 * cz + ((ch >> 2) & 1);
                         if (x >= b[0] || y >= b[1] || z >= b[2]) continue;
                         const size_t c = ((size_t)z * b[1] + y) * b[0] + x;
-                        const bool occ = (L == 1) ? (G.cell_start[c + 1] > G.cell_start[c]) : (G.masks[L - 1][c] != 0);
-                        if (occ) m |= 1u << ch;
+                        if (L == 1) {
+                            if (G.cell_start[c + 1] == G.cell_start[c]) continue;
+                            m |= 1u << ch;
+                            const double cl[3] = {2.0 * cx, 2.0 * cy, 2.0 * cz};
+                            for (uint32_t p = G.cell_start[c]; p < G.cell_start[c + 1]; ++p) {
+                                const double u[3] = {(G.pts[p].x - g.o[0]) * g.inv_h, (G.pts[p].y - g.o[1]) * g.inv_h,
+                                                     (G.pts[p].z - g.o[2]) * g.inv_h};
+                                for (int a = 0; a < 3; ++a) {
+                                    const int q = icpb_node_nibble(u[a], cl[a], 1);
+                                    lo[a] = std::min(lo[a], q);
+                                    hi[a] = std::max(hi[a], q);
+                                }
+                            }
+                        } else {
+                            const uint32_t w = G.masks[L - 1][c];
+                            if (!(w & 255u)) continue;
+                            m |= 1u << ch;
+                            for (int a = 0; a < 3; ++a) {
+                                lo[a] = std::min(lo[a], icpb_nibble_up(w, 8 + 4 * a, (ch >> a) & 1));
+                                hi[a] = std::max(hi[a], icpb_nibble_up(w, 20 + 4 * a, (ch >> a) & 1));
+                            }
+                        }
                     }
-                    G.masks[L][((size_t)cz * d[1] + cy) * d[0] + cx] = (uint8_t)m;
+                    G.masks[L][((size_t)cz * d[1] + cy) * d[0] + cx] = m ? icpb_node_word(m, lo, hi) : 0u;
                 }
     }
     g.L = L;
-    for (int l = 1; l <= L; ++l) g.mask[l] = G.masks[l].data();
+    for (int l = 1; l <= L; ++l) g.node[l] = G.masks[l].data();
     g.cell_start = G.cell_start.data();
     g.pts = G.pts.data();
     g.ptsf = G.ptsf.data();
@@ -107,7 +128,7 @@ void build(HostGrid &G, const double *model, size_t n, double h)
 extern "C" {
 void hs_counters(unsigned long long *out, int reset)
 {
-    out[0] = g_cnt.cells; out[1] = g_cnt.cands; out[2] = g_cnt.pops; out[3] = g_cnt.nodes; out[4] = g_cnt.exact;
+    out[0] = g_cnt.cells; out[1] = g_cnt.cands; out[2] = g_cnt.pops; out[3] = g_cnt.nodes; out[4] = g_cnt.exact; out[5] = g_cnt.expands;
     if (reset) memset(&g_cnt, 0, sizeof(g_cnt));
 }
 
