@@ -183,7 +183,7 @@ struct NNState {
     float ux, uy, uz;   // query in cell units (fp32)
     float slack;
     float boundf;       // min(d_box^2, bd2) in cell units, rounded up
-    float candf;        // fp32 pre-filter radius^2
+    float candf;        // fp32 pre-filter radius^2 that follows from boundf
 };
 
 ICPB_HD void icpb_nn_refresh_bound(NNState &s)
@@ -211,8 +211,63 @@ ICPB_HD float icpb_dist2f(const FPoint &f, const NNState &s)
     const float dx = s.ux - f.x, dy = s.uy - f.y, dz = s.uz - f.z;
     return ICPB_FMAF(dz, dz, ICPB_FMAF(dy, dy, dx * dx));
 }
+// Scan up to four contiguous runs [s_k, e_k) of pts (empty runs have e_k <= s_k) in ONE loop: every trip tests four
+// candidates of the lane's current run (the loads are issued together, the tail repeats the last point) and moves on
+// to the lane's next run when this one is exhausted -- the lanes of a warp stay busy until their own candidates run
+// out instead of waiting for each other run by run.  The fp32 pre-filter only MARKS the candidates that can still
+// win (one bit per point, 32 points at a time); the marked ones are then evaluated exactly back to back.  The point
+// that already is the best (the warm start, usually) is not evaluated again.
+ICPB_HD void icpb_flush_marks(const GridView &g, uint32_t base, uint32_t &marks, NNState &s)
+{
+    while (marks) {
+#ifdef __CUDA_ARCH__
+        const uint32_t pos = base + (uint32_t)(__ffs((int)marks) - 1);
+#else
+        const uint32_t pos = base + (uint32_t)__builtin_ctz(marks);
+#endif
+        marks &= marks - 1u;
+        if (pos != s.bpos) icpb_nn_eval(g.pts[pos], pos, s);
+    }
+}
+ICPB_HD void icpb_scan_runs(const GridView &g, uint32_t s0, uint32_t e0, uint32_t s1, uint32_t e1, uint32_t s2,
+                            uint32_t e2, uint32_t s3, uint32_t e3, NNState &s)
+{
+    uint32_t p = s0, e = e0, base = s0, marks = 0;
+    int r = 0;
+    for (;;) {
+        if (p >= e) { // this run is done: evaluate what it marked, then the lane's next non-empty run
+            icpb_flush_marks(g, base, marks, s);
+            do {
+                ++r;
+                if (r > 3) return;
+                p = r == 1 ? s1 : (r == 2 ? s2 : s3);
+                e = r == 1 ? e1 : (r == 2 ? e2 : e3);
+            } while (p >= e);
+            base = p;
+        }
+        ICPB_COUNT(cells);
+        const uint32_t last = e - 1;
+        const uint32_t p1 = p + 1 < e ? p + 1 : last, p2 = p + 2 < e ? p + 2 : last, p3 = p + 3 < e ? p + 3 : last;
+        const FPoint f0 = g.ptsf[p], f1 = g.ptsf[p1], f2 = g.ptsf[p2], f3 = g.ptsf[p3];
+        const float d0 = icpb_dist2f(f0, s), d1 = icpb_dist2f(f1, s), d2 = icpb_dist2f(f2, s), d3 = icpb_dist2f(f3, s);
+        const float cf = s.candf;
+        const uint32_t sh = p - base;
+        marks |= (d0 <= cf ? 1u : 0u) << sh;
+        marks |= ((d1 <= cf && p1 != p) ? 2u : 0u) << sh;
+        marks |= ((d2 <= cf && p2 != p1) ? 4u : 0u) << sh;
+        marks |= ((d3 <= cf && p3 != p2) ? 8u : 0u) << sh;
+        p += 4;
+        // 32 marks are full -- or there is no bound yet (first candidates of a cold search): evaluate now
+        if ((sh == 28u || !(cf < 3.0e38f)) && p < e) {
+            icpb_flush_marks(g, base, marks, s);
+            base = p;
+        }
+    }
+}
 
-// scan the contiguous run [p, e) of pts: four candidates per step (the loads are issued together, the tail repeats
+// The walk below scans one level-0 cell at a time, where only a few lanes of a warp are at a cell together: there the
+// candidates that pass the pre-filter are evaluated on the spot (the bound tightens at once and prunes the walk).
+// Scan the contiguous run [p, e) of pts: four candidates per step (the loads are issued together, the tail repeats
 // the last point), exact evaluation only for those inside the pre-filter radius
 ICPB_HD void icpb_scan_run(const GridView &g, uint32_t p, uint32_t e, NNState &s)
 {
@@ -319,6 +374,7 @@ ICPB_HD void icpb_nn_search(const GridView &g, double qx, double qy, double qz, 
     s.uz = (float)((qz - g.o[2]) * g.inv_h);
     s.slack = 1e-6f * (fmaxf(fmaxf(fabsf(s.ux), fabsf(s.uy)), fabsf(s.uz)) + 4096.0f);
     s.boundf = s.candf = (float)icpb_inf();
+    const float u[3] = {s.ux, s.uy, s.uz};
     if (warm_pos < g.n) icpb_nn_eval(g.pts[warm_pos], warm_pos, s);
     if (!(s.boundf < (float)icpb_inf())) icpb_nn_refresh_bound(s); // no warm start: the bound is d_box
 
@@ -334,9 +390,8 @@ ICPB_HD void icpb_nn_search(const GridView &g, double qx, double qy, double qz, 
     }
     start_level = l;
     // the <= 2 cells per axis the ball touches at level l: `near` holds the query (or is the closest), `far` the other
-    const float inv_s = 1.0f / (float)(1u << l);
+    const float sl = (float)(1u << l), inv_s = 1.0f / sl;
     int cn[3], cf[3];
-    const float u[3] = {s.ux, s.uy, s.uz};
     for (int a = 0; a < 3; ++a) {
         const float dm1 = (float)(g.dim[l][a] - 1);
         float flo = floorf((u[a] - ru) * inv_s), fhi = floorf((u[a] + ru) * inv_s);
@@ -352,37 +407,46 @@ ICPB_HD void icpb_nn_search(const GridView &g, double qx, double qy, double qz, 
         cn[a] = (int)fc;
         cf[a] = (fc == flo) ? (int)fhi : (int)flo; // == cn[a] when the ball stays inside one cell
     }
+    const uint32_t nx0 = (uint32_t)g.dim[0][0], ny0 = (uint32_t)g.dim[0][1];
 
     if (l == 0) {
         // at most 2x2x2 level-0 cells; x-adjacent cells are contiguous in pts[]: <= 4 runs, the query's column first
         const int x0 = cn[0] < cf[0] ? cn[0] : cf[0], x1 = cn[0] < cf[0] ? cf[0] : cn[0];
         const float gx = fminf(icpb_gap2f((float)x0, (float)(x0 + 1), s.ux, s.slack), icpb_gap2f((float)x1, (float)(x1 + 1), s.ux, s.slack));
+        uint32_t rs[4], re[4];
 #ifdef __CUDACC__
 #pragma unroll
 #endif
         for (int k = 0; k < 4; ++k) {
             const int y = (k & 1) ? cf[1] : cn[1], z = (k & 2) ? cf[2] : cn[2];
+            rs[k] = re[k] = 0;
             if (((k & 1) && cf[1] == cn[1]) || ((k & 2) && cf[2] == cn[2])) continue;
             const float md = (gx + icpb_gap2f((float)y, (float)(y + 1), s.uy, s.slack) + icpb_gap2f((float)z, (float)(z + 1), s.uz, s.slack)) * 0.999999f;
             ICPB_COUNT(pops);
             if (md > s.boundf) continue;
-            const uint32_t c = ((uint32_t)z * (uint32_t)g.dim[0][1] + (uint32_t)y) * (uint32_t)g.dim[0][0];
-            icpb_scan_run(g, g.cell_start[c + (uint32_t)x0], g.cell_start[c + (uint32_t)x1 + 1u], s);
+            const uint32_t c = ((uint32_t)z * ny0 + (uint32_t)y) * nx0;
+            rs[k] = g.cell_start[c + (uint32_t)x0];
+            re[k] = g.cell_start[c + (uint32_t)x1 + 1u];
         }
-    } else {
-        for (int k = 0; k < 8; ++k) {
-            const unsigned code = (ICPB_ORD >> (4 * k)) & 7u;
-            if (((code & 1u) && cf[0] == cn[0]) || ((code & 2u) && cf[1] == cn[1]) || ((code & 4u) && cf[2] == cn[2])) continue;
-            const int x = (code & 1u) ? cf[0] : cn[0], y = (code & 2u) ? cf[1] : cn[1], z = (code & 4u) ? cf[2] : cn[2];
-            ICPB_COUNT(pops);
-            if (icpb_cell_mindist2f(l, x, y, z, s.ux, s.uy, s.uz, s.slack) > s.boundf) continue;
-            const size_t ci = ((size_t)z * g.dim[l][1] + y) * g.dim[l][0] + x;
-            const uint32_t w = g.node[l][ci];
-            ICPB_COUNT(nodes);
-            if (!(w & 255u)) continue;
-            if (icpb_node_mindist2f(w, l, x, y, z, s.ux, s.uy, s.uz, s.slack) > s.boundf) continue;
-            icpb_walk(g, l, x, y, z, w, s);
-        }
+        icpb_scan_runs(g, rs[0], re[0], rs[1], re[1], rs[2], re[2], rs[3], re[3], s);
+        out_pos = s.bpos;
+        out_d2 = s.bd2;
+        return;
+    }
+
+    // wider balls: walk the pyramid below the <= 2x2x2 root nodes of level l, nearest root first
+    for (int k = 0; k < 8; ++k) {
+        const unsigned code = (ICPB_ORD >> (4 * k)) & 7u;
+        if (((code & 1u) && cf[0] == cn[0]) || ((code & 2u) && cf[1] == cn[1]) || ((code & 4u) && cf[2] == cn[2])) continue;
+        const int x = (code & 1u) ? cf[0] : cn[0], y = (code & 2u) ? cf[1] : cn[1], z = (code & 4u) ? cf[2] : cn[2];
+        ICPB_COUNT(pops);
+        if (icpb_cell_mindist2f(l, x, y, z, s.ux, s.uy, s.uz, s.slack) > s.boundf) continue;
+        const size_t ci = ((size_t)z * g.dim[l][1] + y) * g.dim[l][0] + x;
+        const uint32_t w = g.node[l][ci];
+        ICPB_COUNT(nodes);
+        if (!(w & 255u)) continue;
+        if (icpb_node_mindist2f(w, l, x, y, z, s.ux, s.uy, s.uz, s.slack) > s.boundf) continue;
+        icpb_walk(g, l, x, y, z, w, s);
     }
     out_pos = s.bpos;
     out_d2 = s.bd2;

@@ -178,7 +178,7 @@ struct icpb_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     // options
-    double opt_cell_size = 0.0, opt_target = 4.0, opt_max_cells = 64.0 * 1024 * 1024, opt_run_ahead = 2.0,
+    double opt_cell_size = 0.0, opt_target = 10.0, opt_max_cells = 64.0 * 1024 * 1024, opt_run_ahead = 2.0,
            opt_warm = 1.0, opt_profile = 0.0, opt_sort = 1.0, opt_margin = 0.0, opt_merge = 1.0, opt_graph = 1.0;
     // model
     DevBuf<double> model_raw, model_nrm;

@@ -309,10 +309,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, ICPB_SEARCH_MIN_BLOCKS)
 {
     if (st->done) return;
     __shared__ double M[12]; // C_local2globalnew: broadcast reads instead of per-thread global loads
-    __shared__ unsigned int blk_found, blk_far;
     if (threadIdx.x < 12) M[threadIdx.x] = st->M[threadIdx.x];
-    if (threadIdx.x == 12) blk_found = 0;
-    if (threadIdx.x == 13) blk_far = 0;
     __syncthreads();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned found = 0, far = 0;
@@ -348,14 +345,9 @@ __global__ void __launch_bounds__(SEARCH_THREADS, ICPB_SEARCH_MIN_BLOCKS)
     }
     found = __reduce_add_sync(0xFFFFFFFFu, found);
     far = __reduce_add_sync(0xFFFFFFFFu, far);
-    if ((threadIdx.x & 31) == 0) {
-        if (found) atomicAdd(&blk_found, found);
-        if (far) atomicAdd(&blk_far, far);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (blk_found) atomicAdd(&st->found, (unsigned long long)blk_found);
-        if (blk_far) atomicAdd(&st->far, (unsigned long long)blk_far);
+    if ((threadIdx.x & 31) == 0) { // no block barrier here: a finished warp frees its slot at once
+        if (found) atomicAdd(&st->found, (unsigned long long)found);
+        if (far) atomicAdd(&st->far, (unsigned long long)far);
     }
 }
 
