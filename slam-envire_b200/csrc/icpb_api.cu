@@ -179,7 +179,7 @@ struct icpb_ctx {
     std::string err;
     // options
     double opt_cell_size = 0.0, opt_target = 10.0, opt_max_cells = 64.0 * 1024 * 1024, opt_run_ahead = 2.0,
-           opt_warm = 1.0, opt_profile = 0.0, opt_sort = 1.0, opt_margin = 0.0, opt_merge = 1.0, opt_graph = 1.0;
+           opt_warm = 1.0, opt_profile = 0.0, opt_sort = 1.0, opt_margin = 0.0, opt_merge = 1.0, opt_graph = 1.0, opt_trim_bpsm = 2.0, opt_mom_bpsm = 2.0;
     // model
     DevBuf<double> model_raw, model_nrm;
     DevBuf<uint8_t> model_edge;
@@ -420,6 +420,8 @@ static double *opt_slot(icpb_ctx *ctx, const char *key)
     if (!strcmp(key, "growth_margin")) return &ctx->opt_margin;
     if (!strcmp(key, "merge_append")) return &ctx->opt_merge;
     if (!strcmp(key, "graph")) return &ctx->opt_graph;
+    if (!strcmp(key, "trim_blocks_per_sm")) return &ctx->opt_trim_bpsm;
+    if (!strcmp(key, "moments_blocks_per_sm")) return &ctx->opt_mom_bpsm;
     return nullptr;
 }
 int icpb_set_option(icpb_ctx *ctx, const char *key, double value)
@@ -998,7 +1000,7 @@ __global__ void tie_quota_kernel(IcpState *st, const unsigned long long *gathere
 static int launch_trim(icpb_ctx *ctx, uint32_t n)
 {
     cudaStream_t s = ctx->stream;
-    const unsigned blocks = std::max(1u, std::min(grid_for(n, SEL_THREADS * 4), 148u * 4u));
+    const unsigned blocks = std::max(1u, std::min(grid_for(n, SEL_THREADS * 4), 148u * (unsigned)std::max(1.0, std::min(ctx->opt_trim_bpsm, 32.0))));
     const int fused = (ctx->n_ranks == 1 || ctx->use_p2p) ? 1 : 0;
     if (fused) {
         // two grid-wide digit passes, then collect the few remaining candidates and finish on them in one block
@@ -1072,7 +1074,7 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
     const size_t n_po = (size_t)((double)ctx->adapter_size * prm->overlap);
     const size_t max_iter = prm->max_iter;
 
-    const unsigned mom_blocks = std::max(1u, std::min(grid_for(n, MOM_THREADS), 148u * 6u));
+    const unsigned mom_blocks = std::max(1u, std::min(grid_for(n, MOM_THREADS), 148u * (unsigned)std::max(1.0, std::min(ctx->opt_mom_bpsm, 32.0))));
     CK(ctx->partials.ensure((size_t)mom_blocks * ICPB_NSUMS));
     ctx->trace_cap = (int)std::min<size_t>(std::max<size_t>(max_iter, 1), 65536);
     CK(ctx->trace.ensure((size_t)ctx->trace_cap * ICPB_TRACE_COLS_DEV));
@@ -1119,6 +1121,8 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
         add_key(&ctx->p2p, sizeof(ctx->p2p));
         add_key(&ctx->trace_cap, sizeof(ctx->trace_cap));
         add_key(&use_warm, sizeof(use_warm));
+        add_key(&mom_blocks, sizeof(mom_blocks));
+        add_key(&ctx->opt_trim_bpsm, sizeof(double));
         void *init_args[11];
         unsigned long long a_max_iter = max_iter, a_n_po = n_po, a_n = n, a_off = 0;
         double a_mse = prm->min_mse, a_diff = prm->min_mse_diff, a_ov = prm->overlap;

@@ -315,10 +315,10 @@ __global__ void __launch_bounds__(SEARCH_THREADS, ICPB_SEARCH_MIN_BLOCKS)
     unsigned found = 0, far = 0;
     if (i < n) {
         double qx, qy, qz;
-        icpb_aff_apply(M, sx[i], sy[i], sz[i], qx, qy, qz); // C_local2globalnew * v (icp/icp.hpp:130)
+        icpb_aff_apply(M, __ldcs(sx + i), __ldcs(sy + i), __ldcs(sz + i), qx, qy, qz); // C_local2globalnew * v (icp/icp.hpp:130)
         const double d_box = st->d_box;
         const double dbox2s = d_box * d_box * (1.0 + 1e-12);
-        const uint32_t warm = (use_warm && st->warm) ? nn_pos[i] : ICPB_NONE;
+        const uint32_t warm = (use_warm && st->warm) ? __ldcs(nn_pos + i) : ICPB_NONE;
         uint32_t pos;
         double d2;
         int lvl;
@@ -338,8 +338,9 @@ __global__ void __launch_bounds__(SEARCH_THREADS, ICPB_SEARCH_MIN_BLOCKS)
             const double normal_angle = acos(fmin(1.0, dot));
             ok = !edge && (normal_angle < 3.14159265358979323846 / 8.0);
         }
-        nn_pos[i] = ok ? pos : ICPB_NONE;
-        nn_d[i] = ok ? d : icpb_inf();
+        // streamed (evict-first) like the source reads above: the L2 is for the model, which every query gathers from
+        __stcs(nn_pos + i, ok ? pos : ICPB_NONE);
+        __stcs(nn_d + i, ok ? d : icpb_inf());
         found = ok ? 1u : 0u;
         far = lvl > 0 ? 1u : 0u;
     }
@@ -749,7 +750,7 @@ __device__ __forceinline__ double shfl_xor_double(double v, int o)
     return __shfl_xor_sync(0xFFFFFFFFu, v, o);
 }
 
-__global__ void __launch_bounds__(MOM_THREADS, 3)
+__global__ void __launch_bounds__(MOM_THREADS, 2)
     moments_kernel(const GridView g, const double *__restrict__ sx, const double *__restrict__ sy,
                    const double *__restrict__ sz, uint32_t n, IcpState *st,
                    const uint32_t *__restrict__ nn_pos, const double *__restrict__ nn_d,
@@ -768,32 +769,51 @@ __global__ void __launch_bounds__(MOM_THREADS, 3)
     __shared__ double M[12]; // broadcast reads instead of 24 registers per thread
     if (threadIdx.x < 12) M[threadIdx.x] = st->M[threadIdx.x];
     __syncthreads();
-    if (any)
-        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-            const double d = nn_d[i];
-            if (!(d <= tau)) continue;
-            if (!pair_kept(d, perm[i], tau, p_cut)) continue;
-            double px, py, pz;
-            icpb_aff_apply(M, sx[i], sy[i], sz[i], px, py, pz); // p: the transformed source vertex
-            const MPoint m = g.pts[nn_pos[i]];                  // x: its model point
-            acc[0] += px;
-            acc[1] += py;
-            acc[2] += pz;
-            acc[3] += m.x;
-            acc[4] += m.y;
-            acc[5] += m.z;
-            acc[6] += px * m.x;
-            acc[7] += px * m.y;
-            acc[8] += px * m.z;
-            acc[9] += py * m.x;
-            acc[10] += py * m.y;
-            acc[11] += py * m.z;
-            acc[12] += pz * m.x;
-            acc[13] += pz * m.y;
-            acc[14] += pz * m.z;
-            acc[15] += d * d; // mu_d += d*d (icp/icp.cpp:60-61)
-            acc[16] += 1.0;
+    if (any) {
+        // four pairs per trip: their (coalesced) loads are all in flight before the first dependent gather of a
+        // model point, and few, long-lived blocks amortise the fixed cost of a block (state reads, reduction, ticket)
+        const uint32_t T = gridDim.x * blockDim.x;
+        for (uint32_t base = blockIdx.x * blockDim.x + threadIdx.x; base < n; base += 4u * T) {
+            double d[4], vx[4], vy[4], vz[4];
+            uint32_t pos[4];
+            bool in[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t j = base + (uint32_t)u * T;
+                in[u] = j < n && j >= base;
+                d[u] = in[u] ? nn_d[j] : icpb_inf();
+                vx[u] = in[u] ? sx[j] : 0.0;
+                vy[u] = in[u] ? sy[j] : 0.0;
+                vz[u] = in[u] ? sz[j] : 0.0;
+                pos[u] = in[u] ? nn_pos[j] : ICPB_NONE;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (!(d[u] <= tau)) continue; // also +inf (no pair) and the out-of-range slots
+                if (d[u] == tau && !pair_kept(d[u], perm[base + (uint32_t)u * T], tau, p_cut)) continue;
+                double px, py, pz;
+                icpb_aff_apply(M, vx[u], vy[u], vz[u], px, py, pz); // p: the transformed source vertex
+                const MPoint m = g.pts[pos[u]];                     // x: its model point
+                acc[0] += px;
+                acc[1] += py;
+                acc[2] += pz;
+                acc[3] += m.x;
+                acc[4] += m.y;
+                acc[5] += m.z;
+                acc[6] += px * m.x;
+                acc[7] += px * m.y;
+                acc[8] += px * m.z;
+                acc[9] += py * m.x;
+                acc[10] += py * m.y;
+                acc[11] += py * m.z;
+                acc[12] += pz * m.x;
+                acc[13] += pz * m.y;
+                acc[14] += pz * m.z;
+                acc[15] += d[u] * d[u]; // mu_d += d*d (icp/icp.cpp:60-61)
+                acc[16] += 1.0;
+            }
         }
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < ICPB_NSUMS; ++k) {
