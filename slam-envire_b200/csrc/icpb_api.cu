@@ -223,7 +223,7 @@ struct icpb_ctx {
     bool last_valid = false, last_early = false;
     // K7 / debug scratch
     DevBuf<unsigned long long> kd0, kd1, cand_key;
-    DevBuf<uint32_t> cand_idx;
+    DevBuf<uint32_t> cand_idx, xscratch;
     DevBuf<uint32_t> dbg_idx;
     DevBuf<uint8_t> dbg_kept;
     // timing
@@ -331,6 +331,8 @@ int icpb_create(icpb_ctx **out, int device_id)
     CK(cudaMalloc((void **)&ctx->d_counter, 8 * sizeof(unsigned long long)));
     CK(cudaMemset(ctx->d_counter, 0, 8 * sizeof(unsigned long long)));
     CK(cudaMalloc((void **)&ctx->d_gather, 64 * sizeof(unsigned long long)));
+    CK(ctx->xscratch.ensure((size_t)(1 + P2P_MAX_RANKS) * P2P_ROW_WORDS)); // candidate exchange of the multi-GPU trim
+    CK(cudaMemset(ctx->xscratch.p, 0, (size_t)(1 + P2P_MAX_RANKS) * P2P_ROW_WORDS * sizeof(uint32_t)));
     CK(cudaEventCreate(&ctx->ev_begin));
     CK(cudaEventCreate(&ctx->ev_end));
     CK(cudaEventCreate(&ctx->ev_up0));
@@ -389,6 +391,7 @@ void icpb_destroy(icpb_ctx *ctx)
     ctx->kd0.release();
     ctx->cand_key.release();
     ctx->cand_idx.release();
+    ctx->xscratch.release();
     ctx->kd1.release();
     ctx->dbg_idx.release();
     ctx->dbg_kept.release();
@@ -1012,7 +1015,7 @@ static int launch_trim(icpb_ctx *ctx, uint32_t n)
         }
         select_collect_kernel<<<blocks, SEL_THREADS, 0, s>>>(ctx->nn_d.p, ctx->src_perm.p, n, ctx->d_state, ctx->d_ghist,
                                                              ctx->cand_key.p, ctx->cand_idx.p,
-                                                             (unsigned int *)(ctx->d_counter + 2), ctx->p2p);
+                                                             (unsigned int *)(ctx->d_counter + 2), ctx->p2p, ctx->xscratch.p);
         CKL();
         ctx->launches += 3;
         return ICPB_OK;

@@ -296,7 +296,10 @@ __global__ void node_levelN_kernel(const uint32_t *__restrict__ below, int nx, i
 // ---------------------------------------------------------------------------
 // K2 + K3: transform the source vertex and find its exact nearest model point
 // ---------------------------------------------------------------------------
-constexpr int SEARCH_THREADS = 128;
+#ifndef ICPB_SEARCH_THREADS
+#define ICPB_SEARCH_THREADS 128
+#endif
+constexpr int SEARCH_THREADS = ICPB_SEARCH_THREADS;
 #ifndef ICPB_SEARCH_MIN_BLOCKS
 #define ICPB_SEARCH_MIN_BLOCKS 8
 #endif
@@ -381,6 +384,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS)
 // ---------------------------------------------------------------------------
 constexpr int P2P_MAX_RANKS = 8;
 constexpr int P2P_ROW_WORDS = 2112; // 2048 histogram bins + 64 spare words (found count, ...)
+constexpr int P2P_CAND_CAP = (P2P_ROW_WORDS - 1) / 2; // candidate keys (u64) one row carries next to their count
 constexpr size_t P2P_DATA_WORDS = 2ull * P2P_MAX_RANKS * P2P_ROW_WORDS;
 constexpr size_t P2P_BUFFER_WORDS = P2P_DATA_WORDS + 2 * P2P_MAX_RANKS + 64;
 struct P2PView {
@@ -644,12 +648,13 @@ __global__ void __launch_bounds__(1024)
 __global__ void __launch_bounds__(SEL_THREADS)
     select_collect_kernel(const double *__restrict__ nn_d, const uint32_t *__restrict__ perm, uint32_t n,
                           IcpState *st, uint32_t *__restrict__ ghist, unsigned long long *__restrict__ cand_key,
-                          uint32_t *__restrict__ cand_idx, unsigned int *__restrict__ cand_count, const P2PView p2p)
+                          uint32_t *__restrict__ cand_idx, unsigned int *__restrict__ cand_count, const P2PView p2p,
+                          uint32_t *xscratch /* (1 + P2P_MAX_RANKS) * P2P_ROW_WORDS words, zero between uses */)
 {
     if (st->done) return;
     if (st->sel_krem == 0) return; // nothing to select this iteration
     __shared__ uint32_t scan_smem[34];
-    __shared__ int is_last;
+    __shared__ int is_last, all_fit;
     const int hs = c_sel_d_shift[1]; // bits >= hs are fixed by the first two passes
     const unsigned long long want = st->sel_prefix >> hs;
     const int lane = threadIdx.x & 31;
@@ -683,6 +688,61 @@ __global__ void __launch_bounds__(SEL_THREADS)
     if (!is_last) return;
     __threadfence();
     const unsigned cnt = *((volatile unsigned int *)cand_count);
+    // Several ranks: instead of one all-reduce per remaining digit, the ranks exchange their (few) candidates ONCE and
+    // every rank finishes the selection on the union -- identical arithmetic everywhere, three exchanges per trim
+    // instead of six.  If some rank holds more candidates than a row carries, all ranks fall back to the digit loop.
+    const uint32_t *crow = nullptr;
+    if (p2p.world > 1) {
+        uint32_t *xb = xscratch;
+        const bool fits = cnt <= (unsigned)P2P_CAND_CAP;
+        if (threadIdx.x == 0) xb[0] = cnt;
+        if (fits)
+            for (unsigned j = threadIdx.x; j < cnt; j += blockDim.x) {
+                const unsigned long long k = __ldcg(cand_key + j);
+                xb[1 + 2 * j] = (uint32_t)k;
+                xb[2 + 2 * j] = (uint32_t)(k >> 32);
+            }
+        __threadfence();
+        __syncthreads();
+        crow = p2p_exchange(p2p, st, xb, fits ? 1 + 2 * (int)cnt : 1);
+        if (threadIdx.x == 0) {
+            int ok = 1;
+            for (int q = 0; q < p2p.world; ++q)
+                if (__ldcv(crow + (size_t)q * P2P_ROW_WORDS) > (uint32_t)P2P_CAND_CAP) ok = 0;
+            all_fit = ok;
+        }
+        __syncthreads();
+        if (!all_fit) crow = nullptr;
+    }
+    if (crow) {
+        uint32_t *tie_rows = xscratch + P2P_ROW_WORDS; // per-rank counts of the last digit (what select_pick splits the tie quota by)
+        for (int pass = 2; pass < SEL_D_PASSES; ++pass) {
+            const int bits = c_sel_d_bits[pass], shift = c_sel_d_shift[pass], hsp = shift + bits;
+            const unsigned bin_mask = (1u << bits) - 1u;
+            const unsigned long long prefix = st->sel_prefix;
+            const bool lastp = pass == SEL_D_PASSES - 1;
+            if (st->sel_krem == 0) break;
+            for (int q = 0; q < p2p.world; ++q) {
+                const uint32_t *r = crow + (size_t)q * P2P_ROW_WORDS;
+                const unsigned cq = __ldcv(r);
+                for (unsigned j = threadIdx.x; j < cq; j += blockDim.x) {
+                    const unsigned long long k = (unsigned long long)__ldcv(r + 1 + 2 * j) | ((unsigned long long)__ldcv(r + 2 + 2 * j) << 32);
+                    if ((k >> hsp) != (prefix >> hsp)) continue;
+                    const unsigned b = (unsigned)(k >> shift) & bin_mask;
+                    atomicAdd(&ghist[b], 1u);
+                    if (lastp) atomicAdd(&tie_rows[(size_t)q * P2P_ROW_WORDS + b], 1u);
+                }
+            }
+            __threadfence();
+            __syncthreads();
+            select_pick(st, ghist, pass, false, scan_smem, lastp ? tie_rows : nullptr, p2p.world, p2p.rank);
+            __threadfence();
+            __syncthreads();
+            if (lastp)
+                for (int q = 0; q < p2p.world; ++q)
+                    for (int b = threadIdx.x; b < (1 << bits); b += blockDim.x) tie_rows[(size_t)q * P2P_ROW_WORDS + b] = 0u;
+        }
+    } else
     for (int pass = 2; pass < SEL_D_PASSES; ++pass) {
         const int bits = c_sel_d_bits[pass], shift = c_sel_d_shift[pass], hsp = shift + bits;
         const unsigned bin_mask = (1u << bits) - 1u;
