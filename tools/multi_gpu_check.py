@@ -15,14 +15,15 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ok = True
 cases = [("cfg1", 0.2, 1.0, {}), ("cfg2", 0.05, 1.0, dict(max_iter=15)), ("cfg1", 0.1, 0.37, dict(max_iter=10, overlap=0.6)),
-         ("ties", 0, 1.0, {})]
+         ("ties", 24, 1.0, {}), ("ties", 72, 1.0, {})]
 mode = os.environ.get("ICPB_COMM", "p2p")
 icp = pkg.Icp(local)
 sharding.init_comm(icp, dist, torch.device("cuda", local), mode=mode)
 single = pkg.Icp(local)
 for name, scale, density, over in cases:
-    if name == "ties":  # lattice data: massive equidistant ties at the threshold, split across ranks
-        g = np.arange(0, 24, dtype=np.float64)
+    if name == "ties":  # lattice data: massive equidistant ties at the threshold, split across ranks; the larger lattice
+        # leaves more candidates per rank than one exchange row carries (the digit-by-digit fallback of the trim)
+        g = np.arange(0, scale, dtype=np.float64)
         m = np.stack(np.meshgrid(g, g, indexing="ij"), -1).reshape(-1, 2)
         m = np.concatenate([m, np.zeros((len(m), 1))], 1)
         s = m + [0.3, 0.2, 0.0]
