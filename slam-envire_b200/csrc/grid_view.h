@@ -351,33 +351,37 @@ ICPB_HD void icpb_walk(const GridView &g, int top, int cx, int cy, int cz, uint3
     }
 }
 
-// Exact NN of q.  dbox2s = d_box^2 widened by a few ulps (+inf when unbounded);
-// warm_pos = position in pts[] of a candidate to seed the bound (ICPB_NONE for none).
-// Returns the position in pts[] (ICPB_NONE if the model is empty or nothing lies
-// within the bound) and the exact squared distance; start_level = level the search started at.
-ICPB_HD void icpb_nn_search(const GridView &g, double qx, double qy, double qz, double dbox2s, uint32_t warm_pos,
-                            uint32_t &out_pos, double &out_d2, int &start_level)
+// ---- the search, in the pieces the kernels compose -----------------------------------------------------------------
+// What the bound of one query implies for the grid: the level whose cells cover the ball with <= 2 per axis and those
+// cells (`cn` holds the query or is the closest, `cf` is the other one, == cn when the ball stays inside one cell).
+struct NNPlan {
+    int l;      // start level; -1: nothing to search (empty model, or the ball misses the grid)
+    int cn[3], cf[3];
+};
+
+// state of a fresh query: cell-unit copy of the point, nothing found yet, the bound is d_box
+ICPB_HD void icpb_nn_init(const GridView &g, double qx, double qy, double qz, double dbox2s, NNState &s)
 {
-    NNState s;
     s.qx = qx, s.qy = qy, s.qz = qz;
     s.dbox2s = dbox2s;
     s.inv_h2 = g.inv_h * g.inv_h;
     s.bd2 = icpb_inf();
     s.bidx = ~0ull;
     s.bpos = ICPB_NONE;
-    start_level = 0;
-    out_pos = ICPB_NONE;
-    out_d2 = s.bd2;
-    if (g.n == 0) return;
     s.ux = (float)((qx - g.o[0]) * g.inv_h);
     s.uy = (float)((qy - g.o[1]) * g.inv_h);
     s.uz = (float)((qz - g.o[2]) * g.inv_h);
     s.slack = 1e-6f * (fmaxf(fmaxf(fabsf(s.ux), fabsf(s.uy)), fabsf(s.uz)) + 4096.0f);
-    s.boundf = s.candf = (float)icpb_inf();
-    const float u[3] = {s.ux, s.uy, s.uz};
-    if (warm_pos < g.n) icpb_nn_eval(g.pts[warm_pos], warm_pos, s);
-    if (!(s.boundf < (float)icpb_inf())) icpb_nn_refresh_bound(s); // no warm start: the bound is d_box
+    icpb_nn_refresh_bound(s);
+}
 
+// from the current bound to the cells to search
+ICPB_HD void icpb_nn_plan(const GridView &g, const NNState &s, NNPlan &pl)
+{
+    pl.l = -1;
+    for (int a = 0; a < 3; ++a) pl.cn[a] = pl.cf[a] = 0;
+    if (g.n == 0) return;
+    const float u[3] = {s.ux, s.uy, s.uz};
     // radius of the ball in cell units, rounded up: covers the fp32 copy's distance from the exact query coordinate
     const float ru = sqrtf(s.boundf) * 1.000001f + s.slack;
     // start level: smallest l with 2^l >= 2*(ru + slack), so the ball spans <= 2 cells per axis even after the fp32
@@ -388,53 +392,51 @@ ICPB_HD void icpb_nn_search(const GridView &g, double qx, double qy, double qz, 
     } else {
         l = g.L;
     }
-    start_level = l;
-    // the <= 2 cells per axis the ball touches at level l: `near` holds the query (or is the closest), `far` the other
-    const float sl = (float)(1u << l), inv_s = 1.0f / sl;
-    int cn[3], cf[3];
+    const float inv_s = 1.0f / (float)(1u << l);
     for (int a = 0; a < 3; ++a) {
         const float dm1 = (float)(g.dim[l][a] - 1);
         float flo = floorf((u[a] - ru) * inv_s), fhi = floorf((u[a] + ru) * inv_s);
         if (!(flo > 0.0f)) flo = 0.0f; // also -inf / NaN
         if (!(fhi < dm1)) fhi = dm1;
-        if (flo > fhi) { // the ball misses the grid on this axis
-            out_pos = s.bpos;
-            out_d2 = s.bd2;
-            return;
-        }
+        if (flo > fhi) return; // the ball misses the grid on this axis
         float fc = floorf(u[a] * inv_s);
         fc = fminf(fmaxf(fc, flo), fhi);
-        cn[a] = (int)fc;
-        cf[a] = (fc == flo) ? (int)fhi : (int)flo; // == cn[a] when the ball stays inside one cell
+        pl.cn[a] = (int)fc;
+        pl.cf[a] = (fc == flo) ? (int)fhi : (int)flo;
     }
-    const uint32_t nx0 = (uint32_t)g.dim[0][0], ny0 = (uint32_t)g.dim[0][1];
+    pl.l = l;
+}
 
-    if (l == 0) {
-        // at most 2x2x2 level-0 cells; x-adjacent cells are contiguous in pts[]: <= 4 runs, the query's column first
-        const int x0 = cn[0] < cf[0] ? cn[0] : cf[0], x1 = cn[0] < cf[0] ? cf[0] : cn[0];
-        const float gx = fminf(icpb_gap2f((float)x0, (float)(x0 + 1), s.ux, s.slack), icpb_gap2f((float)x1, (float)(x1 + 1), s.ux, s.slack));
-        uint32_t rs[4], re[4];
+// pl.l == 0: at most 2x2x2 level-0 cells; x-adjacent cells are contiguous in pts[]: <= 4 runs, the query's column first
+ICPB_HD void icpb_nn_fast(const GridView &g, NNState &s, const NNPlan &pl)
+{
+    const int *cn = pl.cn, *cf = pl.cf;
+    const uint32_t nx0 = (uint32_t)g.dim[0][0], ny0 = (uint32_t)g.dim[0][1];
+    const int x0 = cn[0] < cf[0] ? cn[0] : cf[0], x1 = cn[0] < cf[0] ? cf[0] : cn[0];
+    const float gx = fminf(icpb_gap2f((float)x0, (float)(x0 + 1), s.ux, s.slack), icpb_gap2f((float)x1, (float)(x1 + 1), s.ux, s.slack));
+    uint32_t rs[4], re[4];
 #ifdef __CUDACC__
 #pragma unroll
 #endif
-        for (int k = 0; k < 4; ++k) {
-            const int y = (k & 1) ? cf[1] : cn[1], z = (k & 2) ? cf[2] : cn[2];
-            rs[k] = re[k] = 0;
-            if (((k & 1) && cf[1] == cn[1]) || ((k & 2) && cf[2] == cn[2])) continue;
-            const float md = (gx + icpb_gap2f((float)y, (float)(y + 1), s.uy, s.slack) + icpb_gap2f((float)z, (float)(z + 1), s.uz, s.slack)) * 0.999999f;
-            ICPB_COUNT(pops);
-            if (md > s.boundf) continue;
-            const uint32_t c = ((uint32_t)z * ny0 + (uint32_t)y) * nx0;
-            rs[k] = g.cell_start[c + (uint32_t)x0];
-            re[k] = g.cell_start[c + (uint32_t)x1 + 1u];
-        }
-        icpb_scan_runs(g, rs[0], re[0], rs[1], re[1], rs[2], re[2], rs[3], re[3], s);
-        out_pos = s.bpos;
-        out_d2 = s.bd2;
-        return;
+    for (int k = 0; k < 4; ++k) {
+        const int y = (k & 1) ? cf[1] : cn[1], z = (k & 2) ? cf[2] : cn[2];
+        rs[k] = re[k] = 0;
+        if (((k & 1) && cf[1] == cn[1]) || ((k & 2) && cf[2] == cn[2])) continue;
+        const float md = (gx + icpb_gap2f((float)y, (float)(y + 1), s.uy, s.slack) + icpb_gap2f((float)z, (float)(z + 1), s.uz, s.slack)) * 0.999999f;
+        ICPB_COUNT(pops);
+        if (md > s.boundf) continue;
+        const uint32_t c = ((uint32_t)z * ny0 + (uint32_t)y) * nx0;
+        rs[k] = g.cell_start[c + (uint32_t)x0];
+        re[k] = g.cell_start[c + (uint32_t)x1 + 1u];
     }
+    icpb_scan_runs(g, rs[0], re[0], rs[1], re[1], rs[2], re[2], rs[3], re[3], s);
+}
 
-    // wider balls: walk the pyramid below the <= 2x2x2 root nodes of level l, nearest root first
+// pl.l >= 1: walk the pyramid below the <= 2x2x2 root nodes of level l, nearest root first
+ICPB_HD void icpb_nn_walk_roots(const GridView &g, NNState &s, const NNPlan &pl)
+{
+    const int l = pl.l;
+    const int *cn = pl.cn, *cf = pl.cf;
     for (int k = 0; k < 8; ++k) {
         const unsigned code = (ICPB_ORD >> (4 * k)) & 7u;
         if (((code & 1u) && cf[0] == cn[0]) || ((code & 2u) && cf[1] == cn[1]) || ((code & 4u) && cf[2] == cn[2])) continue;
@@ -448,6 +450,25 @@ ICPB_HD void icpb_nn_search(const GridView &g, double qx, double qy, double qz, 
         if (icpb_node_mindist2f(w, l, x, y, z, s.ux, s.uy, s.uz, s.slack) > s.boundf) continue;
         icpb_walk(g, l, x, y, z, w, s);
     }
+}
+
+// Exact NN of q by one thread on its own.  dbox2s = d_box^2 widened by a few ulps (+inf when unbounded);
+// warm_pos = position in pts[] of a candidate to seed the bound (ICPB_NONE for none).
+// Returns the position in pts[] (ICPB_NONE if the model is empty or nothing lies
+// within the bound) and the exact squared distance; start_level = level the search started at.
+ICPB_HD void icpb_nn_search(const GridView &g, double qx, double qy, double qz, double dbox2s, uint32_t warm_pos,
+                            uint32_t &out_pos, double &out_d2, int &start_level)
+{
+    NNState s;
+    NNPlan pl;
+    icpb_nn_init(g, qx, qy, qz, dbox2s, s);
+    if (warm_pos < g.n) icpb_nn_eval(g.pts[warm_pos], warm_pos, s);
+    icpb_nn_plan(g, s, pl);
+    if (pl.l == 0)
+        icpb_nn_fast(g, s, pl);
+    else if (pl.l > 0)
+        icpb_nn_walk_roots(g, s, pl);
+    start_level = pl.l > 0 ? pl.l : 0;
     out_pos = s.bpos;
     out_d2 = s.bd2;
 }
