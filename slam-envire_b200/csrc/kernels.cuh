@@ -654,7 +654,9 @@ __global__ void __launch_bounds__(SEL_THREADS)
     if (st->done) return;
     if (st->sel_krem == 0) return; // nothing to select this iteration
     __shared__ uint32_t scan_smem[34];
+    __shared__ uint32_t fhist[SEL_MAX_BINS]; // histogram of the last block's finish (zero on entry, select_pick re-zeroes it)
     __shared__ int is_last, all_fit;
+    for (int b = threadIdx.x; b < SEL_MAX_BINS; b += SEL_THREADS) fhist[b] = 0u;
     const int hs = c_sel_d_shift[1]; // bits >= hs are fixed by the first two passes
     const unsigned long long want = st->sel_prefix >> hs;
     const int lane = threadIdx.x & 31;
@@ -742,19 +744,18 @@ __global__ void __launch_bounds__(SEL_THREADS)
                 for (int q = 0; q < p2p.world; ++q)
                     for (int b = threadIdx.x; b < (1 << bits); b += blockDim.x) tie_rows[(size_t)q * P2P_ROW_WORDS + b] = 0u;
         }
-    } else
-    for (int pass = 2; pass < SEL_D_PASSES; ++pass) {
-        const int bits = c_sel_d_bits[pass], shift = c_sel_d_shift[pass], hsp = shift + bits;
-        const unsigned bin_mask = (1u << bits) - 1u;
-        const unsigned long long prefix = st->sel_prefix;
-        if (st->sel_krem == 0) break;
-        for (unsigned j = threadIdx.x; j < cnt; j += blockDim.x) {
-            const unsigned long long k = __ldcg(cand_key + j);
-            if ((k >> hsp) == (prefix >> hsp)) atomicAdd(&ghist[(unsigned)(k >> shift) & bin_mask], 1u);
-        }
-        __threadfence();
-        __syncthreads();
-        if (p2p.world > 1) {
+    } else if (p2p.world > 1) {
+        for (int pass = 2; pass < SEL_D_PASSES; ++pass) { // one all-reduce per remaining digit
+            const int bits = c_sel_d_bits[pass], shift = c_sel_d_shift[pass], hsp = shift + bits;
+            const unsigned bin_mask = (1u << bits) - 1u;
+            const unsigned long long prefix = st->sel_prefix;
+            if (st->sel_krem == 0) break;
+            for (unsigned j = threadIdx.x; j < cnt; j += blockDim.x) {
+                const unsigned long long k = __ldcg(cand_key + j);
+                if ((k >> hsp) == (prefix >> hsp)) atomicAdd(&ghist[(unsigned)(k >> shift) & bin_mask], 1u);
+            }
+            __threadfence();
+            __syncthreads();
             const int bins = 1 << bits;
             const uint32_t *rows = p2p_exchange(p2p, st, ghist, bins);
             for (int b = threadIdx.x; b < bins; b += blockDim.x) {
@@ -764,11 +765,24 @@ __global__ void __launch_bounds__(SEL_THREADS)
             }
             __syncthreads();
             select_pick(st, ghist, pass, false, scan_smem, rows, p2p.world, p2p.rank);
-        } else {
-            select_pick(st, ghist, pass, false, scan_smem);
+            __threadfence();
+            __syncthreads();
         }
-        __threadfence();
-        __syncthreads();
+    } else {
+        // one rank: the few candidates are histogrammed in shared memory -- no global atomics or fences in this tail
+        for (int pass = 2; pass < SEL_D_PASSES; ++pass) {
+            const int bits = c_sel_d_bits[pass], shift = c_sel_d_shift[pass], hsp = shift + bits;
+            const unsigned bin_mask = (1u << bits) - 1u;
+            const unsigned long long prefix = st->sel_prefix;
+            if (st->sel_krem == 0) break;
+            for (unsigned j = threadIdx.x; j < cnt; j += blockDim.x) {
+                const unsigned long long k = __ldcg(cand_key + j);
+                if ((k >> hsp) == (prefix >> hsp)) atomicAdd(&fhist[(unsigned)(k >> shift) & bin_mask], 1u);
+            }
+            __syncthreads();
+            select_pick(st, fhist, pass, false, scan_smem);
+            __syncthreads();
+        }
     }
     if (st->need_tie) { // which of the equidistant pairs survive: the lowest pair indices (rank-local quota)
         const unsigned long long tau_bits = (unsigned long long)__double_as_longlong(st->tau);
@@ -779,12 +793,10 @@ __global__ void __launch_bounds__(SEL_THREADS)
             for (unsigned j = threadIdx.x; j < cnt; j += blockDim.x) {
                 if (__ldcg(cand_key + j) != tau_bits) continue;
                 const uint32_t pi = perm[__ldcg(cand_idx + j)];
-                if (pass == 0 || hst >= 32 || (pi >> hst) == (prefix >> hst)) atomicAdd(&ghist[(pi >> shift) & bin_mask], 1u);
+                if (pass == 0 || hst >= 32 || (pi >> hst) == (prefix >> hst)) atomicAdd(&fhist[(pi >> shift) & bin_mask], 1u);
             }
-            __threadfence();
             __syncthreads();
-            select_pick(st, ghist, pass, true, scan_smem);
-            __threadfence();
+            select_pick(st, fhist, pass, true, scan_smem);
             __syncthreads();
         }
     }
