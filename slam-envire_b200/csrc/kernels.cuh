@@ -318,6 +318,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, ICPB_SEARCH_MIN_BLOCKS)
     unsigned found = 0, far = 0;
     if (i < n) {
         double qx, qy, qz;
+        // source read with evict-first hints: the L2 is for the model, which every query gathers from
         icpb_aff_apply(M, __ldcs(sx + i), __ldcs(sy + i), __ldcs(sz + i), qx, qy, qz); // C_local2globalnew * v (icp/icp.hpp:130)
         const double d_box = st->d_box;
         const double dbox2s = d_box * d_box * (1.0 + 1e-12);
@@ -341,9 +342,8 @@ __global__ void __launch_bounds__(SEARCH_THREADS, ICPB_SEARCH_MIN_BLOCKS)
             const double normal_angle = acos(fmin(1.0, dot));
             ok = !edge && (normal_angle < 3.14159265358979323846 / 8.0);
         }
-        // streamed (evict-first) like the source reads above: the L2 is for the model, which every query gathers from
-        __stcs(nn_pos + i, ok ? pos : ICPB_NONE);
-        __stcs(nn_d + i, ok ? d : icpb_inf());
+        nn_pos[i] = ok ? pos : ICPB_NONE;
+        nn_d[i] = ok ? d : icpb_inf();
         found = ok ? 1u : 0u;
         far = lvl > 0 ? 1u : 0u;
     }
