@@ -10,6 +10,8 @@
 //   ptsf[n]         the same points as float4 in cell units relative to the grid origin (candidate pre-filter)
 //   cell_start[c]   exclusive prefix of points per level-0 cell, ncell+1 entries
 //                   (so x-adjacent cells form one contiguous run of pts)
+//   cell_box[c]     tight bounding box of the points of level-0 cell c, six nibbles like bits 8-31 of a node word
+//                   (sixteenths of h); read by the pyramid walk before it scans a cell
 //   node[l][c]      l >= 1: one 32-bit word per level-l cell.  Bits 0-7: child occupancy, bit (dx|dy<<1|dz<<2)
 //                   set when that child cell of level l-1 holds at least one point.  Bits 8-31: the TIGHT
 //                   bounding box of the points below the node, six nibbles lo x,y,z / hi x,y,z in sixteenths
@@ -88,6 +90,7 @@ struct GridView {
     int dim[ICPB_MAX_LEVELS][3];
     int L; // top level: dim[L] == {1,1,1}
     const uint32_t *cell_start;
+    const uint32_t *cell_box; // level-0 tight boxes: six nibbles like a node word (bits 8-31), sixteenths of h
     const uint32_t *node[ICPB_MAX_LEVELS]; // see the layout comment
     const MPoint *pts;
     const FPoint *ptsf; // same order as pts
@@ -337,7 +340,9 @@ ICPB_HD void icpb_walk(const GridView &g, int top, int cx, int cy, int cz, uint3
         if (icpb_cell_mindist2f(lev - 1, x, y, z, s.ux, s.uy, s.uz, s.slack) > s.boundf) continue;
         if (lev == 1) {
             const uint32_t c = ((uint32_t)z * (uint32_t)g.dim[0][1] + (uint32_t)y) * (uint32_t)g.dim[0][0] + (uint32_t)x;
-            icpb_scan_run(g, g.cell_start[c], g.cell_start[c + 1], s);
+            const uint32_t cb = g.cell_box[c], cs = g.cell_start[c], ce = g.cell_start[c + 1];
+            if (icpb_node_mindist2f(cb, 0, x, y, z, s.ux, s.uy, s.uz, s.slack) > s.boundf) continue; // the cell's tight box
+            icpb_scan_run(g, cs, ce, s);
             continue;
         }
         const size_t ci = ((size_t)z * g.dim[lev - 1][1] + y) * g.dim[lev - 1][0] + x;

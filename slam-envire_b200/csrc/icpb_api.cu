@@ -178,7 +178,7 @@ struct icpb_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     // options
-    double opt_cell_size = 0.0, opt_target = 10.0, opt_max_cells = 64.0 * 1024 * 1024, opt_run_ahead = 2.0,
+    double opt_cell_size = 0.0, opt_target = 12.0, opt_max_cells = 64.0 * 1024 * 1024, opt_run_ahead = 2.0,
            opt_warm = 1.0, opt_profile = 0.0, opt_sort = 1.0, opt_margin = 0.0, opt_merge = 1.0, opt_graph = 1.0, opt_trim_bpsm = 2.0, opt_mom_bpsm = 2.0;
     // model
     DevBuf<double> model_raw, model_nrm;
@@ -194,7 +194,7 @@ struct icpb_ctx {
     DevBuf<NPoint> npts2;
     GridDims gdims;
     unsigned long long merges = 0;
-    DevBuf<uint32_t> cell_start;
+    DevBuf<uint32_t> cell_start, cell_box;
     DevBuf<uint32_t> masks;
     DevBuf<uint32_t> keys0, keys1, vals0, vals1, sort_scratch;
     DevBuf<double> bbox_part;
@@ -372,6 +372,7 @@ void icpb_destroy(icpb_ctx *ctx)
     ctx->newpref.release();
     ctx->npts2.release();
     ctx->cell_start.release();
+    ctx->cell_box.release();
     ctx->masks.release();
     ctx->keys0.release();
     ctx->keys1.release();
@@ -642,13 +643,15 @@ static int build_masks(icpb_ctx *ctx)
     }
     g.L = L;
     CK(ctx->masks.ensure(mask_total + 16));
+    CK(ctx->cell_box.ensure((size_t)g.dim[0][0] * g.dim[0][1] * g.dim[0][2] + 16));
+    g.cell_box = ctx->cell_box.p;
     for (int l = 1; l <= L; ++l) {
         uint32_t *ml = ctx->masks.p + mask_off[l];
         g.node[l] = ml;
         const size_t cells = (size_t)g.dim[l][0] * g.dim[l][1] * g.dim[l][2];
         if (l == 1)
             node_level1_kernel<<<grid_for(cells, 256), 256, 0, s>>>(ctx->cell_start.p, ctx->pts.p, ctx->gdims, g.dim[1][0],
-                                                                    g.dim[1][1], g.dim[1][2], ml);
+                                                                    g.dim[1][1], g.dim[1][2], ml, ctx->cell_box.p);
         else
             node_levelN_kernel<<<grid_for(cells, 256), 256, 0, s>>>(g.node[l - 1], g.dim[l - 1][0], g.dim[l - 1][1],
                                                                     g.dim[l - 1][2], g.dim[l][0], g.dim[l][1],

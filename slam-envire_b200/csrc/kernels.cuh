@@ -242,7 +242,7 @@ __global__ void add_prefix_kernel(uint32_t *__restrict__ cell_start, const uint3
 
 // level-1 node words (child occupancy + tight box of the points below, grid_view.h) from the level-0 prefix array
 __global__ void node_level1_kernel(const uint32_t *__restrict__ cell_start, const MPoint *__restrict__ pts, GridDims g,
-                                   int mx, int my, int mz, uint32_t *__restrict__ node)
+                                   int mx, int my, int mz, uint32_t *__restrict__ node, uint32_t *__restrict__ cell_box)
 {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)mx * my * mz) return;
@@ -257,6 +257,8 @@ __global__ void node_level1_kernel(const uint32_t *__restrict__ cell_start, cons
         const uint32_t s = cell_start[c], e = cell_start[c + 1];
         if (e == s) continue;
         m |= 1u << ch;
+        int clo[3] = {15, 15, 15}, chi[3] = {0, 0, 0}; // the child cell's own tight box (level 0)
+        const double cc[3] = {(double)x, (double)y, (double)z};
         for (uint32_t p = s; p < e; ++p) {
             const MPoint q = pts[p];
             const double u[3] = {(q.x - g.o[0]) * g.inv_h, (q.y - g.o[1]) * g.inv_h, (q.z - g.o[2]) * g.inv_h};
@@ -264,8 +266,12 @@ __global__ void node_level1_kernel(const uint32_t *__restrict__ cell_start, cons
                 const int nb = icpb_node_nibble(u[a], cl[a], 1);
                 lo[a] = min(lo[a], nb);
                 hi[a] = max(hi[a], nb);
+                const int cb = icpb_node_nibble(u[a], cc[a], 0);
+                clo[a] = min(clo[a], cb);
+                chi[a] = max(chi[a], cb);
             }
         }
+        cell_box[c] = icpb_node_word(0u, clo, chi);
     }
     node[t] = m ? icpb_node_word(m, lo, hi) : 0u;
 }

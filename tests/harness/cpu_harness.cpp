@@ -24,7 +24,7 @@ struct HostGrid {
     GridView g;
     std::vector<MPoint> pts;
     std::vector<FPoint> ptsf;
-    std::vector<uint32_t> cell_start;
+    std::vector<uint32_t> cell_start, cell_box;
     std::vector<std::vector<uint32_t>> masks;
     std::vector<uint32_t> pos_of_idx;
 };
@@ -74,6 +74,24 @@ void build(HostGrid &G, const double *model, size_t n, double h)
         G.cell_start[key[s] + 1]++;
     }
     for (size_t c = 0; c < ncell; ++c) G.cell_start[c + 1] += G.cell_start[c];
+    G.cell_box.assign(ncell, 0u);
+    for (int cz = 0; cz < g.dim[0][2]; ++cz)
+        for (int cy = 0; cy < g.dim[0][1]; ++cy)
+            for (int cx = 0; cx < g.dim[0][0]; ++cx) {
+                const size_t c = ((size_t)cz * g.dim[0][1] + cy) * g.dim[0][0] + cx;
+                if (G.cell_start[c + 1] == G.cell_start[c]) continue;
+                int lo[3] = {15, 15, 15}, hi[3] = {0, 0, 0};
+                const double cl[3] = {(double)cx, (double)cy, (double)cz};
+                for (uint32_t p = G.cell_start[c]; p < G.cell_start[c + 1]; ++p) {
+                    const double u[3] = {(G.pts[p].x - g.o[0]) * g.inv_h, (G.pts[p].y - g.o[1]) * g.inv_h, (G.pts[p].z - g.o[2]) * g.inv_h};
+                    for (int a = 0; a < 3; ++a) {
+                        const int q = icpb_node_nibble(u[a], cl[a], 0);
+                        lo[a] = std::min(lo[a], q);
+                        hi[a] = std::max(hi[a], q);
+                    }
+                }
+                G.cell_box[c] = icpb_node_word(0u, lo, hi);
+            }
     int L = 0;
     G.masks.assign(ICPB_MAX_LEVELS, {});
     while (g.dim[L][0] > 1 || g.dim[L][1] > 1 || g.dim[L][2] > 1) {
@@ -119,6 +137,7 @@ void build(HostGrid &G, const double *model, size_t n, double h)
     g.L = L;
     for (int l = 1; l <= L; ++l) g.node[l] = G.masks[l].data();
     g.cell_start = G.cell_start.data();
+    g.cell_box = G.cell_box.data();
     g.pts = G.pts.data();
     g.ptsf = G.ptsf.data();
     g.n = (uint32_t)n;
