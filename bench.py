@@ -31,7 +31,7 @@ N_SOURCE = 1_000_000
 # max_iter is a cap only: the reference's own stopping rule (mse_diff <= min_mse_diff) ends the align after ~90 iterations
 ALIGN = dict(max_iter=300, min_mse=1e-10, min_mse_diff=1e-9, overlap=0.8)
 # dram__bytes_read.sum + dram__bytes_write.sum of one search_kernel launch (ncu --set full, cold-cache replay:
-# profiles/r1b_search_it1.md / r1b_search_it45.md / r1b_search_it88.md: 80.0 / 81.2 / 81.3 MB)
+# profiles/r1b_search_it1.md / r1b_search_it45.md / r1b_search_it88.md: 81.1 / 82.2 / 81.0 MB)
 K3_DRAM_TRAFFIC_BYTES = 81.0e6
 METRIC = "icp_correspondences_per_sec"
 UNIT = "correspondences/s"

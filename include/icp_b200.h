@@ -65,7 +65,7 @@ const char *icpb_last_error(const icpb_ctx *);
 const char *icpb_version(void);
 
 /* ---- tunables (GPU-only knobs; ICPConfiguration stays untouched) ------ */
-/* keys: "cell_size" (m, 0 = auto), "target_pts_per_cell" (default 10), "max_cells",
+/* keys: "cell_size" (m, 0 = auto), "target_pts_per_cell" (default 12), "max_cells",
  *       "trim_blocks_per_sm" / "moments_blocks_per_sm" (grid sizes of K4 / K5, default 2 / 2),
  *       "poll_every" (iterations between host polls of the done flag),
  *       "warm_start" (0/1: seed the search with the previous iteration's pair),
