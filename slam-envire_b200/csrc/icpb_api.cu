@@ -168,7 +168,7 @@ const T *density_gather_t(const T *v, size_t n, int width, double density, std::
     }
     return tmp.data();
 }
-constexpr int MAX_DIM = 2048; // cells per axis (bounds the pyramid depth and the search stack)
+constexpr int MAX_DIM = 2048; // cells per axis (bounds the pyramid depth: the walk's trail holds 12 levels)
 constexpr int EVENT_ITERS = 512;
 constexpr int FLAG_RING = 4096;
 } // namespace
@@ -788,7 +788,7 @@ static int build_grid(icpb_ctx *ctx)
         CKL();
     }
 
-    // pyramid of occupancy masks
+    // pyramid of node words (occupancy + tight boxes) and the level-0 cell boxes
     GridView &g = ctx->gv;
     memset(&g, 0, sizeof(g));
     for (int a = 0; a < 3; ++a) {

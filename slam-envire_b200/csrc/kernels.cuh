@@ -1,7 +1,7 @@
 // kernels.cuh -- the sm_100a kernels of the trimmed-ICP hot path.
 //
 //   K0  transform_append_kernel   model vertices -> global frame (addModel, icp/icp.hpp:231-240)
-//   K1  keys / gather / cell counts / occupancy masks: uniform-grid index build
+//   K1  keys / gather / cell counts / node words (occupancy + tight boxes) / cell boxes: uniform-grid index build
 //   K2+K3 search_kernel           source transform fused with the exact NN search (findPairs, icp/icp.hpp:242-252)
 //   K4  select_kernel             radix-select of the n_po-th smallest distance (Pairs::trim, icp/icp.cpp:23-41)
 //   K5  moments_kernel            17 fp64 sums over the kept pairs (Pairs::getTransform, icp/icp.cpp:55-73)
