@@ -291,37 +291,45 @@ ICPB_HD void icpb_scan_run(const GridView &g, uint32_t p, uint32_t e, NNState &s
 // child visiting order as XOR codes relative to the child octant the query is in: 0,1,2,4,3,5,6,7
 #define ICPB_ORD 0x76534210u
 
-// Depth-first walk below node (cx,cy,cz) of level `top` >= 1 whose word is w (already known to be non-empty and
-// within the bound).  trail byte b holds the pending children of the current path's node at level b+1 in visiting
-// order (bit k <-> child near ^ ORD[k]).
-ICPB_HD void icpb_walk(const GridView &g, int top, int cx, int cy, int cz, uint32_t w, NNState &s)
+// the child octant of node (cx,cy,cz) at `lev` that holds the query (clamped to the node)
+ICPB_HD unsigned icpb_near_code(const NNState &s, int lev, int cx, int cy, int cz)
 {
-    unsigned long long tr0 = 0;
-    unsigned int tr1 = 0;
-    int lev = top;
-    bool enter = true; // the current node was just entered: w is its word
-    for (;;) {
-        const float hc = (float)(1u << (lev - 1));
-        const unsigned near = (s.ux >= (float)(2 * cx + 1) * hc ? 1u : 0u) | (s.uy >= (float)(2 * cy + 1) * hc ? 2u : 0u) |
-                              (s.uz >= (float)(2 * cz + 1) * hc ? 4u : 0u);
-        const int b = lev - 1;
-        unsigned pend;
-        if (enter) {
-            // occupancy bits permuted into visiting order
-            pend = 0;
+    const float hc = (float)(1u << (lev - 1));
+    return (s.ux >= (float)(2 * cx + 1) * hc ? 1u : 0u) | (s.uy >= (float)(2 * cy + 1) * hc ? 2u : 0u) |
+           (s.uz >= (float)(2 * cz + 1) * hc ? 4u : 0u);
+}
+// occupancy bits of node word w permuted into visiting order (bit k <-> child near ^ ORD[k])
+ICPB_HD unsigned icpb_pending(uint32_t w, unsigned near)
+{
+    unsigned pend = 0;
 #ifdef __CUDACC__
 #pragma unroll
 #endif
-            for (int k = 0; k < 8; ++k) pend |= ((w >> (near ^ ((ICPB_ORD >> (4 * k)) & 7u))) & 1u) << k;
-            ICPB_COUNT(expands);
-            enter = false;
-        } else {
-            pend = b < 8 ? (unsigned)(tr0 >> (8 * b)) & 255u : (tr1 >> (8 * (b - 8))) & 255u;
-        }
+    for (int k = 0; k < 8; ++k) pend |= ((w >> (near ^ ((ICPB_ORD >> (4 * k)) & 7u))) & 1u) << k;
+    return pend;
+}
+
+// Depth-first walk below node (cx,cy,cz) of level `top` >= 1 whose word is w (already known to be non-empty and
+// within the bound).  trail byte b holds the pending children of the path's node at level b+1 in visiting order
+// (bit k <-> child near ^ ORD[k]).
+ICPB_HD void icpb_walk(const GridView &g, int top, int cx, int cy, int cz, uint32_t w, NNState &s)
+{
+    // The current node's pending children (visiting order) and its `near` octant live in registers; the trail is
+    // written when the walk descends and read when it comes back up, not at every child.
+    unsigned long long tr0 = 0;
+    unsigned int tr1 = 0;
+    int lev = top;
+    unsigned near = icpb_near_code(s, lev, cx, cy, cz);
+    unsigned pend = icpb_pending(w, near);
+    ICPB_COUNT(expands);
+    for (;;) {
         if (pend == 0) { // this node is finished: back to its parent
             if (lev == top) return;
             ++lev;
             cx >>= 1, cy >>= 1, cz >>= 1;
+            const int b = lev - 1;
+            pend = b < 8 ? (unsigned)(tr0 >> (8 * b)) & 255u : (tr1 >> (8 * (b - 8))) & 255u;
+            near = icpb_near_code(s, lev, cx, cy, cz);
             continue;
         }
 #ifdef __CUDA_ARCH__
@@ -330,10 +338,6 @@ ICPB_HD void icpb_walk(const GridView &g, int top, int cx, int cy, int cz, uint3
         const int k = __builtin_ctz(pend);
 #endif
         pend &= pend - 1u;
-        if (b < 8)
-            tr0 = (tr0 & ~(255ull << (8 * b))) | ((unsigned long long)pend << (8 * b));
-        else
-            tr1 = (tr1 & ~(255u << (8 * (b - 8)))) | (pend << (8 * (b - 8)));
         const unsigned ch = near ^ ((ICPB_ORD >> (4 * k)) & 7u);
         const int x = 2 * cx + (int)(ch & 1u), y = 2 * cy + (int)((ch >> 1) & 1u), z = 2 * cz + (int)((ch >> 2) & 1u);
         ICPB_COUNT(pops);
@@ -349,10 +353,16 @@ ICPB_HD void icpb_walk(const GridView &g, int top, int cx, int cy, int cz, uint3
         const uint32_t cw = g.node[lev - 1][ci];
         ICPB_COUNT(nodes);
         if (icpb_node_mindist2f(cw, lev - 1, x, y, z, s.ux, s.uy, s.uz, s.slack) > s.boundf) continue; // tight box
+        const int b = lev - 1; // descend: park this node's remaining children on the trail
+        if (b < 8)
+            tr0 = (tr0 & ~(255ull << (8 * b))) | ((unsigned long long)pend << (8 * b));
+        else
+            tr1 = (tr1 & ~(255u << (8 * (b - 8)))) | (pend << (8 * (b - 8)));
         --lev;
         cx = x, cy = y, cz = z;
-        w = cw;
-        enter = true;
+        near = icpb_near_code(s, lev, cx, cy, cz);
+        pend = icpb_pending(cw, near);
+        ICPB_COUNT(expands);
     }
 }
 
