@@ -134,17 +134,18 @@ ICPB_HD float icpb_gap2f(float lo, float hi, float u, float slack)
     const float gap = fmaxf(fmaxf(lo - u, u - hi) - slack, 0.0f);
     return gap * gap;
 }
-// lower bound of the squared distance to the cube of cell (cx,cy,cz) at `level`
+// lower bound of the squared distance to the cube of cell (cx,cy,cz) at `level`: per axis the gap is
+// |u - centre| - half edge (centre and half edge are exact in fp32), shrunk by slack like icpb_gap2f
 ICPB_HD float icpb_cell_mindist2f(int level, int cx, int cy, int cz, float ux, float uy, float uz, float slack)
 {
-    const float s = (float)(1u << level);
-    float lo, d2;
-    lo = (float)cx * s;
-    d2 = icpb_gap2f(lo, lo + s, ux, slack);
-    lo = (float)cy * s;
-    d2 += icpb_gap2f(lo, lo + s, uy, slack);
-    lo = (float)cz * s;
-    d2 += icpb_gap2f(lo, lo + s, uz, slack);
+    const float s = (float)(1u << level), half = 0.5f * s, hs = half + slack;
+    float gap, d2;
+    gap = fmaxf(fabsf(ux - ICPB_FMAF((float)cx, s, half)) - hs, 0.0f);
+    d2 = gap * gap;
+    gap = fmaxf(fabsf(uy - ICPB_FMAF((float)cy, s, half)) - hs, 0.0f);
+    d2 = ICPB_FMAF(gap, gap, d2);
+    gap = fmaxf(fabsf(uz - ICPB_FMAF((float)cz, s, half)) - hs, 0.0f);
+    d2 = ICPB_FMAF(gap, gap, d2);
     return d2 * 0.999999f;
 }
 // lower bound of the squared distance to the tight box stored in node word w of cell (cx,cy,cz) at `level` >= 1
