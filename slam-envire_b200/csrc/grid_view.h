@@ -7,7 +7,9 @@
 // Layout (all in HBM, built once per model by the K1 kernels):
 //   pts[n]          model points sorted by level-0 cell key (x fastest), 32 B
 //                   each: fp64 x,y,z in the global frame + insertion index
-//   ptsf[n]         the same points as float4 in cell units relative to the grid origin (candidate pre-filter)
+//   ptsf[n]         the same points as float4 in cell units relative to the grid origin (candidate pre-filter);
+//                   both arrays are followed by ICPB_PAD sentinel entries (far away, insertion index ~0) so that
+//                   the scanners can always read four candidates
 //   cell_start[c]   exclusive prefix of points per level-0 cell, ncell+1 entries
 //                   (so x-adjacent cells form one contiguous run of pts)
 //   cell_box[c]     tight bounding box of the points of level-0 cell c, six nibbles like bits 8-31 of a node word
@@ -48,6 +50,7 @@
 
 #define ICPB_MAX_LEVELS 16
 #define ICPB_NONE 0xFFFFFFFFu
+#define ICPB_PAD 3 // sentinel entries behind pts[n-1] / ptsf[n-1]: the scanners read four candidates at a time
 #ifndef ICPB_COUNT
 #define ICPB_COUNT(what) // instrumentation hook (tests/harness defines it to count traversal work)
 #endif
@@ -250,16 +253,13 @@ ICPB_HD void icpb_scan_runs(const GridView &g, uint32_t s0, uint32_t e0, uint32_
             base = p;
         }
         ICPB_COUNT(cells);
-        const uint32_t last = e - 1;
-        const uint32_t p1 = p + 1 < e ? p + 1 : last, p2 = p + 2 < e ? p + 2 : last, p3 = p + 3 < e ? p + 3 : last;
-        const FPoint f0 = g.ptsf[p], f1 = g.ptsf[p1], f2 = g.ptsf[p2], f3 = g.ptsf[p3];
+        // four candidates per trip, no tail handling: past the end of the run lie the next cell's points (real model
+        // points: testing them is harmless) and pts/ptsf end in ICPB_PAD far-away sentinels
+        const FPoint f0 = g.ptsf[p], f1 = g.ptsf[p + 1], f2 = g.ptsf[p + 2], f3 = g.ptsf[p + 3];
         const float d0 = icpb_dist2f(f0, s), d1 = icpb_dist2f(f1, s), d2 = icpb_dist2f(f2, s), d3 = icpb_dist2f(f3, s);
         const float cf = s.candf;
         const uint32_t sh = p - base;
-        marks |= (d0 <= cf ? 1u : 0u) << sh;
-        marks |= ((d1 <= cf && p1 != p) ? 2u : 0u) << sh;
-        marks |= ((d2 <= cf && p2 != p1) ? 4u : 0u) << sh;
-        marks |= ((d3 <= cf && p3 != p2) ? 8u : 0u) << sh;
+        marks |= ((d0 <= cf ? 1u : 0u) | (d1 <= cf ? 2u : 0u) | (d2 <= cf ? 4u : 0u) | (d3 <= cf ? 8u : 0u)) << sh;
         p += 4;
         // 32 marks are full -- or there is no bound yet (first candidates of a cold search): evaluate now
         if ((sh == 28u || !(cf < 3.0e38f)) && p < e) {
@@ -277,15 +277,13 @@ ICPB_HD void icpb_scan_run(const GridView &g, uint32_t p, uint32_t e, NNState &s
 {
     ICPB_COUNT(cells);
     for (; p < e; p += 4) {
-        const uint32_t last = e - 1;
-        const uint32_t p1 = p + 1 < e ? p + 1 : last, p2 = p + 2 < e ? p + 2 : last, p3 = p + 3 < e ? p + 3 : last;
-        const FPoint f0 = g.ptsf[p], f1 = g.ptsf[p1], f2 = g.ptsf[p2], f3 = g.ptsf[p3];
+        const FPoint f0 = g.ptsf[p], f1 = g.ptsf[p + 1], f2 = g.ptsf[p + 2], f3 = g.ptsf[p + 3]; // see icpb_scan_runs
         const float d0 = icpb_dist2f(f0, s), d1 = icpb_dist2f(f1, s), d2 = icpb_dist2f(f2, s), d3 = icpb_dist2f(f3, s);
         if (fminf(fminf(d0, d1), fminf(d2, d3)) > s.candf) continue; // none can be nearer than the best so far (nor tie)
         if (d0 <= s.candf) icpb_nn_eval(g.pts[p], p, s);
-        if (p1 != p && d1 <= s.candf) icpb_nn_eval(g.pts[p1], p1, s);
-        if (p2 != p1 && d2 <= s.candf) icpb_nn_eval(g.pts[p2], p2, s);
-        if (p3 != p2 && d3 <= s.candf) icpb_nn_eval(g.pts[p3], p3, s);
+        if (d1 <= s.candf) icpb_nn_eval(g.pts[p + 1], p + 1, s);
+        if (d2 <= s.candf) icpb_nn_eval(g.pts[p + 2], p + 2, s);
+        if (d3 <= s.candf) icpb_nn_eval(g.pts[p + 3], p + 3, s);
     }
 }
 

@@ -487,8 +487,8 @@ static int try_merge_append(icpb_ctx *ctx, size_t n_old, size_t k, bool *done)
     CK(ctx->vals1.ensure(k));
     CK(ctx->sort_scratch.ensure(rs_scratch_elems(k)));
     CK(ctx->newpref.ensure(ncell + 1 + scan_scratch_elems(ncell + 1)));
-    CK(ctx->pts2.ensure(n_old + k));
-    CK(ctx->ptsf2.ensure(n_old + k));
+    CK(ctx->pts2.ensure(n_old + k + ICPB_PAD));
+    CK(ctx->ptsf2.ensure(n_old + k + ICPB_PAD));
     CK(ctx->pkey2.ensure(n_old + k));
     if (ctx->model_ean) CK(ctx->npts2.ensure(n_old + k));
     cell_keys_kernel<<<grid_for(k, 256), 256, 0, s>>>(ctx->model_raw.p + 3 * n_old, (uint32_t)k, ctx->gdims, ctx->keys0.p,
@@ -517,6 +517,7 @@ static int try_merge_append(icpb_ctx *ctx, size_t n_old, size_t k, bool *done)
     add_prefix_kernel<<<grid_for(ncell + 1, 256), 256, 0, s>>>(ctx->cell_start.p, ctx->newpref.p, ncell + 1);
     CKL();
     ctx->launches += 5;
+    pad_tail_kernel<<<1, 32, 0, s>>>(ctx->pts2.p, ctx->ptsf2.p, (uint32_t)(n_old + k));
     std::swap(ctx->pts, ctx->pts2);
     std::swap(ctx->ptsf, ctx->ptsf2);
     std::swap(ctx->pkey, ctx->pkey2);
@@ -772,12 +773,13 @@ static int build_grid(icpb_ctx *ctx)
     const uint32_t *perm = sorted_in ? ctx->vals1.p : ctx->vals0.p;
     const size_t ncell = (size_t)dim0[0] * dim0[1] * dim0[2];
 
-    CK(ctx->pts.ensure(n));
-    CK(ctx->ptsf.ensure(n));
+    CK(ctx->pts.ensure(n + ICPB_PAD));
+    CK(ctx->ptsf.ensure(n + ICPB_PAD));
     CK(ctx->cell_start.ensure(ncell + 1 + scan_scratch_elems(ncell + 1)));
     CK(cudaMemsetAsync(ctx->cell_start.p, 0, (ncell + 1) * sizeof(uint32_t), s));
     gather_points_kernel<<<grid_for(n, 256), 256, 0, s>>>(ctx->model_raw.p, keys_sorted, perm, (uint32_t)n, gd,
                                                           ctx->pts.p, ctx->ptsf.p, ctx->cell_start.p);
+    pad_tail_kernel<<<1, 32, 0, s>>>(ctx->pts.p, ctx->ptsf.p, (uint32_t)n);
     CKL();
     exclusive_scan_u32(ctx->cell_start.p, ctx->cell_start.p, ncell + 1, ctx->cell_start.p + ncell + 1, s,
                        &ctx->launches);

@@ -143,6 +143,20 @@ __global__ void cell_keys_kernel(const double *__restrict__ pts, uint32_t n, Gri
     vals[i] = base + i; // insertion index
 }
 
+// ICPB_PAD sentinel entries behind the sorted points (grid_view.h): never the nearest neighbour of anything
+__global__ void pad_tail_kernel(MPoint *__restrict__ pts, FPoint *__restrict__ ptsf, uint32_t n)
+{
+    if (threadIdx.x >= ICPB_PAD) return;
+    MPoint m;
+    m.x = m.y = m.z = 1.0e300;
+    m.idx = ~0ull;
+    pts[n + threadIdx.x] = m;
+    FPoint f;
+    f.x = f.y = f.z = 3.0e18f; // squared distances overflow to +inf
+    f.w = 0.0f;
+    ptsf[n + threadIdx.x] = f;
+}
+
 // number of distinct keys in a sorted key array (occupied cells)
 __global__ void __launch_bounds__(256) count_unique_kernel(const uint32_t *__restrict__ keys, uint32_t n,
                                                            unsigned long long *__restrict__ counter)

@@ -56,8 +56,14 @@ void build(HostGrid &G, const double *model, size_t n, double h)
     }
     std::iota(perm.begin(), perm.end(), 0u);
     std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
-    G.pts.resize(n);
-    G.ptsf.resize(n);
+    G.pts.resize(n + ICPB_PAD);
+    G.ptsf.resize(n + ICPB_PAD);
+    for (size_t j = n; j < n + ICPB_PAD; ++j) { // the sentinels the device build appends (pad_tail_kernel)
+        G.pts[j].x = G.pts[j].y = G.pts[j].z = 1.0e300;
+        G.pts[j].idx = ~0ull;
+        G.ptsf[j].x = G.ptsf[j].y = G.ptsf[j].z = 3.0e18f;
+        G.ptsf[j].w = 0.0f;
+    }
     G.pos_of_idx.resize(n);
     G.cell_start.assign(ncell + 1, 0);
     for (size_t j = 0; j < n; ++j) {
