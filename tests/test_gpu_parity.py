@@ -23,6 +23,8 @@ def _pairs_match(i_gpu, d_gpu, i_ref, d_ref, d_box):
 @pytest.mark.parametrize("nm,nq,d_box,seed", [
     (20000, 20000, np.inf, 1), (20000, 20000, 0.3, 2), (5, 1000, np.inf, 3), (1, 10, 0.5, 4),
     (200000, 100000, np.inf, 5), (200000, 100000, 0.05, 6),
+    # array tails (the scanners read four candidates at a time and rely on the sentinels behind the last point)
+    (2, 100, np.inf, 7), (3, 100, 5.0, 8), (19999, 5000, np.inf, 9), (20001, 5000, 0.4, 10), (20002, 5000, 2.5, 11),
 ])
 def test_find_pairs_random(icp, oracle, nm, nq, d_box, seed):
     rng = np.random.default_rng(seed)

@@ -16,6 +16,9 @@ from conftest import ROOT, assert_transform_close
 @pytest.mark.parametrize("nm,nq,h,d_box,seed", [
     (5000, 2000, 0.7, np.inf, 1), (5000, 2000, 0.25, np.inf, 2), (5000, 2000, 4.0, np.inf, 3),
     (5000, 2000, 0.5, 0.4, 4), (5000, 2000, 0.5, 1.7, 5), (1, 50, 1.0, np.inf, 6), (9, 50, 1.0, 0.5, 7),
+    # array tails: the scanners read four candidates at a time and rely on the sentinels behind the last point
+    (2, 64, 1.0, np.inf, 8), (3, 64, 0.3, 0.9, 9), (4999, 1500, 0.6, np.inf, 10), (5001, 1500, 0.6, 0.8, 11),
+    (4998, 1500, 40.0, np.inf, 12),  # one cell holds everything
 ])
 def test_grid_search_exact(harness, oracle, nm, nq, h, d_box, seed):
     rng = np.random.default_rng(seed)
