@@ -1,5 +1,6 @@
 """cfg4 (env_slam6d-style) at reduced length: N scans x P points registered sequentially into a growing model through the
-C++ driver slam-envire_b200/tools/env_slam6d (TrimmedGPU).  usage: python tools/run_cfg4.py [n_scans] [pts_per_scan]"""
+C++ driver slam-envire_b200/tools/env_slam6d (TrimmedGPU).  usage: python tools/run_cfg4.py [n_scans] [pts_per_scan]
+[procedural]   (procedural: every scan samples the scene afresh, O(points) per scan -- for the full 1000 scans)"""
 import importlib, json, os, subprocess, sys, tempfile, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -7,6 +8,7 @@ import numpy as np
 synth = importlib.import_module("slam-envire_b200.synth")
 n_scans = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 pts = int(sys.argv[2]) if len(sys.argv) > 2 else 100000
+procedural = len(sys.argv) > 3 and sys.argv[3] == "procedural"
 PK = os.path.join(ROOT, "slam-envire_b200")
 exe = os.path.join(PK, "tools", "env_slam6d")
 subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I" + PK, "-I" + os.path.join(PK, "compat"),
@@ -14,7 +16,7 @@ subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I" + P
                        "-L" + PK, "-licp_b200", "-Wl,-rpath," + PK])
 d = tempfile.mkdtemp()
 t0 = time.time()
-seq = synth.scan_sequence(n_scans, pts, seed=5, extent=max(120.0, 1.5 * n_scans + 40.0), radius=15.0)
+seq = synth.scan_sequence(n_scans, pts, seed=5, extent=max(120.0, 1.5 * n_scans + 40.0), radius=15.0, procedural=procedural)
 for i, sc in enumerate(seq):
     synth.write_ply(d + "/scan%03d.ply" % i, sc["scan"])
     np.savetxt(d + "/scan%03d.pose" % i, sc["pose_init"])
