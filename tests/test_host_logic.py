@@ -49,6 +49,23 @@ def test_grid_search_ties_lowest_index(harness, oracle):
         assert np.array_equal(i0, i1) and np.array_equal(d0, d1)
 
 
+def test_grid_search_deep_pyramid(harness, oracle):
+    """An elongated cloud in small cells: 2000 cells along x, 11 pyramid levels -- the walk's trail uses its second
+    register (levels 9 and up), cold searches start at the top level."""
+    rng = np.random.default_rng(21)
+    m = np.stack([rng.uniform(0, 20, 3000), rng.uniform(0, 0.05, 3000), rng.uniform(0, 0.05, 3000)], 1)
+    q = np.concatenate([m[:400] + rng.normal(0, 0.3, (400, 3)), rng.uniform(-3, 23, (300, 3)) * [1, 0.1, 0.1]])
+    M = oracle.Model()
+    M.add(m)
+    for d_box in (np.inf, 2.5, 0.2):
+        i0, d0 = M.find_pairs(q, d_box=d_box, brute=True)
+        d0 = np.where(i0 == 0xFFFFFFFF, d_box, d0)
+        i1, d1, lv = harness.search(m, 0.01, q, d_box)
+        assert np.array_equal(i0, i1) and np.array_equal(d0, d1)
+        if d_box == np.inf:
+            assert lv.max() == 11
+
+
 def test_grid_search_surface_scene(harness, oracle, synth):
     m, s, T, prm = synth.config("cfg1", 0.2)
     M = oracle.Model()
