@@ -39,6 +39,26 @@ def test_find_pairs_random(icp, oracle, nm, nq, d_box, seed):
     assert _pairs_match(i_gpu, d_gpu, i_ref, d_ref, d_box) == 0  # random data: no ties at all
 
 
+def test_find_pairs_deep_pyramid(pkg, oracle):
+    """2000 cells along x, 11 pyramid levels: the walk's trail uses its second register, cold searches start at the top."""
+    rng = np.random.default_rng(21)
+    m = np.stack([rng.uniform(0, 20, 30000), rng.uniform(0, 0.05, 30000), rng.uniform(0, 0.05, 30000)], 1)
+    q = np.concatenate([m[:4000] + rng.normal(0, 0.3, (4000, 3)), rng.uniform(-3, 23, (3000, 3)) * [1, 0.1, 0.1]])
+    ctx = pkg.Icp(0)
+    try:
+        ctx.set_option("cell_size", 0.01)
+        ctx.add_to_model(m)
+        assert ctx.build().levels == 11
+        M = oracle.Model()
+        M.add(m)
+        for d_box in (np.inf, 2.5, 0.2):
+            i_ref, d_ref = M.find_pairs(q, d_box=d_box)
+            i_gpu, d_gpu = ctx.find_pairs(q, d_box=d_box)
+            assert _pairs_match(i_gpu, d_gpu, i_ref, d_ref, d_box) == 0
+    finally:
+        ctx.close()
+
+
 def test_find_pairs_scene_accumulated_model(icp, oracle, synth):
     """addToModel accumulates (icp/icp.hpp:231-240); model clouds carry their own C_local2global."""
     m = synth.scene(60000, 20.0, 7)
