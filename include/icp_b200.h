@@ -37,7 +37,7 @@ extern "C" {
 #define ICPB_NO_PAIR 0xFFFFFFFFu
 #define ICPB_NCCL_ID_BYTES 128
 #define ICPB_IPC_HANDLE_BYTES 64
-#define ICPB_TRACE_COLS 24
+#define ICPB_TRACE_COLS 28
 
 typedef struct icpb_ctx icpb_ctx;
 
@@ -69,6 +69,10 @@ const char *icpb_version(void);
  *       "trim_blocks_per_sm" / "moments_blocks_per_sm" (grid sizes of K4 / K5, default 2 / 2),
  *       "poll_every" (iterations between host polls of the done flag),
  *       "warm_start" (0/1: seed the search with the previous iteration's pair),
+ *       "skip" (0/1, default 1: a query whose previous nearest neighbour provably is still the exact one -- it lies
+ *       strictly inside the lower bound on all other points, reduced by the query's motion -- is not searched again),
+ *       "skip_kappa" / "skip_floor_cells" (how far beyond the needed radius a search looks so that its bound is
+ *       useful: kappa * motion + floor * cell edge; results never depend on these),
  *       "sort_source" (0/1), "graph" (0/1, default 1: the whole _align loop is ONE CUDA-graph launch whose WHILE
  *       node is driven by the device-side loop condition), "profile" (0/1, default 0: 1 enqueues the loop kernel by
  *       kernel on the stream with CUDA events around every phase -- icpb_last_timing / icpb_iteration_times --
@@ -133,7 +137,8 @@ int icpb_pairs_distance(icpb_ctx *, double *out_sorted, size_t capacity, size_t 
 int icpb_debug_pairs(icpb_ctx *, uint32_t *model_idx, double *dist, uint8_t *kept, size_t capacity, size_t *n_out);
 /* Per-iteration trace (the reference's commented-out trace, icp/icp.hpp:487-495):
  * rows of ICPB_TRACE_COLS doubles:
- * [0]=iter [1]=found [2]=kept [3]=tau [4]=d_box [5]=mse [6]=mse_diff [7]=far_queries [8..23]=C (col-major) */
+ * [0]=iter [1]=found [2]=kept [3]=tau [4]=d_box [5]=mse [6]=mse_diff [7]=far_queries [8..23]=C (col-major)
+ * [24]=queries answered by the skip test (no search) [25..27]=reserved */
 int icpb_trace(icpb_ctx *, double *rows, size_t capacity_rows, size_t *n_rows);
 /* device time (ms, CUDA events) of the last align: total, and summed per phase */
 typedef struct {

@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libicp_b200.so")
 NO_PAIR = 0xFFFFFFFF
-TRACE_COLS = 24
+TRACE_COLS = 28
 NCCL_ID_BYTES = 128
 IPC_HANDLE_BYTES = 64
 
@@ -252,7 +252,7 @@ class Icp:
         out = []
         for r in rows:
             out.append(dict(iter=int(r[0]), found=int(r[1]), kept=int(r[2]), tau=r[3], d_box=r[4], mse=r[5],
-                            mse_diff=r[6], far=int(r[7]), C=r[8:24].reshape(4, 4).T.copy()))
+                            mse_diff=r[6], far=int(r[7]), skipped=int(r[24]), C=r[8:24].reshape(4, 4).T.copy()))
         return out
 
     def timing(self):

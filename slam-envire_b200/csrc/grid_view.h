@@ -185,18 +185,29 @@ struct NNState {
     double dbox2s;      // d_box^2 widened by a few ulps (+inf when unbounded)
     double inv_h2;
     double bd2;         // best exact squared distance so far
+    double sd2;         // smallest exact squared distance of an evaluated point that is NOT the best (runner-up)
+    double rs2;         // the search covers at least this squared radius (0: only what the answer needs), see below
     unsigned long long bidx;
     uint32_t bpos;
     float ux, uy, uz;   // query in cell units (fp32)
     float slack;
-    float boundf;       // min(d_box^2, bd2) in cell units, rounded up
-    float candf;        // fp32 pre-filter radius^2 that follows from boundf
+    float boundf;       // PRUNING radius^2 in cell units, rounded up: max(min(d_box^2, bd2), rs2)
+    float candf;        // fp32 pre-filter radius^2 for candidates that can still WIN: from min(d_box^2, bd2)
+    float mf;           // smallest fp32 squared distance (cell units) of a scanned candidate that was not evaluated
 };
 
+// Search skipping (K3): besides the winner a search reports a lower bound `lb` on the distance from the query to
+// every model point OTHER than the winner.  Everything the search prunes lies outside the pruning radius, every
+// candidate it scans is either evaluated exactly (runner-up sd2) or has an fp32 distance above candf (tracked in
+// mf), hence  lb^2 = min(sd2, lower bound from mf, pruning radius^2).  When the query moves by delta the bound
+// drops to lb - delta; as long as the old winner stays strictly inside it, it provably is still the exact nearest
+// neighbour (no tie possible) and the next search is skipped (icpb_nn_skip).  rs2 widens the pruning radius beyond
+// what the answer needs so that the bound is useful; it never changes the answer.
 ICPB_HD void icpb_nn_refresh_bound(NNState &s)
 {
-    s.boundf = icpb_bound_cells((s.dbox2s < s.bd2) ? s.dbox2s : s.bd2, s.inv_h2);
-    s.candf = icpb_cand_radius2(s.boundf, s.slack);
+    const double need = (s.dbox2s < s.bd2) ? s.dbox2s : s.bd2;
+    s.candf = icpb_cand_radius2(icpb_bound_cells(need, s.inv_h2), s.slack);
+    s.boundf = icpb_bound_cells(need < s.rs2 ? s.rs2 : need, s.inv_h2);
 }
 
 ICPB_HD void icpb_nn_eval(const MPoint &m, uint32_t pos, NNState &s)
@@ -206,10 +217,13 @@ ICPB_HD void icpb_nn_eval(const MPoint &m, uint32_t pos, NNState &s)
     ICPB_COUNT(exact);
     if (d2 < s.bd2 || (d2 == s.bd2 && m.idx < s.bidx)) {
         const bool nearer = d2 < s.bd2;
+        if (s.bd2 < s.sd2) s.sd2 = s.bd2; // the old best becomes a runner-up
         s.bd2 = d2;
         s.bidx = m.idx;
         s.bpos = pos;
         if (nearer) icpb_nn_refresh_bound(s);
+    } else if (pos != s.bpos && d2 < s.sd2) {
+        s.sd2 = d2;
     }
 }
 
@@ -260,6 +274,9 @@ ICPB_HD void icpb_scan_runs(const GridView &g, uint32_t s0, uint32_t e0, uint32_
         const float cf = s.candf;
         const uint32_t sh = p - base;
         marks |= ((d0 <= cf ? 1u : 0u) | (d1 <= cf ? 2u : 0u) | (d2 <= cf ? 4u : 0u) | (d3 <= cf ? 8u : 0u)) << sh;
+        // candidates that are not marked are never evaluated: their fp32 distance bounds the runner-up
+        s.mf = fminf(s.mf, fminf(fminf(d0 <= cf ? 3.0e38f : d0, d1 <= cf ? 3.0e38f : d1),
+                                 fminf(d2 <= cf ? 3.0e38f : d2, d3 <= cf ? 3.0e38f : d3)));
         p += 4;
         // 32 marks are full -- or there is no bound yet (first candidates of a cold search): evaluate now
         if ((sh == 28u || !(cf < 3.0e38f)) && p < e) {
@@ -279,11 +296,15 @@ ICPB_HD void icpb_scan_run(const GridView &g, uint32_t p, uint32_t e, NNState &s
     for (; p < e; p += 4) {
         const FPoint f0 = g.ptsf[p], f1 = g.ptsf[p + 1], f2 = g.ptsf[p + 2], f3 = g.ptsf[p + 3]; // see icpb_scan_runs
         const float d0 = icpb_dist2f(f0, s), d1 = icpb_dist2f(f1, s), d2 = icpb_dist2f(f2, s), d3 = icpb_dist2f(f3, s);
-        if (fminf(fminf(d0, d1), fminf(d2, d3)) > s.candf) continue; // none can be nearer than the best so far (nor tie)
-        if (d0 <= s.candf) icpb_nn_eval(g.pts[p], p, s);
-        if (d1 <= s.candf) icpb_nn_eval(g.pts[p + 1], p + 1, s);
-        if (d2 <= s.candf) icpb_nn_eval(g.pts[p + 2], p + 2, s);
-        if (d3 <= s.candf) icpb_nn_eval(g.pts[p + 3], p + 3, s);
+        const float m4 = fminf(fminf(d0, d1), fminf(d2, d3));
+        if (m4 > s.candf) { // none can be nearer than the best so far (nor tie)
+            s.mf = fminf(s.mf, m4);
+            continue;
+        }
+        if (d0 <= s.candf) icpb_nn_eval(g.pts[p], p, s); else s.mf = fminf(s.mf, d0);
+        if (d1 <= s.candf) icpb_nn_eval(g.pts[p + 1], p + 1, s); else s.mf = fminf(s.mf, d1);
+        if (d2 <= s.candf) icpb_nn_eval(g.pts[p + 2], p + 2, s); else s.mf = fminf(s.mf, d2);
+        if (d3 <= s.candf) icpb_nn_eval(g.pts[p + 3], p + 3, s); else s.mf = fminf(s.mf, d3);
     }
 }
 
@@ -374,12 +395,15 @@ struct NNPlan {
 };
 
 // state of a fresh query: cell-unit copy of the point, nothing found yet, the bound is d_box
-ICPB_HD void icpb_nn_init(const GridView &g, double qx, double qy, double qz, double dbox2s, NNState &s)
+ICPB_HD void icpb_nn_init(const GridView &g, double qx, double qy, double qz, double dbox2s, NNState &s, double rs2 = 0.0)
 {
     s.qx = qx, s.qy = qy, s.qz = qz;
     s.dbox2s = dbox2s;
     s.inv_h2 = g.inv_h * g.inv_h;
     s.bd2 = icpb_inf();
+    s.sd2 = icpb_inf();
+    s.rs2 = rs2;
+    s.mf = 3.0e38f;
     s.bidx = ~0ull;
     s.bpos = ICPB_NONE;
     s.ux = (float)((qx - g.o[0]) * g.inv_h);
@@ -387,6 +411,20 @@ ICPB_HD void icpb_nn_init(const GridView &g, double qx, double qy, double qz, do
     s.uz = (float)((qz - g.o[2]) * g.inv_h);
     s.slack = 1e-6f * (fmaxf(fmaxf(fabsf(s.ux), fabsf(s.uy)), fabsf(s.uz)) + 4096.0f);
     icpb_nn_refresh_bound(s);
+}
+
+// start level: smallest l with 2^l >= 2*(ru + slack), so the ball spans <= 2 cells per axis even after the fp32
+// rounding of the range arithmetic in icpb_nn_plan (which the extra slack dominates)
+ICPB_HD int icpb_nn_start_level(const GridView &g, const NNState &s)
+{
+    const float ru = sqrtf(s.boundf) * 1.000001f + s.slack;
+    int l = 0;
+    if (ru < 1.0e30f) {
+        while (l < g.L && (float)(1u << l) < 2.0f * (ru + s.slack)) ++l;
+    } else {
+        l = g.L;
+    }
+    return l;
 }
 
 // from the current bound to the cells to search
@@ -398,14 +436,7 @@ ICPB_HD void icpb_nn_plan(const GridView &g, const NNState &s, NNPlan &pl)
     const float u[3] = {s.ux, s.uy, s.uz};
     // radius of the ball in cell units, rounded up: covers the fp32 copy's distance from the exact query coordinate
     const float ru = sqrtf(s.boundf) * 1.000001f + s.slack;
-    // start level: smallest l with 2^l >= 2*(ru + slack), so the ball spans <= 2 cells per axis even after the fp32
-    // rounding of the range arithmetic below (which the extra slack dominates)
-    int l = 0;
-    if (ru < 1.0e30f) {
-        while (l < g.L && (float)(1u << l) < 2.0f * (ru + s.slack)) ++l;
-    } else {
-        l = g.L;
-    }
+    const int l = icpb_nn_start_level(g, s);
     const float inv_s = 1.0f / (float)(1u << l);
     for (int a = 0; a < 3; ++a) {
         const float dm1 = (float)(g.dim[l][a] - 1);
@@ -466,23 +497,111 @@ ICPB_HD void icpb_nn_walk_roots(const GridView &g, NNState &s, const NNPlan &pl)
     }
 }
 
-// Exact NN of q by one thread on its own.  dbox2s = d_box^2 widened by a few ulps (+inf when unbounded);
-// warm_pos = position in pts[] of a candidate to seed the bound (ICPB_NONE for none).
-// Returns the position in pts[] (ICPB_NONE if the model is empty or nothing lies
-// within the bound) and the exact squared distance; start_level = level the search started at.
-ICPB_HD void icpb_nn_search(const GridView &g, double qx, double qy, double qz, double dbox2s, uint32_t warm_pos,
-                            uint32_t &out_pos, double &out_d2, int &start_level)
+// After a search: lower bound (global units, rounded down) on the distance from the query to every model point
+// other than the reported best (to every model point when nothing was found).  See the comment at NNState.
+ICPB_HD float icpb_nn_lower_bound(const GridView &g, const NNState &s)
 {
-    NNState s;
+    const double need = (s.dbox2s < s.bd2) ? s.dbox2s : s.bd2;
+    double lb2 = need < s.rs2 ? s.rs2 : need; // everything pruned lies outside the pruning radius
+    if (s.sd2 < lb2) lb2 = s.sd2;
+    float lb = !(lb2 < 1.0e37) ? 3.0e18f : sqrtf((float)lb2) * 0.999999f;
+    if (s.mf < 3.0e38f) { // scanned, never evaluated: true cell-unit distance >= sqrt(mf) - 2*slack (see icpb_cand_radius2)
+        const float lc = (sqrtf(s.mf) * 0.99999f - 2.0f * s.slack) * (float)g.h * 0.999999f;
+        lb = fminf(lb, lc);
+    }
+    return lb > 0.0f ? lb : 0.0f;
+}
+
+// The search proper for a prepared state (icpb_nn_init + optional warm start): fast path or pyramid walk.
+ICPB_HD int icpb_nn_run(const GridView &g, NNState &s)
+{
     NNPlan pl;
-    icpb_nn_init(g, qx, qy, qz, dbox2s, s);
-    if (warm_pos < g.n) icpb_nn_eval(g.pts[warm_pos], warm_pos, s);
     icpb_nn_plan(g, s, pl);
     if (pl.l == 0)
         icpb_nn_fast(g, s, pl);
     else if (pl.l > 0)
         icpb_nn_walk_roots(g, s, pl);
-    start_level = pl.l > 0 ? pl.l : 0;
+    return pl.l > 0 ? pl.l : 0;
+}
+
+// Exact NN of q by one thread on its own.  dbox2s = d_box^2 widened by a few ulps (+inf when unbounded);
+// warm_pos = position in pts[] of a candidate to seed the bound (ICPB_NONE for none); rs2 = squared radius the
+// search is made to cover at least (0: only what the answer needs) so that *out_lb is useful.
+// Returns the position in pts[] (ICPB_NONE if the model is empty or nothing lies
+// within the bound) and the exact squared distance; start_level = level the search started at.
+ICPB_HD void icpb_nn_search(const GridView &g, double qx, double qy, double qz, double dbox2s, uint32_t warm_pos,
+                            uint32_t &out_pos, double &out_d2, int &start_level, double rs2 = 0.0, float *out_lb = nullptr)
+{
+    NNState s;
+    icpb_nn_init(g, qx, qy, qz, dbox2s, s, rs2);
+    if (warm_pos < g.n) icpb_nn_eval(g.pts[warm_pos], warm_pos, s);
+    start_level = icpb_nn_run(g, s);
     out_pos = s.bpos;
     out_d2 = s.bd2;
+    if (out_lb) *out_lb = icpb_nn_lower_bound(g, s);
+}
+
+// ---- search skipping ------------------------------------------------------------------------------------------------
+struct NNTune {
+    float kappa;       // the covered radius is widened by kappa * (this iteration's motion of the query) ...
+    float floor_cells; // ... plus this many cell edges
+    int skip;          // 0: every query is searched every iteration
+};
+
+// Upper bound (fp32, rounded up) of |dM * v|: how far the query moved when its transform changed by
+// dM = M_new - M_old (3x4 row-major, already rounded to float).  The fp32 evaluation error is covered per axis.
+ICPB_HD float icpb_motion_bound(const float *dM, float vx, float vy, float vz)
+{
+    float n2 = 0.0f;
+#ifdef __CUDACC__
+#pragma unroll
+#endif
+    for (int r = 0; r < 3; ++r) {
+        const float a = dM[4 * r] * vx, b = dM[4 * r + 1] * vy, c = dM[4 * r + 2] * vz, t = dM[4 * r + 3];
+        const float v = fabsf((a + b) + (c + t)) + 1.0e-6f * ((fabsf(a) + fabsf(b)) + (fabsf(c) + fabsf(t)));
+        n2 = ICPB_FMAF(v, v, n2);
+    }
+    return sqrtf(n2) * 1.00001f + 1.0e-30f;
+}
+
+// Can the search of this query be skipped?  wpos/lb_prev: winner and bound of its last search (bound already reduced
+// by earlier motions), delta: upper bound of the motion since then.  Returns 1 and the answer (pos, d2; pos ==
+// ICPB_NONE / d2 == inf: no pair within d_box) when it can; always returns the reduced bound in lb_out and the exact
+// squared distance to the old winner in d2w (inf without one) for the warm start of the search that follows otherwise.
+ICPB_HD int icpb_nn_skip(const GridView &g, double qx, double qy, double qz, double d_box, uint32_t wpos, float lb_prev,
+                         float delta, double &d2w, float &lb_out)
+{
+    float lbn = (lb_prev - delta) * 0.999999f;
+    if (!(lbn > 0.0f)) lbn = 0.0f;
+    lb_out = lbn;
+    d2w = icpb_inf();
+    if (wpos < g.n) {
+        const MPoint m = g.pts[wpos];
+        const double dx = qx - m.x, dy = qy - m.y, dz = qz - m.z;
+        d2w = (dx * dx + dy * dy) + dz * dz;
+    }
+    const double lb2 = (double)lbn * (double)lbn; // exact product of two floats
+    if (d2w < lb2) return 1;                      // every other point is farther than the old winner: still the exact NN
+    if (lb2 > d_box * d_box * (1.0 + 1e-12) && d2w > d_box * d_box * (1.0 + 1e-12)) { // nothing can lie within d_box
+        d2w = icpb_inf();
+        return 2;
+    }
+    return 0;
+}
+
+// radius^2 a search that has to happen anyway is made to cover, so that its bound lets later iterations skip:
+// need2 = min(d_box^2, warm-start distance^2) is what the answer requires
+ICPB_HD double icpb_cover_radius2(const GridView &g, double need2, bool has_pair_candidate, float delta, const NNTune &t)
+{
+    if (!t.skip || !(need2 < 1.0e30)) return 0.0; // cold search: no bound to speak of
+    const float h = (float)g.h;
+    const float U = sqrtf((float)need2);
+    float R = U + t.kappa * delta + t.floor_cells * h;
+    const float half = 0.48f * h; // a ball of this radius stays inside a 2x2x2 cell block (the fast path), slack included
+    if (U <= 0.95f * half) {
+        if (R > half) R = half;
+    } else if (has_pair_candidate) {
+        return 0.0; // wide ball around a query that has a pair: its runner-up is close anyway, widening only costs
+    }
+    return (double)R * (double)R;
 }

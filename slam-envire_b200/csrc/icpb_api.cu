@@ -179,7 +179,7 @@ struct icpb_ctx {
     std::string err;
     // options
     double opt_cell_size = 0.0, opt_target = 12.0, opt_max_cells = 64.0 * 1024 * 1024, opt_run_ahead = 2.0,
-           opt_warm = 1.0, opt_profile = 0.0, opt_sort = 1.0, opt_margin = 0.0, opt_merge = 1.0, opt_graph = 1.0, opt_trim_bpsm = 2.0, opt_mom_bpsm = 2.0;
+           opt_warm = 1.0, opt_skip = 1.0, opt_skip_kappa = 4.0, opt_skip_floor = 0.05, opt_profile = 0.0, opt_sort = 1.0, opt_margin = 0.0, opt_merge = 1.0, opt_graph = 1.0, opt_trim_bpsm = 2.0, opt_mom_bpsm = 2.0;
     // model
     DevBuf<double> model_raw, model_nrm;
     DevBuf<uint8_t> model_edge;
@@ -210,6 +210,7 @@ struct icpb_ctx {
     bool have_source = false;
     DevBuf<uint32_t> nn_pos, src_perm;
     DevBuf<double> nn_d;
+    DevBuf<float> nn_lb; // per query: lower bound on the distance to every model point but its winner (search skipping)
     // iteration
     IcpState *d_state = nullptr;
     IcpState *h_state = nullptr; // pinned
@@ -387,6 +388,7 @@ void icpb_destroy(icpb_ctx *ctx)
     ctx->nn_pos.release();
     ctx->src_perm.release();
     ctx->nn_d.release();
+    ctx->nn_lb.release();
     ctx->partials.release();
     ctx->trace.release();
     ctx->kd0.release();
@@ -419,6 +421,9 @@ static double *opt_slot(icpb_ctx *ctx, const char *key)
     if (!strcmp(key, "max_cells")) return &ctx->opt_max_cells;
     if (!strcmp(key, "run_ahead") || !strcmp(key, "poll_every")) return &ctx->opt_run_ahead;
     if (!strcmp(key, "warm_start")) return &ctx->opt_warm;
+    if (!strcmp(key, "skip")) return &ctx->opt_skip;
+    if (!strcmp(key, "skip_kappa")) return &ctx->opt_skip_kappa;
+    if (!strcmp(key, "skip_floor_cells")) return &ctx->opt_skip_floor;
     if (!strcmp(key, "profile")) return &ctx->opt_profile;
     if (!strcmp(key, "sort_source")) return &ctx->opt_sort;
     if (!strcmp(key, "growth_margin")) return &ctx->opt_margin;
@@ -855,6 +860,7 @@ static int upload_points(icpb_ctx *ctx, const double *src, size_t m)
     CK(ctx->sz.ensure(std::max<size_t>(m, 1)));
     CK(ctx->nn_pos.ensure(std::max<size_t>(m, 1)));
     CK(ctx->nn_d.ensure(std::max<size_t>(m, 1)));
+    CK(ctx->nn_lb.ensure(std::max<size_t>(m, 1)));
     CK(ctx->src_perm.ensure(std::max<size_t>(m, 1)));
     if (m) {
         CK(cudaMemcpyAsync(ctx->stage.p, src, 3 * m * sizeof(double), cudaMemcpyHostToDevice, s));
@@ -1101,13 +1107,20 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
     int use_cond = 0;
     const int use_warm = ctx->opt_warm != 0.0 ? 1 : 0;
     // one loop body of Trimmed::_align: search, trim, moments + pose
+    NNTune tune;
+    tune.kappa = (float)std::max(0.0, ctx->opt_skip_kappa);
+    tune.floor_cells = (float)std::max(0.0, ctx->opt_skip_floor);
+    tune.skip = (use_warm && ctx->opt_skip != 0.0) ? 1 : 0;
+    const unsigned search_blocks = grid_for(std::max<uint32_t>(n, 1), SEARCH_TILE);
     auto enqueue_iteration = [&]() -> int {
         if (ean.on)
-            search_kernel<true><<<grid_for(std::max<uint32_t>(n, 1), SEARCH_THREADS), SEARCH_THREADS, 0, s>>>(
-                ctx->gv, ctx->sx.p, ctx->sy.p, ctx->sz.p, n, ctx->d_state, ctx->nn_pos.p, ctx->nn_d.p, use_warm, ean);
+            search_kernel<true><<<search_blocks, SEARCH_THREADS, 0, s>>>(ctx->gv, ctx->sx.p, ctx->sy.p, ctx->sz.p, n,
+                                                                         ctx->d_state, ctx->nn_pos.p, ctx->nn_d.p,
+                                                                         ctx->nn_lb.p, use_warm, tune, ean);
         else
-            search_kernel<false><<<grid_for(std::max<uint32_t>(n, 1), SEARCH_THREADS), SEARCH_THREADS, 0, s>>>(
-                ctx->gv, ctx->sx.p, ctx->sy.p, ctx->sz.p, n, ctx->d_state, ctx->nn_pos.p, ctx->nn_d.p, use_warm, ean);
+            search_kernel<false><<<search_blocks, SEARCH_THREADS, 0, s>>>(ctx->gv, ctx->sx.p, ctx->sy.p, ctx->sz.p, n,
+                                                                          ctx->d_state, ctx->nn_pos.p, ctx->nn_d.p,
+                                                                          ctx->nn_lb.p, use_warm, tune, ean);
         CKL();
         ++ctx->launches;
         return ICPB_OK;
@@ -1120,7 +1133,7 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
         CK(ctx->cand_idx.ensure(std::max<size_t>(n, 1)));
         std::vector<unsigned char> key;
         auto add_key = [&](const void *p, size_t bytes) { key.insert(key.end(), (const unsigned char *)p, (const unsigned char *)p + bytes); };
-        const void *ptrs[] = {ctx->sx.p, ctx->sy.p, ctx->sz.p, ctx->nn_pos.p, ctx->nn_d.p, ctx->src_perm.p, ctx->partials.p,
+        const void *ptrs[] = {ctx->sx.p, ctx->sy.p, ctx->sz.p, ctx->nn_pos.p, ctx->nn_d.p, ctx->nn_lb.p, ctx->src_perm.p, ctx->partials.p,
                               ctx->trace.p, ctx->cand_key.p, ctx->cand_idx.p, ctx->d_state, ctx->d_ghist};
         add_key(&n, sizeof(n));
         add_key(&ctx->gv, sizeof(ctx->gv));
@@ -1129,6 +1142,7 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
         add_key(&ctx->p2p, sizeof(ctx->p2p));
         add_key(&ctx->trace_cap, sizeof(ctx->trace_cap));
         add_key(&use_warm, sizeof(use_warm));
+        add_key(&tune, sizeof(tune));
         add_key(&mom_blocks, sizeof(mom_blocks));
         add_key(&ctx->opt_trim_bpsm, sizeof(double));
         void *init_args[11];

@@ -317,38 +317,66 @@ __global__ void node_levelN_kernel(const uint32_t *__restrict__ below, int nx, i
 // K2 + K3: transform the source vertex and find its exact nearest model point
 // ---------------------------------------------------------------------------
 #ifndef ICPB_SEARCH_THREADS
-#define ICPB_SEARCH_THREADS 128
+#define ICPB_SEARCH_THREADS 256
+#endif
+#ifndef ICPB_SEARCH_QPT
+#define ICPB_SEARCH_QPT 2
+#endif
+#ifndef ICPB_SEARCH_MIN_BLOCKS
+#define ICPB_SEARCH_MIN_BLOCKS 3
 #endif
 constexpr int SEARCH_THREADS = ICPB_SEARCH_THREADS;
-#ifndef ICPB_SEARCH_MIN_BLOCKS
-#define ICPB_SEARCH_MIN_BLOCKS 8
-#endif
+constexpr int SEARCH_QPT = ICPB_SEARCH_QPT;                // queries per thread in the set-up phase
+constexpr int SEARCH_TILE = SEARCH_THREADS * SEARCH_QPT;   // queries per block
 
+// A query that has to be searched, parked in shared memory between the set-up phase and the search phase
+struct __align__(16) QRec {
+    double qx, qy, qz; // transformed source vertex (global frame)
+    double bd2;        // exact squared distance to the previous winner (+inf without one): the warm start
+    uint32_t wpos;     // previous winner (position in pts[]) or ICPB_NONE
+    uint32_t widx;     // its insertion index
+    float rs;          // radius the search is made to cover (0: only what the answer needs)
+    uint32_t pad;
+};
+
+// One block = one tile of SEARCH_TILE consecutive (Morton-ordered) source vertices, two phases:
+//   set-up  every thread transforms its vertices (C_local2globalnew * v, fp64), evaluates the previous winner exactly
+//           and applies the skip test (icpb_nn_skip): a query whose old winner provably is still the exact nearest
+//           neighbour -- or that provably has no pair within d_box -- is answered on the spot.  The others are
+//           parked in shared memory and appended to one of two lists: "fast" (ball inside a 2x2x2 cell block) or
+//           "walk" (pyramid).
+//   search  the lists are handed out to the threads densely, whole warps per list, so that a warp's lanes run the
+//           same kind of search and no lane idles for a neighbour that was skipped.
 template <bool EAN>
 __global__ void __launch_bounds__(SEARCH_THREADS, ICPB_SEARCH_MIN_BLOCKS)
     search_kernel(const GridView g, const double *__restrict__ sx, const double *__restrict__ sy,
                   const double *__restrict__ sz, uint32_t n, IcpState *st, uint32_t *__restrict__ nn_pos,
-                  double *__restrict__ nn_d, int use_warm, const EanView ean)
+                  double *__restrict__ nn_d, float *__restrict__ nn_lb, int use_warm, const NNTune tune, const EanView ean)
 {
     if (st->done) return;
+    __shared__ QRec rec[SEARCH_TILE];
+    __shared__ uint16_t list[SEARCH_TILE]; // fast slots from the front, walk slots from the back
+    __shared__ unsigned cnt[2];
     __shared__ double M[12]; // C_local2globalnew: broadcast reads instead of per-thread global loads
-    if (threadIdx.x < 12) M[threadIdx.x] = st->M[threadIdx.x];
+    __shared__ float dM[12]; // M - Mprev: how the source moved since the previous loop body
+    if (threadIdx.x < 12) {
+        M[threadIdx.x] = st->M[threadIdx.x];
+        dM[threadIdx.x] = (float)(st->M[threadIdx.x] - st->Mprev[threadIdx.x]);
+    }
+    if (threadIdx.x < 2) cnt[threadIdx.x] = 0u;
     __syncthreads();
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned found = 0, far = 0;
-    if (i < n) {
-        double qx, qy, qz;
-        // source read with evict-first hints: the L2 is for the model, which every query gathers from
-        icpb_aff_apply(M, __ldcs(sx + i), __ldcs(sy + i), __ldcs(sz + i), qx, qy, qz); // C_local2globalnew * v (icp/icp.hpp:130)
-        const double d_box = st->d_box;
-        const double dbox2s = d_box * d_box * (1.0 + 1e-12);
-        const uint32_t warm = (use_warm && st->warm) ? __ldcs(nn_pos + i) : ICPB_NONE;
-        uint32_t pos;
-        double d2;
-        int lvl;
-        icpb_nn_search(g, qx, qy, qz, dbox2s, warm, pos, d2, lvl);
+    const double d_box = st->d_box;
+    const double dbox2s = d_box * d_box * (1.0 + 1e-12);
+    const bool warm_on = use_warm && st->warm;
+    NNTune tn = tune;
+    if (!warm_on) tn.skip = 0;
+    const uint32_t tile0 = blockIdx.x * (uint32_t)SEARCH_TILE;
+    unsigned found = 0, nskip = 0;
+
+    // answer of one query: inclusive ball (find_nearest(val, max)), then the optional edge/normal pair filter
+    auto finish = [&](uint32_t i, uint32_t pos, double d2, float lb) {
         const double d = sqrt(d2);
-        bool ok = (pos != ICPB_NONE) && (d <= d_box); // inclusive ball (find_nearest(val, max))
+        bool ok = (pos != ICPB_NONE) && (d <= d_box);
         if (EAN && ok) {
             // EdgeAndNormalPairFilter (icp/icp.hpp:206-221) on the nearest neighbour: neither vertex on a scan edge,
             // normals (source normal mapped by C_local2globalnew.linear()) less than pi/8 apart
@@ -362,17 +390,85 @@ __global__ void __launch_bounds__(SEARCH_THREADS, ICPB_SEARCH_MIN_BLOCKS)
             const double normal_angle = acos(fmin(1.0, dot));
             ok = !edge && (normal_angle < 3.14159265358979323846 / 8.0);
         }
-        nn_pos[i] = ok ? pos : ICPB_NONE;
-        nn_d[i] = ok ? d : icpb_inf();
-        found = ok ? 1u : 0u;
-        far = lvl > 0 ? 1u : 0u;
+        nn_pos[i] = pos; // the nearest neighbour as such (warm start and skip test of the next iteration) ...
+        nn_d[i] = ok ? d : icpb_inf(); // ... a pair only when this is finite
+        nn_lb[i] = lb;
+        found += ok ? 1u : 0u;
+    };
+
+    // ---- set-up phase ----
+#pragma unroll
+    for (int k = 0; k < SEARCH_QPT; ++k) {
+        const uint32_t slot = (uint32_t)k * SEARCH_THREADS + threadIdx.x;
+        const uint32_t i = tile0 + slot;
+        if (i >= n) continue;
+        // source read with evict-first hints: the L2 is for the model, which every query gathers from
+        const double vx = __ldcs(sx + i), vy = __ldcs(sy + i), vz = __ldcs(sz + i);
+        double qx, qy, qz;
+        icpb_aff_apply(M, vx, vy, vz, qx, qy, qz); // C_local2globalnew * v (icp/icp.hpp:130)
+        const uint32_t wpos = warm_on ? __ldcs(nn_pos + i) : ICPB_NONE;
+        const float lbp = tn.skip ? __ldcs(nn_lb + i) : 0.0f;
+        const float delta = tn.skip ? icpb_motion_bound(dM, (float)vx, (float)vy, (float)vz) : 0.0f;
+        double d2w;
+        float lbn;
+        const int sk = icpb_nn_skip(g, qx, qy, qz, d_box, wpos, lbp, delta, d2w, lbn);
+        if (sk) {
+            finish(i, wpos, d2w, lbn);
+            ++nskip;
+            continue;
+        }
+        const double need2 = dbox2s < d2w ? dbox2s : d2w;
+        const double rs2 = icpb_cover_radius2(g, need2, d2w <= dbox2s, delta, tn);
+        QRec r;
+        r.qx = qx, r.qy = qy, r.qz = qz;
+        r.bd2 = d2w;
+        r.wpos = wpos < g.n ? wpos : ICPB_NONE;
+        r.widx = wpos < g.n ? (uint32_t)g.pts[wpos].idx : 0u;
+        r.rs = (float)sqrt(rs2);
+        r.pad = 0u;
+        rec[slot] = r;
+        // which list: the level the search will start at, computed exactly like icpb_nn_plan does
+        NNState s;
+        icpb_nn_init(g, qx, qy, qz, dbox2s, s, (double)r.rs * (double)r.rs);
+        if (r.wpos != ICPB_NONE) {
+            s.bd2 = d2w;
+            icpb_nn_refresh_bound(s);
+        }
+        const int fast = icpb_nn_start_level(g, s) == 0 ? 1 : 0;
+        const unsigned at = atomicAdd(&cnt[fast ? 0 : 1], 1u);
+        list[fast ? at : (unsigned)SEARCH_TILE - 1u - at] = (uint16_t)slot;
+    }
+    __syncthreads();
+
+    // ---- search phase: whole warps per list ----
+    const unsigned nf = cnt[0], nw = cnt[1], nf_pad = (nf + 31u) & ~31u;
+    for (unsigned j = threadIdx.x; j < nf_pad + nw; j += SEARCH_THREADS) {
+        unsigned slot;
+        if (j < nf_pad) {
+            if (j >= nf) continue;
+            slot = list[j];
+        } else {
+            slot = list[(unsigned)SEARCH_TILE - 1u - (j - nf_pad)];
+        }
+        const QRec r = rec[slot];
+        NNState s;
+        icpb_nn_init(g, r.qx, r.qy, r.qz, dbox2s, s, (double)r.rs * (double)r.rs);
+        if (r.wpos != ICPB_NONE) {
+            s.bd2 = r.bd2;
+            s.bidx = r.widx;
+            s.bpos = r.wpos;
+            icpb_nn_refresh_bound(s);
+        }
+        icpb_nn_run(g, s);
+        finish(tile0 + slot, s.bpos, s.bd2, icpb_nn_lower_bound(g, s));
     }
     found = __reduce_add_sync(0xFFFFFFFFu, found);
-    far = __reduce_add_sync(0xFFFFFFFFu, far);
+    nskip = __reduce_add_sync(0xFFFFFFFFu, nskip);
     if ((threadIdx.x & 31) == 0) { // no block barrier here: a finished warp frees its slot at once
         if (found) atomicAdd(&st->found, (unsigned long long)found);
-        if (far) atomicAdd(&st->far, (unsigned long long)far);
+        if (nskip) atomicAdd(&st->skipped, (unsigned long long)nskip);
     }
+    if (threadIdx.x == 0 && nw) atomicAdd(&st->far, (unsigned long long)nw);
 }
 
 // stand-alone form for icpb_find_pairs(): queries already in the global frame (AoS)
@@ -1015,7 +1111,8 @@ __global__ void debug_pairs_kernel(const GridView g, const uint32_t *__restrict_
     if (i >= n) return;
     const uint32_t pos = nn_pos[i];
     const uint32_t o = perm[i]; // back to the adapter's visiting order
-    idx_out[o] = pos == ICPB_NONE ? ICPB_NONE : (uint32_t)g.pts[pos].idx;
+    // nn_pos keeps the nearest neighbour as such; it is a pair only when its distance is finite (within d_box, filter passed)
+    idx_out[o] = (pos == ICPB_NONE || !(nn_d[i] < icpb_inf())) ? ICPB_NONE : (uint32_t)g.pts[pos].idx;
     d_out[o] = nn_d[i];
     kept_out[o] = (st->sel_k > 0 && pair_kept(nn_d[i], o, st->tau, st->p_cut)) ? 1 : 0;
 }

@@ -17,13 +17,14 @@
 #include "grid_view.h"
 
 #define ICPB_NSUMS 17 // sum p (3), sum x (3), sum p x^T (9, row-major), sum d^2, n
-#define ICPB_TRACE_COLS_DEV 24
+#define ICPB_TRACE_COLS_DEV 28
 
 struct IcpState {
     // transforms, 3x4 row-major [L | t]
     double C[12];    // C_global2globalnew
     double Cl2g[12]; // source C_local2global
     double M[12];    // C_local2globalnew = C * Cl2g   (setOffsetTransform)
+    double Mprev[12]; // M of the previous loop body (search skipping: how far every query moved since then)
     double d_box, mse, mse_diff;
     double min_mse, min_mse_diff, overlap;
     unsigned long long iter, max_iter, pairs, n_po;
@@ -31,6 +32,7 @@ struct IcpState {
     // per-iteration scratch
     unsigned long long found; // pairs found by K3 (all ranks after the collective)
     unsigned long long far;   // queries that started above level 0 (diagnostic)
+    unsigned long long skipped; // queries answered by the skip test, without a search (diagnostic)
     double sums[ICPB_NSUMS];
     // trim (K4)
     unsigned long long sel_prefix, sel_krem, sel_k;
@@ -163,7 +165,7 @@ ICPB_HD void icpb_state_init(IcpState &s, const double *Cl2g, unsigned long long
 {
     icpb_aff_identity(s.C);
     for (int i = 0; i < 12; ++i) s.Cl2g[i] = Cl2g[i];
-    for (int i = 0; i < 12; ++i) s.M[i] = Cl2g[i]; // C_local2globalnew = C_local2global (icp/icp.hpp:118)
+    for (int i = 0; i < 12; ++i) s.M[i] = s.Mprev[i] = Cl2g[i]; // C_local2globalnew = C_local2global (icp/icp.hpp:118)
     s.d_box = icpb_inf();
     s.mse = s.mse_diff = icpb_inf();
     s.min_mse = min_mse;
@@ -175,6 +177,7 @@ ICPB_HD void icpb_state_init(IcpState &s, const double *Cl2g, unsigned long long
     s.n_po = n_po;
     s.found = 0;
     s.far = 0;
+    s.skipped = 0;
     s.early = 0;
     s.executed = 0;
     s.warm = 0;
@@ -203,6 +206,8 @@ ICPB_HD void icpb_iteration_finish(IcpState &s, double *trace_row)
         trace_row[3] = tau;
         trace_row[4] = s.d_box;
         trace_row[7] = (double)s.far;
+        trace_row[24] = (double)s.skipped;
+        trace_row[25] = trace_row[26] = trace_row[27] = 0.0;
     }
     if (kept < 3) { // Pairs::MIN_PAIRS (icp/icp.hpp:475-476): return result as is
         s.early = 1;
@@ -210,6 +215,7 @@ ICPB_HD void icpb_iteration_finish(IcpState &s, double *trace_row)
     } else {
         double T[12], mse;
         icpb_transform_from_sums(s.sums, T, &mse);
+        for (int i = 0; i < 12; ++i) s.Mprev[i] = s.M[i];
         icpb_aff_mul(T, s.C, s.C);      // C = T * C                       (icp/icp.hpp:479)
         icpb_aff_mul(s.C, s.Cl2g, s.M); // measurement.setOffsetTransform   (icp/icp.hpp:480)
         s.mse = mse;
@@ -229,4 +235,5 @@ ICPB_HD void icpb_iteration_finish(IcpState &s, double *trace_row)
     s.executed += 1;
     s.found = 0;
     s.far = 0;
+    s.skipped = 0;
 }

@@ -186,7 +186,7 @@ void hs_transform_from_sums(const double *sums, double *T12, double *mse) { icpb
 // trace: rows of 24 doubles.  Returns the number of executed loop bodies.
 int hs_align(const double *model, size_t nm, double h, const double *src, size_t ns, size_t adapter_size,
              const double *T_l2g_cm, size_t max_iter, double min_mse, double min_mse_diff, double overlap,
-             int use_warm, double *result, double *trace, size_t trace_cap)
+             int use_warm, double *result, double *trace, size_t trace_cap, int skip, double kappa, double floor_cells)
 {
     HostGrid G;
     build(G, model, nm, h);
@@ -201,19 +201,44 @@ int hs_align(const double *model, size_t nm, double h, const double *src, size_t
     icpb_state_init(st, Cl2g, max_iter, min_mse, min_mse_diff, overlap, n_po);
     std::vector<uint32_t> nn_pos(ns, ICPB_NONE);
     std::vector<double> nn_d(ns, 0.0);
+    std::vector<float> nn_lb(ns, 0.0f);
+    NNTune tune;
+    tune.kappa = (float)kappa;
+    tune.floor_cells = (float)floor_cells;
     while (!st.done) {
+        // the set-up / search phases of search_kernel (kernels.cuh), one query after the other
+        const bool warm_on = use_warm && st.warm;
+        NNTune tn = tune;
+        tn.skip = (skip && warm_on) ? 1 : 0;
+        float dM[12];
+        for (int k = 0; k < 12; ++k) dM[k] = (float)(st.M[k] - st.Mprev[k]);
+        const double dbox2s = st.d_box * st.d_box * (1.0 + 1e-12);
         for (size_t i = 0; i < ns; ++i) {
             double qx, qy, qz;
             icpb_aff_apply(st.M, src[3 * i], src[3 * i + 1], src[3 * i + 2], qx, qy, qz);
+            const uint32_t wpos = warm_on ? nn_pos[i] : ICPB_NONE;
+            const float lbp = tn.skip ? nn_lb[i] : 0.0f;
+            const float delta = tn.skip ? icpb_motion_bound(dM, (float)src[3 * i], (float)src[3 * i + 1], (float)src[3 * i + 2]) : 0.0f;
+            double d2w;
+            float lb;
             uint32_t pos;
             double d2;
-            int lvl;
-            icpb_nn_search(G.g, qx, qy, qz, st.d_box * st.d_box * (1.0 + 1e-12),
-                           (use_warm && st.warm) ? nn_pos[i] : ICPB_NONE, pos, d2, lvl);
+            int lvl = 0;
+            const int sk = icpb_nn_skip(G.g, qx, qy, qz, st.d_box, wpos, lbp, delta, d2w, lb);
+            if (sk) {
+                pos = wpos;
+                d2 = d2w;
+                st.skipped += 1;
+            } else {
+                const double need2 = dbox2s < d2w ? dbox2s : d2w;
+                const float rs = (float)std::sqrt(icpb_cover_radius2(G.g, need2, d2w <= dbox2s, delta, tn));
+                icpb_nn_search(G.g, qx, qy, qz, dbox2s, wpos, pos, d2, lvl, (double)rs * (double)rs, &lb);
+            }
             const double d = std::sqrt(d2);
             const bool ok = pos != ICPB_NONE && d <= st.d_box;
-            nn_pos[i] = ok ? pos : ICPB_NONE;
+            nn_pos[i] = pos;
             nn_d[i] = ok ? d : INFINITY;
+            nn_lb[i] = lb;
             st.found += ok ? 1 : 0;
             st.far += lvl > 0 ? 1 : 0;
         }
@@ -249,7 +274,7 @@ int hs_align(const double *model, size_t nm, double h, const double *src, size_t
             st.sums[16] += 1.0;
         }
         const int row = st.executed;
-        icpb_iteration_finish(st, (size_t)row < trace_cap ? trace + (size_t)row * 24 : nullptr);
+        icpb_iteration_finish(st, (size_t)row < trace_cap ? trace + (size_t)row * ICPB_TRACE_COLS_DEV : nullptr);
     }
     for (int r = 0; r < 3; ++r) {
         for (int c = 0; c < 3; ++c) result[c * 4 + r] = st.C[r * 4 + c];
@@ -264,5 +289,54 @@ int hs_align(const double *model, size_t nm, double h, const double *src, size_t
     result[20] = st.d_box;
     result[21] = (double)st.early;
     return st.executed;
+}
+
+// The skip protocol on caller-supplied query positions: `steps` sets of nq queries (the same queries moved a little
+// from set to set).  Every set is answered with icpb_nn_skip / icpb_nn_search exactly like search_kernel does,
+// delta = the true displacement rounded up.  out_idx/out_d: answers of every set; out_skipped: 1 where no search ran.
+int hs_skip_sequence(const double *model, size_t nm, double h, const double *q, size_t nq, int steps, const double *d_box,
+                     double kappa, double floor_cells, uint32_t *out_idx, double *out_d, uint8_t *out_skipped)
+{
+    HostGrid G;
+    build(G, model, nm, h);
+    std::vector<uint32_t> nn_pos(nq, ICPB_NONE);
+    std::vector<float> nn_lb(nq, 0.0f);
+    NNTune tn;
+    tn.kappa = (float)kappa;
+    tn.floor_cells = (float)floor_cells;
+    for (int t = 0; t < steps; ++t) {
+        tn.skip = t > 0;
+        const double db = d_box[t], dbox2s = db * db * (1.0 + 1e-12);
+        for (size_t i = 0; i < nq; ++i) {
+            const double *c = q + ((size_t)t * nq + i) * 3;
+            float delta = 0.0f;
+            if (t > 0) {
+                const double *b = c - nq * 3;
+                const double m = std::sqrt((c[0] - b[0]) * (c[0] - b[0]) + (c[1] - b[1]) * (c[1] - b[1]) + (c[2] - b[2]) * (c[2] - b[2]));
+                delta = (float)m * 1.00001f + 1e-30f;
+            }
+            double d2w, d2;
+            float lb;
+            uint32_t pos;
+            int lvl;
+            const int sk = icpb_nn_skip(G.g, c[0], c[1], c[2], db, t > 0 ? nn_pos[i] : ICPB_NONE, nn_lb[i], delta, d2w, lb);
+            if (sk) {
+                pos = nn_pos[i];
+                d2 = d2w;
+            } else {
+                const double need2 = dbox2s < d2w ? dbox2s : d2w;
+                const float rs = (float)std::sqrt(icpb_cover_radius2(G.g, need2, d2w <= dbox2s, delta, tn));
+                icpb_nn_search(G.g, c[0], c[1], c[2], dbox2s, t > 0 ? nn_pos[i] : ICPB_NONE, pos, d2, lvl, (double)rs * (double)rs, &lb);
+            }
+            nn_pos[i] = pos;
+            nn_lb[i] = lb;
+            const double d = std::sqrt(d2);
+            const bool ok = pos != ICPB_NONE && d <= db;
+            out_idx[(size_t)t * nq + i] = ok ? (uint32_t)G.pts[pos].idx : ICPB_NONE;
+            out_d[(size_t)t * nq + i] = ok ? d : db;
+            out_skipped[(size_t)t * nq + i] = sk ? 1 : 0;
+        }
+    }
+    return 0;
 }
 }

@@ -88,14 +88,49 @@ def test_pose_step_matches_oracle(harness, oracle):
     assert np.allclose(T, T_ref, rtol=0, atol=1e-12) and abs(mse - mse_ref) <= 1e-14 * mse_ref
 
 
-@pytest.mark.parametrize("warm", [0, 1])
-def test_emulated_device_loop_matches_oracle(harness, oracle, synth, warm):
+@pytest.mark.parametrize("h,d_box,step,kappa,floor", [
+    (0.5, np.inf, 0.01, 4.0, 0.05), (0.5, 0.6, 0.02, 4.0, 0.05), (0.25, 0.3, 0.004, 0.0, 0.0), (1.5, 0.2, 0.03, 8.0, 0.4),
+    (0.5, 0.05, 0.001, 4.0, 0.05),
+])
+def test_search_skipping_is_exact(harness, oracle, synth, h, d_box, step, kappa, floor):
+    """Search skipping (icpb_nn_skip, grid_view.h): queries drift a little from step to step, as the source of an align
+    does; every step's answers -- searched or skipped -- must be the exact nearest neighbours the oracle finds, with
+    bit-identical distances.  The model is a surface scene plus exact duplicates and a lattice patch (ties)."""
+    rng = np.random.default_rng(17)
+    m = synth.scene(6000, 12.0, 5)
+    g = np.arange(0, 6, dtype=np.float64) * 0.25
+    lat = np.stack(np.meshgrid(g, g, [0.0], indexing="ij"), -1).reshape(-1, 3) + [1.0, 1.0, 2.0]
+    m = np.concatenate([m, m[:200], lat])
+    q0 = np.concatenate([m[rng.choice(len(m), 1500, replace=False)] + rng.normal(0, 0.02, (1500, 3)),
+                         lat[:20] + [0.125, 0.125, 0.0],                       # equidistant from four lattice points
+                         rng.uniform(-8, 8, (200, 3))])
+    steps = 12
+    drift = rng.normal(0, 1, 3)
+    drift *= step / np.linalg.norm(drift)
+    q = np.stack([q0 + t * drift + (rng.normal(0, step * 0.1, q0.shape) if t else 0) for t in range(steps)])
+    dbs = np.full(steps, d_box) * np.linspace(1.0, 0.7, steps)                 # d_box shrinks like 2*tau does
+    idx, d, sk = harness.skip_sequence(m, h, q, dbs, kappa, floor)
+    M = oracle.Model()
+    M.add(m)
+    for t in range(steps):
+        i0, d0 = M.find_pairs(q[t], d_box=dbs[t], brute=True)
+        d0 = np.where(i0 == 0xFFFFFFFF, dbs[t], d0)
+        assert np.array_equal(i0, idx[t]) and np.array_equal(d0, d[t]), t
+    assert not sk[0].any()
+    if floor > 0:
+        assert sk[1:].mean() > 0.3  # the rule does fire
+
+
+@pytest.mark.parametrize("warm,skip", [(0, 0), (1, 0), (1, 1)])
+def test_emulated_device_loop_matches_oracle(harness, oracle, synth, warm, skip):
     m, s, T, prm = synth.config("cfg1", 0.1)
     M = oracle.Model()
     M.add(m)
     run = oracle.Run()
     r = M.align(s, run=run, **prm)
-    e = harness.align(m, 0.5, s, warm=warm, **prm)
+    e = harness.align(m, 0.5, s, warm=warm, skip=skip, **prm)
+    if skip:
+        assert e["trace"][:, 24].sum() > 0 and e["trace"][0, 24] == 0
     assert e["iter"] == r.iter and e["pairs"] == r.pairs and not e["early"]
     assert_transform_close(e["C"], r.matrix(), 20.0)
     assert abs(e["mse"] - r.mse) <= 1e-5 * r.mse

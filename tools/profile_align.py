@@ -29,5 +29,5 @@ E = r.matrix() @ np.linalg.inv(T)
 print("vs truth: rot %.3g rad, trans %.3g m" % (np.arccos(min(1, (np.trace(E[:3, :3]) - 1) / 2)), np.linalg.norm(E[:3, 3])))
 its = icp.iteration_times()
 for row, tm in zip(icp.trace(), its):
-    print("it %3d found %8d kept %8d tau %.5f mse %.6g far %8d | search %.3f trim %.3f solve %.3f ms" % (
-        row["iter"], row["found"], row["kept"], row["tau"], row["mse"], row["far"], tm[0], tm[1], tm[2]))
+    print("it %3d found %8d kept %8d tau %.5f mse %.6g far %8d skipped %8d | search %.3f trim %.3f solve %.3f ms" % (
+        row["iter"], row["found"], row["kept"], row["tau"], row["mse"], row["far"], row["skipped"], tm[0], tm[1], tm[2]))
