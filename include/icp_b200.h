@@ -35,6 +35,7 @@ extern "C" {
 #define ICPB_ERR_NOT_ENOUGH_PAIRS 7 /* Pairs::getTransform would throw (icp/icp.cpp:45-46) */
 
 #define ICPB_NO_PAIR 0xFFFFFFFFu
+#define ICPB_DEFERRED 0xFFFFFFFEu /* icpb_debug_pairs: a pair exists but was not resolved (lazy search, see "lazy") */
 #define ICPB_NCCL_ID_BYTES 128
 #define ICPB_IPC_HANDLE_BYTES 64
 #define ICPB_TRACE_COLS 28
@@ -71,8 +72,14 @@ const char *icpb_version(void);
  *       "warm_start" (0/1: seed the search with the previous iteration's pair),
  *       "skip" (0/1, default 1: a query whose previous nearest neighbour provably is still the exact one -- it lies
  *       strictly inside the lower bound on all other points, reduced by the query's motion -- is not searched again),
- *       "skip_kappa" / "skip_floor_cells" (how far beyond the needed radius a search looks so that its bound is
- *       useful: kappa * motion + floor * cell edge; results never depend on these),
+ *       "lazy" (0/1, default 1: lazy search -- only the n_po nearest pairs survive Pairs::trim; a query whose nearest
+ *       neighbour provably is farther than the previous tau * (1 + "lazy_margin") while its previous winner still lies
+ *       within d_box is not searched: its pair exists and will not be kept, whichever point it is with.  If the new
+ *       tau exceeds that guard the loop body is run again exactly, so results never depend on this),
+ *       "skip_reach_cells" / "skip_floor_cells" (a search that needs a radius of at most `reach` cell edges covers
+ *       `floor` cell edges more, so that its bound is useful; results never depend on these),
+ *       "block_levels" (-1/0/1, default 1: searches whose ball spans at most 2 (0) / 3 (1) cells per axis scan that
+ *       cell block flat instead of walking the pyramid),
  *       "sort_source" (0/1), "graph" (0/1, default 1: the whole _align loop is ONE CUDA-graph launch whose WHILE
  *       node is driven by the device-side loop condition), "profile" (0/1, default 0: 1 enqueues the loop kernel by
  *       kernel on the stream with CUDA events around every phase -- icpb_last_timing / icpb_iteration_times --
@@ -133,12 +140,14 @@ int icpb_align(icpb_ctx *, const double *xyz_aos, size_t n_vertices, const doubl
 int icpb_pairs_distance(icpb_ctx *, double *out_sorted, size_t capacity, size_t *n_out);
 /* Parity hook: correspondences of the last executed iteration, one entry per
  * visited source vertex: model index in insertion order (ICPB_NO_PAIR if
- * none within d_box), Euclidean distance, kept flag after the trim. */
+ * none within d_box; ICPB_DEFERRED: a pair exists, beyond what the trim keeps, not resolved -- the distance then is a
+ * lower bound), Euclidean distance, kept flag after the trim. */
 int icpb_debug_pairs(icpb_ctx *, uint32_t *model_idx, double *dist, uint8_t *kept, size_t capacity, size_t *n_out);
 /* Per-iteration trace (the reference's commented-out trace, icp/icp.hpp:487-495):
  * rows of ICPB_TRACE_COLS doubles:
  * [0]=iter [1]=found [2]=kept [3]=tau [4]=d_box [5]=mse [6]=mse_diff [7]=far_queries [8..23]=C (col-major)
- * [24]=queries answered by the skip test (no search) [25..27]=reserved */
+ * [24]=queries answered by the skip test (no search) [25]=queries deferred by the lazy search
+ * [26]=loop bodies run again so far because a lazy trim did not verify [27]=reserved */
 int icpb_trace(icpb_ctx *, double *rows, size_t capacity_rows, size_t *n_rows);
 /* device time (ms, CUDA events) of the last align: total, and summed per phase */
 typedef struct {

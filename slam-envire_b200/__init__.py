@@ -13,8 +13,10 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libicp_b200.so")
+# ICPB_LIB: another build of the same library (kernel tuning variants, tools/build_variant.py); default = the in-tree one
+LIB_PATH = os.environ.get("ICPB_LIB") or os.path.join(_HERE, "libicp_b200.so")
 NO_PAIR = 0xFFFFFFFF
+DEFERRED = 0xFFFFFFFE
 TRACE_COLS = 28
 NCCL_ID_BYTES = 128
 IPC_HANDLE_BYTES = 64
@@ -252,7 +254,7 @@ class Icp:
         out = []
         for r in rows:
             out.append(dict(iter=int(r[0]), found=int(r[1]), kept=int(r[2]), tau=r[3], d_box=r[4], mse=r[5],
-                            mse_diff=r[6], far=int(r[7]), skipped=int(r[24]), C=r[8:24].reshape(4, 4).T.copy()))
+                            mse_diff=r[6], far=int(r[7]), skipped=int(r[24]), deferred=int(r[25]), redone=int(r[26]), C=r[8:24].reshape(4, 4).T.copy()))
         return out
 
     def timing(self):

@@ -98,6 +98,7 @@ struct GridView {
     const MPoint *pts;
     const FPoint *ptsf; // same order as pts
     uint32_t n;
+    int block_levels; // searches that start at a level <= this scan their cell block flat (icpb_nn_block); -1: never
 };
 
 ICPB_HD double icpb_inf() { return __builtin_huge_val(); }
@@ -250,6 +251,7 @@ ICPB_HD void icpb_flush_marks(const GridView &g, uint32_t base, uint32_t &marks,
         if (pos != s.bpos) icpb_nn_eval(g.pts[pos], pos, s);
     }
 }
+template <bool TRACK>
 ICPB_HD void icpb_scan_runs(const GridView &g, uint32_t s0, uint32_t e0, uint32_t s1, uint32_t e1, uint32_t s2,
                             uint32_t e2, uint32_t s3, uint32_t e3, NNState &s)
 {
@@ -275,8 +277,9 @@ ICPB_HD void icpb_scan_runs(const GridView &g, uint32_t s0, uint32_t e0, uint32_
         const uint32_t sh = p - base;
         marks |= ((d0 <= cf ? 1u : 0u) | (d1 <= cf ? 2u : 0u) | (d2 <= cf ? 4u : 0u) | (d3 <= cf ? 8u : 0u)) << sh;
         // candidates that are not marked are never evaluated: their fp32 distance bounds the runner-up
-        s.mf = fminf(s.mf, fminf(fminf(d0 <= cf ? 3.0e38f : d0, d1 <= cf ? 3.0e38f : d1),
-                                 fminf(d2 <= cf ? 3.0e38f : d2, d3 <= cf ? 3.0e38f : d3)));
+        if (TRACK)
+            s.mf = fminf(s.mf, fminf(fminf(d0 <= cf ? 3.0e38f : d0, d1 <= cf ? 3.0e38f : d1),
+                                     fminf(d2 <= cf ? 3.0e38f : d2, d3 <= cf ? 3.0e38f : d3)));
         p += 4;
         // 32 marks are full -- or there is no bound yet (first candidates of a cold search): evaluate now
         if ((sh == 28u || !(cf < 3.0e38f)) && p < e) {
@@ -296,15 +299,11 @@ ICPB_HD void icpb_scan_run(const GridView &g, uint32_t p, uint32_t e, NNState &s
     for (; p < e; p += 4) {
         const FPoint f0 = g.ptsf[p], f1 = g.ptsf[p + 1], f2 = g.ptsf[p + 2], f3 = g.ptsf[p + 3]; // see icpb_scan_runs
         const float d0 = icpb_dist2f(f0, s), d1 = icpb_dist2f(f1, s), d2 = icpb_dist2f(f2, s), d3 = icpb_dist2f(f3, s);
-        const float m4 = fminf(fminf(d0, d1), fminf(d2, d3));
-        if (m4 > s.candf) { // none can be nearer than the best so far (nor tie)
-            s.mf = fminf(s.mf, m4);
-            continue;
-        }
-        if (d0 <= s.candf) icpb_nn_eval(g.pts[p], p, s); else s.mf = fminf(s.mf, d0);
-        if (d1 <= s.candf) icpb_nn_eval(g.pts[p + 1], p + 1, s); else s.mf = fminf(s.mf, d1);
-        if (d2 <= s.candf) icpb_nn_eval(g.pts[p + 2], p + 2, s); else s.mf = fminf(s.mf, d2);
-        if (d3 <= s.candf) icpb_nn_eval(g.pts[p + 3], p + 3, s); else s.mf = fminf(s.mf, d3);
+        if (fminf(fminf(d0, d1), fminf(d2, d3)) > s.candf) continue; // none can be nearer than the best so far (nor tie)
+        if (d0 <= s.candf) icpb_nn_eval(g.pts[p], p, s);
+        if (d1 <= s.candf) icpb_nn_eval(g.pts[p + 1], p + 1, s);
+        if (d2 <= s.candf) icpb_nn_eval(g.pts[p + 2], p + 2, s);
+        if (d3 <= s.candf) icpb_nn_eval(g.pts[p + 3], p + 3, s);
     }
 }
 
@@ -453,6 +452,7 @@ ICPB_HD void icpb_nn_plan(const GridView &g, const NNState &s, NNPlan &pl)
 }
 
 // pl.l == 0: at most 2x2x2 level-0 cells; x-adjacent cells are contiguous in pts[]: <= 4 runs, the query's column first
+template <bool TRACK>
 ICPB_HD void icpb_nn_fast(const GridView &g, NNState &s, const NNPlan &pl)
 {
     const int *cn = pl.cn, *cf = pl.cf;
@@ -474,7 +474,7 @@ ICPB_HD void icpb_nn_fast(const GridView &g, NNState &s, const NNPlan &pl)
         rs[k] = g.cell_start[c + (uint32_t)x0];
         re[k] = g.cell_start[c + (uint32_t)x1 + 1u];
     }
-    icpb_scan_runs(g, rs[0], re[0], rs[1], re[1], rs[2], re[2], rs[3], re[3], s);
+    icpb_scan_runs<TRACK>(g, rs[0], re[0], rs[1], re[1], rs[2], re[2], rs[3], re[3], s);
 }
 
 // pl.l >= 1: walk the pyramid below the <= 2x2x2 root nodes of level l, nearest root first
@@ -505,22 +505,129 @@ ICPB_HD float icpb_nn_lower_bound(const GridView &g, const NNState &s)
     double lb2 = need < s.rs2 ? s.rs2 : need; // everything pruned lies outside the pruning radius
     if (s.sd2 < lb2) lb2 = s.sd2;
     float lb = !(lb2 < 1.0e37) ? 3.0e18f : sqrtf((float)lb2) * 0.999999f;
-    if (s.mf < 3.0e38f) { // scanned, never evaluated: true cell-unit distance >= sqrt(mf) - 2*slack (see icpb_cand_radius2)
-        const float lc = (sqrtf(s.mf) * 0.99999f - 2.0f * s.slack) * (float)g.h * 0.999999f;
-        lb = fminf(lb, lc);
-    }
+    // scanned, never evaluated: a candidate's true cell-unit distance is >= sqrt(its fp32 d^2) - 2*slack (see
+    // icpb_cand_radius2); its fp32 d^2 was tracked in mf, or -- without tracking, and in the pyramid walk -- is only
+    // known to exceed the pre-filter radius, which never is below what the final answer needs
+    const float f2 = s.rs2 > 0.0 ? s.mf : icpb_bound_cells(need, s.inv_h2);
+    if (f2 < 3.0e38f) lb = fminf(lb, (sqrtf(f2) * 0.99999f - 2.0f * s.slack) * (float)g.h * 0.999999f);
     return lb > 0.0f ? lb : 0.0f;
 }
 
-// The search proper for a prepared state (icpb_nn_init + optional warm start): fast path or pyramid walk.
-ICPB_HD int icpb_nn_run(const GridView &g, NNState &s)
+// ---- flat block scan (start level <= 1: the pruning ball spans at most 3 level-0 cells per axis) -------------------
+// The pyramid walk pays for its pruning with a divergent depth-first traversal.  When the ball is at most two cell
+// edges wide it touches at most 3x3x3 level-0 cells, and those are enumerated directly instead: per (y,z) row the
+// cells that survive the cube test, are not empty and whose TIGHT box (cell_box) the ball reaches; x-adjacent cells
+// are contiguous in pts[], so a row contributes one run.  Scenes are surfaces: a query some way off the surface
+// prunes most of the block on the tight boxes, like the walk does, but with independent loads and no traversal.
+// The runs are then scanned in one flattened loop with deferred exact evaluation (see icpb_scan_runs).
+#define ICPB_BLOCK_ROWS 9
+struct NNRun {
+    uint32_t s, e;
+};
+
+ICPB_HD bool icpb_nn_block_ranges(const GridView &g, const NNState &s, int lo[3], int hi[3])
 {
+    if (g.n == 0) return false;
+    const float ru = sqrtf(s.boundf) * 1.000001f + s.slack;
+    const float u[3] = {s.ux, s.uy, s.uz};
+    for (int a = 0; a < 3; ++a) {
+        const float dm1 = (float)(g.dim[0][a] - 1);
+        float flo = floorf(u[a] - ru), fhi = floorf(u[a] + ru);
+        if (!(flo > 0.0f)) flo = 0.0f;
+        if (!(fhi < dm1)) fhi = dm1;
+        if (flo > fhi) return false; // the ball misses the grid on this axis
+        lo[a] = (int)flo;
+        hi[a] = (int)fhi;
+    }
+    return true;
+}
+
+template <bool TRACK>
+ICPB_HD void icpb_nn_block(const GridView &g, NNState &s, NNRun *runs, int stride)
+{
+    int lo[3], hi[3];
+    if (!icpb_nn_block_ranges(g, s, lo, hi)) return;
+    const uint32_t nx0 = (uint32_t)g.dim[0][0], ny0 = (uint32_t)g.dim[0][1];
+    const float bf = s.boundf;
+    int nr = 0;
+    for (int z = lo[2]; z <= hi[2]; ++z) {
+        const float gz = icpb_gap2f((float)z, (float)(z + 1), s.uz, s.slack);
+        for (int y = lo[1]; y <= hi[1]; ++y) {
+            const float gyz = gz + icpb_gap2f((float)y, (float)(y + 1), s.uy, s.slack);
+            ICPB_COUNT(pops);
+            if (gyz * 0.999999f > bf) continue; // the whole row is out of reach
+            const uint32_t row = ((uint32_t)z * ny0 + (uint32_t)y) * nx0;
+            uint32_t rs = 0, re = 0;
+            for (int x = lo[0]; x <= hi[0]; ++x) {
+                if ((gyz + icpb_gap2f((float)x, (float)(x + 1), s.ux, s.slack)) * 0.999999f > bf) continue;
+                const uint32_t c = row + (uint32_t)x;
+                const uint32_t cs = g.cell_start[c], ce = g.cell_start[c + 1];
+                if (cs == ce) continue;
+                ICPB_COUNT(nodes);
+                if (icpb_node_mindist2f(g.cell_box[c], 0, x, y, z, s.ux, s.uy, s.uz, s.slack) > bf) continue; // tight box
+                if (re == 0) rs = cs;
+                re = ce;
+            }
+            if (re > rs && nr < ICPB_BLOCK_ROWS) {
+                runs[nr * stride].s = rs;
+                runs[nr * stride].e = re;
+                ++nr;
+            }
+        }
+    }
+    // one flattened loop over the runs: four candidates per trip, marks, deferred exact evaluation (icpb_scan_runs)
+    uint32_t p = 0, e = 0, base = 0, marks = 0;
+    int r = -1;
+    for (;;) {
+        if (p >= e) {
+            icpb_flush_marks(g, base, marks, s);
+            ++r;
+            if (r >= nr) return;
+            p = runs[r * stride].s;
+            e = runs[r * stride].e;
+            base = p;
+        }
+        ICPB_COUNT(cells);
+        const FPoint f0 = g.ptsf[p], f1 = g.ptsf[p + 1], f2 = g.ptsf[p + 2], f3 = g.ptsf[p + 3];
+        const float d0 = icpb_dist2f(f0, s), d1 = icpb_dist2f(f1, s), d2 = icpb_dist2f(f2, s), d3 = icpb_dist2f(f3, s);
+        const float cf = s.candf;
+        const uint32_t sh = p - base;
+        marks |= ((d0 <= cf ? 1u : 0u) | (d1 <= cf ? 2u : 0u) | (d2 <= cf ? 4u : 0u) | (d3 <= cf ? 8u : 0u)) << sh;
+        if (TRACK)
+            s.mf = fminf(s.mf, fminf(fminf(d0 <= cf ? 3.0e38f : d0, d1 <= cf ? 3.0e38f : d1),
+                                     fminf(d2 <= cf ? 3.0e38f : d2, d3 <= cf ? 3.0e38f : d3)));
+        p += 4;
+        if ((sh == 28u || !(cf < 3.0e38f)) && p < e) {
+            icpb_flush_marks(g, base, marks, s);
+            base = p;
+        }
+    }
+}
+
+// The search proper for a prepared state (icpb_nn_init + optional warm start): flat block scan, fast path or
+// pyramid walk.  runs: scratch for ICPB_BLOCK_ROWS entries, `stride` apart (shared memory on the device).
+ICPB_HD int icpb_nn_run(const GridView &g, NNState &s, NNRun *runs, int stride)
+{
+    if (g.n == 0) return 0;
+    const int l0 = icpb_nn_start_level(g, s);
+    const bool track = s.rs2 > 0.0; // the candidates' fp32 distances are tracked only when the bound can be useful
+    if (l0 <= g.block_levels) {
+        if (track)
+            icpb_nn_block<true>(g, s, runs, stride);
+        else
+            icpb_nn_block<false>(g, s, runs, stride);
+        return l0;
+    }
     NNPlan pl;
     icpb_nn_plan(g, s, pl);
-    if (pl.l == 0)
-        icpb_nn_fast(g, s, pl);
-    else if (pl.l > 0)
+    if (pl.l == 0) {
+        if (track)
+            icpb_nn_fast<true>(g, s, pl);
+        else
+            icpb_nn_fast<false>(g, s, pl);
+    } else if (pl.l > 0) {
         icpb_nn_walk_roots(g, s, pl);
+    }
     return pl.l > 0 ? pl.l : 0;
 }
 
@@ -533,9 +640,10 @@ ICPB_HD void icpb_nn_search(const GridView &g, double qx, double qy, double qz, 
                             uint32_t &out_pos, double &out_d2, int &start_level, double rs2 = 0.0, float *out_lb = nullptr)
 {
     NNState s;
+    NNRun runs[ICPB_BLOCK_ROWS];
     icpb_nn_init(g, qx, qy, qz, dbox2s, s, rs2);
     if (warm_pos < g.n) icpb_nn_eval(g.pts[warm_pos], warm_pos, s);
-    start_level = icpb_nn_run(g, s);
+    start_level = icpb_nn_run(g, s, runs, 1);
     out_pos = s.bpos;
     out_d2 = s.bd2;
     if (out_lb) *out_lb = icpb_nn_lower_bound(g, s);
@@ -543,8 +651,8 @@ ICPB_HD void icpb_nn_search(const GridView &g, double qx, double qy, double qz, 
 
 // ---- search skipping ------------------------------------------------------------------------------------------------
 struct NNTune {
-    float kappa;       // the covered radius is widened by kappa * (this iteration's motion of the query) ...
-    float floor_cells; // ... plus this many cell edges
+    float reach_cells; // a search whose needed radius is at most this many cell edges (the converged regime) ...
+    float floor_cells; // ... is made to cover this many cell edges more, so that its bound lets later iterations skip
     int skip;          // 0: every query is searched every iteration
 };
 
@@ -564,44 +672,67 @@ ICPB_HD float icpb_motion_bound(const float *dM, float vx, float vy, float vz)
     return sqrtf(n2) * 1.00001f + 1.0e-30f;
 }
 
-// Can the search of this query be skipped?  wpos/lb_prev: winner and bound of its last search (bound already reduced
-// by earlier motions), delta: upper bound of the motion since then.  Returns 1 and the answer (pos, d2; pos ==
-// ICPB_NONE / d2 == inf: no pair within d_box) when it can; always returns the reduced bound in lb_out and the exact
-// squared distance to the old winner in d2w (inf without one) for the warm start of the search that follows otherwise.
-ICPB_HD int icpb_nn_skip(const GridView &g, double qx, double qy, double qz, double d_box, uint32_t wpos, float lb_prev,
-                         float delta, double &d2w, float &lb_out)
+// Can the search of this query be skipped?  wm/has_w: the winner of its last search, lb_prev: the bound of that search
+// (already reduced by earlier motions), delta: upper bound of the motion since then.  Returns 1 (the old winner is
+// still the exact nearest neighbour, squared distance d2w) or 2 (provably no pair within d_box; d2w = inf) when it
+// can; always returns the reduced bound in lb_out and -- for the warm start of the search that follows otherwise --
+// the exact squared distance to the old winner in d2w (inf without one).
+ICPB_HD int icpb_nn_skip_pt(double qx, double qy, double qz, double d_box, bool has_w, const MPoint &wm, float lb_prev,
+                            float delta, double &d2w, float &lb_out)
 {
     float lbn = (lb_prev - delta) * 0.999999f;
     if (!(lbn > 0.0f)) lbn = 0.0f;
     lb_out = lbn;
     d2w = icpb_inf();
-    if (wpos < g.n) {
-        const MPoint m = g.pts[wpos];
-        const double dx = qx - m.x, dy = qy - m.y, dz = qz - m.z;
+    if (has_w) {
+        const double dx = qx - wm.x, dy = qy - wm.y, dz = qz - wm.z;
         d2w = (dx * dx + dy * dy) + dz * dz;
     }
     const double lb2 = (double)lbn * (double)lbn; // exact product of two floats
     if (d2w < lb2) return 1;                      // every other point is farther than the old winner: still the exact NN
-    if (lb2 > d_box * d_box * (1.0 + 1e-12) && d2w > d_box * d_box * (1.0 + 1e-12)) { // nothing can lie within d_box
+    const double dbox2s = d_box * d_box * (1.0 + 1e-12);
+    if (lb2 > dbox2s && d2w > dbox2s) { // nothing can lie within d_box
         d2w = icpb_inf();
         return 2;
     }
     return 0;
 }
-
-// radius^2 a search that has to happen anyway is made to cover, so that its bound lets later iterations skip:
-// need2 = min(d_box^2, warm-start distance^2) is what the answer requires
-ICPB_HD double icpb_cover_radius2(const GridView &g, double need2, bool has_pair_candidate, float delta, const NNTune &t)
+ICPB_HD int icpb_nn_skip(const GridView &g, double qx, double qy, double qz, double d_box, uint32_t wpos, float lb_prev,
+                         float delta, double &d2w, float &lb_out)
 {
-    if (!t.skip || !(need2 < 1.0e30)) return 0.0; // cold search: no bound to speak of
+    MPoint wm;
+    wm.x = wm.y = wm.z = 0.0;
+    wm.idx = 0;
+    if (wpos < g.n) wm = g.pts[wpos];
+    return icpb_nn_skip_pt(qx, qy, qz, d_box, wpos < g.n, wm, lb_prev, delta, d2w, lb_out);
+}
+
+// Lazy search: may the search of this query be DEFERRED?  Only the n_po nearest pairs survive the trim
+// (Pairs::trim, icp/icp.cpp:23-41); of the others nothing but their existence is ever used (the pair count).  A query
+// whose nearest neighbour provably is farther than tau_guard -- min(distance to its old winner, bound on all other
+// points) > tau_guard -- while its old winner lies within d_box has a pair that will not be kept, whichever point it
+// is with: no search, and the lower bound stands in for its distance (it only has to stay above the new tau, which
+// icpb_iteration_finish verifies).  These are the queries with the widest balls, i.e. the most expensive searches.
+ICPB_HD int icpb_nn_defer(double d2w, float lbn, double d_box, double tau_guard, double &standin)
+{
+    if (!(d2w < icpb_inf())) return 0;
+    const double dw = sqrt(d2w);
+    if (!(dw <= d_box)) return 0; // no sure pair: the nearest neighbour has to be found (or ruled out by the skip test)
+    standin = dw < (double)lbn ? dw : (double)lbn;
+    return standin > tau_guard ? 1 : 0;
+}
+
+// Radius a search that has to happen anyway is made to cover, so that its bound lets later iterations skip (0: only
+// what the answer needs).  need2 = min(d_box^2, warm-start distance^2) is what the answer requires.  Measured on cfg2:
+// while the source still is a point spacing or more off the model, runner-ups are about as near as winners and a wider
+// search only costs; the reach limits the widening to the converged regime, where it is nearly free.
+ICPB_HD float icpb_cover_radius(const GridView &g, double need2, float delta, const NNTune &t)
+{
+    if (!t.skip || !(need2 < 1.0e30)) return 0.0f; // cold search: no bound to speak of
     const float h = (float)g.h;
     const float U = sqrtf((float)need2);
-    float R = U + t.kappa * delta + t.floor_cells * h;
-    const float half = 0.48f * h; // a ball of this radius stays inside a 2x2x2 cell block (the fast path), slack included
-    if (U <= 0.95f * half) {
-        if (R > half) R = half;
-    } else if (has_pair_candidate) {
-        return 0.0; // wide ball around a query that has a pair: its runner-up is close anyway, widening only costs
-    }
-    return (double)R * (double)R;
+    if (U > t.reach_cells * h) return 0.0f;
+    if (delta > 0.25f * t.floor_cells * h) return 0.0f; // still moving fast: the extra reach would be used up in < 4 iterations
+    const float R = fminf(U + t.floor_cells * h, 0.48f * h); // stays inside a 2x2x2 cell block, slack included
+    return R > U ? R : 0.0f;
 }

@@ -179,7 +179,7 @@ struct icpb_ctx {
     std::string err;
     // options
     double opt_cell_size = 0.0, opt_target = 12.0, opt_max_cells = 64.0 * 1024 * 1024, opt_run_ahead = 2.0,
-           opt_warm = 1.0, opt_skip = 1.0, opt_skip_kappa = 4.0, opt_skip_floor = 0.05, opt_profile = 0.0, opt_sort = 1.0, opt_margin = 0.0, opt_merge = 1.0, opt_graph = 1.0, opt_trim_bpsm = 2.0, opt_mom_bpsm = 2.0;
+           opt_warm = 1.0, opt_skip = 1.0, opt_skip_reach = 0.25, opt_skip_floor = 0.05, opt_lazy = 1.0, opt_lazy_margin = 0.05, opt_block_levels = 1.0, opt_profile = 0.0, opt_sort = 1.0, opt_margin = 0.0, opt_merge = 1.0, opt_graph = 1.0, opt_trim_bpsm = 2.0, opt_mom_bpsm = 2.0;
     // model
     DevBuf<double> model_raw, model_nrm;
     DevBuf<uint8_t> model_edge;
@@ -422,8 +422,11 @@ static double *opt_slot(icpb_ctx *ctx, const char *key)
     if (!strcmp(key, "run_ahead") || !strcmp(key, "poll_every")) return &ctx->opt_run_ahead;
     if (!strcmp(key, "warm_start")) return &ctx->opt_warm;
     if (!strcmp(key, "skip")) return &ctx->opt_skip;
-    if (!strcmp(key, "skip_kappa")) return &ctx->opt_skip_kappa;
+    if (!strcmp(key, "skip_reach_cells")) return &ctx->opt_skip_reach;
     if (!strcmp(key, "skip_floor_cells")) return &ctx->opt_skip_floor;
+    if (!strcmp(key, "block_levels")) return &ctx->opt_block_levels;
+    if (!strcmp(key, "lazy")) return &ctx->opt_lazy;
+    if (!strcmp(key, "lazy_margin")) return &ctx->opt_lazy_margin;
     if (!strcmp(key, "profile")) return &ctx->opt_profile;
     if (!strcmp(key, "sort_source")) return &ctx->opt_sort;
     if (!strcmp(key, "growth_margin")) return &ctx->opt_margin;
@@ -651,6 +654,10 @@ static int build_masks(icpb_ctx *ctx)
     CK(ctx->masks.ensure(mask_total + 16));
     CK(ctx->cell_box.ensure((size_t)g.dim[0][0] * g.dim[0][1] * g.dim[0][2] + 16));
     g.cell_box = ctx->cell_box.p;
+    if (L == 0) { // one single cell: no level 1 to compute its tight box along with
+        cell_box_single_kernel<<<1, 256, 0, s>>>(ctx->pts.p, g.n ? g.n : (uint32_t)ctx->model_n, ctx->gdims, ctx->cell_box.p);
+        CKL();
+    }
     for (int l = 1; l <= L; ++l) {
         uint32_t *ml = ctx->masks.p + mask_off[l];
         g.node[l] = ml;
@@ -1074,6 +1081,7 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
     if (ctx->src_ean && ctx->model_n > 0 && !ctx->model_ean) return ICPB_ERR_ARG; // filter needs model normals
     cudaStream_t s = ctx->stream;
     const uint32_t n = (uint32_t)ctx->src_n;
+    ctx->gv.block_levels = (int)std::max(-1.0, std::min(ctx->opt_block_levels, 1.0));
     EanView ean;
     memset(&ean, 0, sizeof(ean));
     if (ctx->src_ean && ctx->model_n > 0) {
@@ -1108,10 +1116,12 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
     const int use_warm = ctx->opt_warm != 0.0 ? 1 : 0;
     // one loop body of Trimmed::_align: search, trim, moments + pose
     NNTune tune;
-    tune.kappa = (float)std::max(0.0, ctx->opt_skip_kappa);
+    tune.reach_cells = (float)std::max(0.0, ctx->opt_skip_reach);
     tune.floor_cells = (float)std::max(0.0, ctx->opt_skip_floor);
     tune.skip = (use_warm && ctx->opt_skip != 0.0) ? 1 : 0;
-    const unsigned search_blocks = grid_for(std::max<uint32_t>(n, 1), SEARCH_TILE);
+    // lazy search needs the skip state (winner + bound per query); the edge/normal filter decides pairs per winner
+    const double lazy_margin = (tune.skip && ctx->opt_lazy != 0.0 && !ean.on) ? std::max(-0.9, ctx->opt_lazy_margin) : -1.0;
+    const unsigned search_blocks = grid_for(std::max<uint32_t>(n, 1), SEARCH_THREADS);
     auto enqueue_iteration = [&]() -> int {
         if (ean.on)
             search_kernel<true><<<search_blocks, SEARCH_THREADS, 0, s>>>(ctx->gv, ctx->sx.p, ctx->sy.p, ctx->sz.p, n,
@@ -1122,7 +1132,7 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
                                                                           ctx->d_state, ctx->nn_pos.p, ctx->nn_d.p,
                                                                           ctx->nn_lb.p, use_warm, tune, ean);
         CKL();
-        ++ctx->launches;
+        ctx->launches += 1;
         return ICPB_OK;
     };
     size_t it = 0, checked = 0, timed_iters = 0;
@@ -1145,9 +1155,9 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
         add_key(&tune, sizeof(tune));
         add_key(&mom_blocks, sizeof(mom_blocks));
         add_key(&ctx->opt_trim_bpsm, sizeof(double));
-        void *init_args[11];
+        void *init_args[12];
         unsigned long long a_max_iter = max_iter, a_n_po = n_po, a_n = n, a_off = 0;
-        double a_mse = prm->min_mse, a_diff = prm->min_mse_diff, a_ov = prm->overlap;
+        double a_mse = prm->min_mse, a_diff = prm->min_mse_diff, a_ov = prm->overlap, a_lazy = lazy_margin;
         int one = 1;
         if (key != ctx->graph_key || !ctx->graph_exec) {
             if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
@@ -1159,7 +1169,7 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
             CK(cudaGraphConditionalHandleCreate(&ctx->graph_cond, ctx->graph, 1, cudaGraphCondAssignDefault));
             init_args[0] = &ctx->d_state; init_args[1] = &A; init_args[2] = &a_max_iter; init_args[3] = &a_mse;
             init_args[4] = &a_diff; init_args[5] = &a_ov; init_args[6] = &a_n_po; init_args[7] = &a_n; init_args[8] = &a_off;
-            init_args[9] = &ctx->graph_cond; init_args[10] = &one;
+            init_args[9] = &ctx->graph_cond; init_args[10] = &one; init_args[11] = &a_lazy;
             cudaKernelNodeParams kp;
             memset(&kp, 0, sizeof(kp));
             kp.func = (void *)init_state_kernel;
@@ -1196,7 +1206,7 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
         // this align's parameters go into the init node
         init_args[0] = &ctx->d_state; init_args[1] = &A; init_args[2] = &a_max_iter; init_args[3] = &a_mse;
         init_args[4] = &a_diff; init_args[5] = &a_ov; init_args[6] = &a_n_po; init_args[7] = &a_n; init_args[8] = &a_off;
-        init_args[9] = &ctx->graph_cond; init_args[10] = &one;
+        init_args[9] = &ctx->graph_cond; init_args[10] = &one; init_args[11] = &a_lazy;
         cudaKernelNodeParams kp;
         memset(&kp, 0, sizeof(kp));
         kp.func = (void *)init_state_kernel;
@@ -1209,13 +1219,15 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
     } else {
     CK(cudaEventRecord(ctx->ev_begin, s));
     init_state_kernel<<<1, 1, 0, s>>>(ctx->d_state, A, max_iter, prm->min_mse, prm->min_mse_diff, prm->overlap, n_po,
-                                      n, 0ull, 0, 0);
+                                      n, 0ull, 0, 0, lazy_margin);
     CKL();
     ++ctx->launches;
     for (int k = 0; k < FLAG_RING; ++k) ctx->h_flags[k] = -1;
 
     bool stop = false;
-    for (; it < max_iter && !stop; ++it) {
+    // a loop body whose lazy trim did not verify is run again (icpb_iteration_finish): allow for a few more than max_iter
+    const size_t max_bodies = max_iter + (lazy_margin > -1.0 ? std::min<size_t>(max_iter, 64) : 0);
+    for (; it < max_bodies && !stop; ++it) {
         // never run more than run_ahead iterations ahead of the device-side loop condition
         if (it >= (size_t)run_ahead) {
             CK(cudaEventSynchronize(ctx->ring[(it - run_ahead) % ctx->ring.size()]));
@@ -1300,7 +1312,7 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
         ctx->iter_ms[k * 3 + 2] = c;
     }
     ctx->timing.iterations = use_graph ? (unsigned long long)hs.executed : exec_timed;
-    if (use_graph) ctx->launches = launches0 + 1ull + 5ull * (unsigned long long)hs.executed; // init + 5 kernels per executed body
+    if (use_graph) ctx->launches = launches0 + 1ull + 5ull * (unsigned long long)hs.executed; // init + the kernels of every executed body
     ctx->timing.kernels_launched = ctx->launches - launches0;
     return ICPB_OK;
 }
@@ -1383,7 +1395,7 @@ int icpb_debug_pairs(icpb_ctx *ctx, uint32_t *model_idx, double *dist, uint8_t *
     CK(ctx->dbg_idx.ensure(n));
     CK(ctx->dbg_kept.ensure(n));
     CK(ctx->kd0.ensure(n));
-    debug_pairs_kernel<<<grid_for(n, 256), 256, 0, s>>>(ctx->gv, ctx->nn_pos.p, ctx->nn_d.p, ctx->src_perm.p, n,
+    debug_pairs_kernel<<<grid_for(n, 256), 256, 0, s>>>(ctx->gv, ctx->sx.p, ctx->sy.p, ctx->sz.p, ctx->nn_pos.p, ctx->nn_d.p, ctx->src_perm.p, n,
                                                         ctx->d_state, ctx->dbg_idx.p, (double *)ctx->kd0.p,
                                                         ctx->dbg_kept.p);
     CKL();
@@ -1424,6 +1436,7 @@ int icpb_find_pairs(icpb_ctx *ctx, const double *q, size_t n, double d_box, uint
     if (n == 0) return ICPB_OK;
     if (n >= 0xFFFFFFF0ull) return ICPB_ERR_ARG;
     cudaStream_t s = ctx->stream;
+    ctx->gv.block_levels = (int)std::max(-1.0, std::min(ctx->opt_block_levels, 1.0));
     CK(ctx->stage.ensure(3 * n));
     CK(ctx->dbg_idx.ensure(n));
     CK(ctx->kd0.ensure(n));

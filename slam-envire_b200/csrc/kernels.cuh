@@ -290,6 +290,29 @@ __global__ void node_level1_kernel(const uint32_t *__restrict__ cell_start, cons
     node[t] = m ? icpb_node_word(m, lo, hi) : 0u;
 }
 
+// a grid of one single cell has no level 1: its tight box is computed on its own (one block)
+__global__ void __launch_bounds__(256) cell_box_single_kernel(const MPoint *__restrict__ pts, uint32_t n, GridDims g,
+                                                              uint32_t *__restrict__ cell_box)
+{
+    __shared__ int lo[3], hi[3];
+    if (threadIdx.x < 3) {
+        lo[threadIdx.x] = 15;
+        hi[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    for (uint32_t p = threadIdx.x; p < n; p += blockDim.x) {
+        const MPoint q = pts[p];
+        const double u[3] = {(q.x - g.o[0]) * g.inv_h, (q.y - g.o[1]) * g.inv_h, (q.z - g.o[2]) * g.inv_h};
+        for (int a = 0; a < 3; ++a) {
+            const int nb = icpb_node_nibble(u[a], 0.0, 0);
+            atomicMin(&lo[a], nb);
+            atomicMax(&hi[a], nb);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) cell_box[0] = n ? icpb_node_word(0u, lo, hi) : 0u;
+}
+
 // level-l node words (l >= 2) from the words one level below
 __global__ void node_levelN_kernel(const uint32_t *__restrict__ below, int nx, int ny, int nz, int mx, int my, int mz,
                                    uint32_t *__restrict__ node)
@@ -316,37 +339,48 @@ __global__ void node_levelN_kernel(const uint32_t *__restrict__ below, int nx, i
 // ---------------------------------------------------------------------------
 // K2 + K3: transform the source vertex and find its exact nearest model point
 // ---------------------------------------------------------------------------
+// answer of one query: inclusive ball (find_nearest(val, max)), then the optional edge/normal pair filter
+template <bool EAN>
+__device__ __forceinline__ unsigned search_finish(uint32_t i, uint32_t pos, double d2, float lb, bool pos_changed, double d_box,
+                                                  const double *M, const EanView &ean, uint32_t *__restrict__ nn_pos,
+                                                  double *__restrict__ nn_d, float *__restrict__ nn_lb)
+{
+    const double d = sqrt(d2);
+    bool ok = (pos != ICPB_NONE) && (d <= d_box);
+    if (EAN && ok) {
+        // EdgeAndNormalPairFilter (icp/icp.hpp:206-221) on the nearest neighbour: neither vertex on a scan edge,
+        // normals (source normal mapped by C_local2globalnew.linear()) less than pi/8 apart
+        const double ax = ean.snx[i], ay = ean.sny[i], az = ean.snz[i];
+        const double bx = (M[0] * ax + M[1] * ay) + M[2] * az;
+        const double by = (M[4] * ax + M[5] * ay) + M[6] * az;
+        const double bz = (M[8] * ax + M[9] * ay) + M[10] * az;
+        const NPoint mn = ean.mn[pos];
+        const double dot = (bx * mn.nx + by * mn.ny) + bz * mn.nz;
+        const bool edge = ean.sedge[i] || mn.edge;
+        const double normal_angle = acos(fmin(1.0, dot));
+        ok = !edge && (normal_angle < 3.14159265358979323846 / 8.0);
+    }
+    if (pos_changed) nn_pos[i] = pos; // the nearest neighbour as such (warm start / skip test of the next iteration) ...
+    nn_d[i] = ok ? d : icpb_inf();    // ... a pair only when this is finite
+    nn_lb[i] = lb;
+    return ok ? 1u : 0u;
+}
+
+// K2 + K3, one thread per query: transform the source vertex (C_local2globalnew * v, fp64), evaluate the previous
+// winner exactly and apply the skip test (icpb_nn_skip_pt): a query whose old winner provably is still the exact
+// nearest neighbour -- or that provably has no pair within d_box -- is answered on the spot; the others are searched
+// right away (flat block scan / fast path / pyramid walk, grid_view.h).
+// Measured and rejected (round 2, cfg2): parking the queries that need a search in a queue (shared memory per block,
+// or global memory + a second kernel of long-lived warps that take 32 entries at a time, lists per kind of search) so
+// that no lane idles for a skipped neighbour -- 26-28 ms of search per align against 21 ms for this form: the walkers
+// of a warp diverge among themselves whatever their neighbours do, and the queue traffic comes on top.
 #ifndef ICPB_SEARCH_THREADS
-#define ICPB_SEARCH_THREADS 256
-#endif
-#ifndef ICPB_SEARCH_QPT
-#define ICPB_SEARCH_QPT 2
+#define ICPB_SEARCH_THREADS 128
 #endif
 #ifndef ICPB_SEARCH_MIN_BLOCKS
-#define ICPB_SEARCH_MIN_BLOCKS 3
+#define ICPB_SEARCH_MIN_BLOCKS 8
 #endif
 constexpr int SEARCH_THREADS = ICPB_SEARCH_THREADS;
-constexpr int SEARCH_QPT = ICPB_SEARCH_QPT;                // queries per thread in the set-up phase
-constexpr int SEARCH_TILE = SEARCH_THREADS * SEARCH_QPT;   // queries per block
-
-// A query that has to be searched, parked in shared memory between the set-up phase and the search phase
-struct __align__(16) QRec {
-    double qx, qy, qz; // transformed source vertex (global frame)
-    double bd2;        // exact squared distance to the previous winner (+inf without one): the warm start
-    uint32_t wpos;     // previous winner (position in pts[]) or ICPB_NONE
-    uint32_t widx;     // its insertion index
-    float rs;          // radius the search is made to cover (0: only what the answer needs)
-    uint32_t pad;
-};
-
-// One block = one tile of SEARCH_TILE consecutive (Morton-ordered) source vertices, two phases:
-//   set-up  every thread transforms its vertices (C_local2globalnew * v, fp64), evaluates the previous winner exactly
-//           and applies the skip test (icpb_nn_skip): a query whose old winner provably is still the exact nearest
-//           neighbour -- or that provably has no pair within d_box -- is answered on the spot.  The others are
-//           parked in shared memory and appended to one of two lists: "fast" (ball inside a 2x2x2 cell block) or
-//           "walk" (pyramid).
-//   search  the lists are handed out to the threads densely, whole warps per list, so that a warp's lanes run the
-//           same kind of search and no lane idles for a neighbour that was skipped.
 template <bool EAN>
 __global__ void __launch_bounds__(SEARCH_THREADS, ICPB_SEARCH_MIN_BLOCKS)
     search_kernel(const GridView g, const double *__restrict__ sx, const double *__restrict__ sy,
@@ -354,121 +388,85 @@ __global__ void __launch_bounds__(SEARCH_THREADS, ICPB_SEARCH_MIN_BLOCKS)
                   double *__restrict__ nn_d, float *__restrict__ nn_lb, int use_warm, const NNTune tune, const EanView ean)
 {
     if (st->done) return;
-    __shared__ QRec rec[SEARCH_TILE];
-    __shared__ uint16_t list[SEARCH_TILE]; // fast slots from the front, walk slots from the back
-    __shared__ unsigned cnt[2];
     __shared__ double M[12]; // C_local2globalnew: broadcast reads instead of per-thread global loads
     __shared__ float dM[12]; // M - Mprev: how the source moved since the previous loop body
+    __shared__ NNRun runs[ICPB_BLOCK_ROWS][SEARCH_THREADS]; // run lists of the flat block scan, one column per thread
+    __shared__ unsigned sm_cnt[4], sm_ticket;
     if (threadIdx.x < 12) {
         M[threadIdx.x] = st->M[threadIdx.x];
         dM[threadIdx.x] = (float)(st->M[threadIdx.x] - st->Mprev[threadIdx.x]);
     }
-    if (threadIdx.x < 2) cnt[threadIdx.x] = 0u;
+    if (threadIdx.x < 4) sm_cnt[threadIdx.x] = 0u;
+    if (threadIdx.x == 4) sm_ticket = 0u;
     __syncthreads();
-    const double d_box = st->d_box;
-    const double dbox2s = d_box * d_box * (1.0 + 1e-12);
-    const bool warm_on = use_warm && st->warm;
-    NNTune tn = tune;
-    if (!warm_on) tn.skip = 0;
-    const uint32_t tile0 = blockIdx.x * (uint32_t)SEARCH_TILE;
-    unsigned found = 0, nskip = 0;
-
-    // answer of one query: inclusive ball (find_nearest(val, max)), then the optional edge/normal pair filter
-    auto finish = [&](uint32_t i, uint32_t pos, double d2, float lb) {
-        const double d = sqrt(d2);
-        bool ok = (pos != ICPB_NONE) && (d <= d_box);
-        if (EAN && ok) {
-            // EdgeAndNormalPairFilter (icp/icp.hpp:206-221) on the nearest neighbour: neither vertex on a scan edge,
-            // normals (source normal mapped by C_local2globalnew.linear()) less than pi/8 apart
-            const double ax = ean.snx[i], ay = ean.sny[i], az = ean.snz[i];
-            const double bx = (M[0] * ax + M[1] * ay) + M[2] * az;
-            const double by = (M[4] * ax + M[5] * ay) + M[6] * az;
-            const double bz = (M[8] * ax + M[9] * ay) + M[10] * az;
-            const NPoint mn = ean.mn[pos];
-            const double dot = (bx * mn.nx + by * mn.ny) + bz * mn.nz;
-            const bool edge = ean.sedge[i] || mn.edge;
-            const double normal_angle = acos(fmin(1.0, dot));
-            ok = !edge && (normal_angle < 3.14159265358979323846 / 8.0);
-        }
-        nn_pos[i] = pos; // the nearest neighbour as such (warm start and skip test of the next iteration) ...
-        nn_d[i] = ok ? d : icpb_inf(); // ... a pair only when this is finite
-        nn_lb[i] = lb;
-        found += ok ? 1u : 0u;
-    };
-
-    // ---- set-up phase ----
-#pragma unroll
-    for (int k = 0; k < SEARCH_QPT; ++k) {
-        const uint32_t slot = (uint32_t)k * SEARCH_THREADS + threadIdx.x;
-        const uint32_t i = tile0 + slot;
-        if (i >= n) continue;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned found = 0, far = 0, nskip = 0, ndefer = 0;
+    if (i < n) {
+        const double d_box = st->d_box;
+        const double dbox2s = d_box * d_box * (1.0 + 1e-12);
+        const bool warm_on = use_warm && st->warm;
+        NNTune tn = tune;
+        if (!warm_on) tn.skip = 0;
         // source read with evict-first hints: the L2 is for the model, which every query gathers from
         const double vx = __ldcs(sx + i), vy = __ldcs(sy + i), vz = __ldcs(sz + i);
+        const uint32_t wp = warm_on ? __ldcs(nn_pos + i) : ICPB_NONE;
+        const float lbp = tn.skip ? __ldcs(nn_lb + i) : 0.0f;
         double qx, qy, qz;
         icpb_aff_apply(M, vx, vy, vz, qx, qy, qz); // C_local2globalnew * v (icp/icp.hpp:130)
-        const uint32_t wpos = warm_on ? __ldcs(nn_pos + i) : ICPB_NONE;
-        const float lbp = tn.skip ? __ldcs(nn_lb + i) : 0.0f;
+        MPoint wm;
+        wm.x = wm.y = wm.z = 0.0;
+        wm.idx = 0;
+        const bool has_w = wp < g.n;
+        if (has_w) wm = g.pts[wp];
         const float delta = tn.skip ? icpb_motion_bound(dM, (float)vx, (float)vy, (float)vz) : 0.0f;
         double d2w;
         float lbn;
-        const int sk = icpb_nn_skip(g, qx, qy, qz, d_box, wpos, lbp, delta, d2w, lbn);
+        const int sk = icpb_nn_skip_pt(qx, qy, qz, d_box, has_w, wm, lbp, delta, d2w, lbn);
+        double standin;
         if (sk) {
-            finish(i, wpos, d2w, lbn);
-            ++nskip;
-            continue;
-        }
-        const double need2 = dbox2s < d2w ? dbox2s : d2w;
-        const double rs2 = icpb_cover_radius2(g, need2, d2w <= dbox2s, delta, tn);
-        QRec r;
-        r.qx = qx, r.qy = qy, r.qz = qz;
-        r.bd2 = d2w;
-        r.wpos = wpos < g.n ? wpos : ICPB_NONE;
-        r.widx = wpos < g.n ? (uint32_t)g.pts[wpos].idx : 0u;
-        r.rs = (float)sqrt(rs2);
-        r.pad = 0u;
-        rec[slot] = r;
-        // which list: the level the search will start at, computed exactly like icpb_nn_plan does
-        NNState s;
-        icpb_nn_init(g, qx, qy, qz, dbox2s, s, (double)r.rs * (double)r.rs);
-        if (r.wpos != ICPB_NONE) {
-            s.bd2 = d2w;
-            icpb_nn_refresh_bound(s);
-        }
-        const int fast = icpb_nn_start_level(g, s) == 0 ? 1 : 0;
-        const unsigned at = atomicAdd(&cnt[fast ? 0 : 1], 1u);
-        list[fast ? at : (unsigned)SEARCH_TILE - 1u - at] = (uint16_t)slot;
-    }
-    __syncthreads();
-
-    // ---- search phase: whole warps per list ----
-    const unsigned nf = cnt[0], nw = cnt[1], nf_pad = (nf + 31u) & ~31u;
-    for (unsigned j = threadIdx.x; j < nf_pad + nw; j += SEARCH_THREADS) {
-        unsigned slot;
-        if (j < nf_pad) {
-            if (j >= nf) continue;
-            slot = list[j];
+            found = search_finish<EAN>(i, wp, d2w, lbn, false, d_box, M, ean, nn_pos, nn_d, nn_lb);
+            nskip = 1;
+        } else if (!EAN && tn.skip && icpb_nn_defer(d2w, lbn, d_box, st->tau_guard, standin)) {
+            nn_d[i] = standin; // a pair exists (the old winner is within d_box); the trim will not keep it
+            nn_lb[i] = lbn;
+            found = 1;
+            ndefer = 1;
         } else {
-            slot = list[(unsigned)SEARCH_TILE - 1u - (j - nf_pad)];
+            const double need2 = dbox2s < d2w ? dbox2s : d2w;
+            const float rs = icpb_cover_radius(g, need2, delta, tn);
+            NNState s;
+            icpb_nn_init(g, qx, qy, qz, dbox2s, s, (double)rs * (double)rs);
+            if (has_w) {
+                s.bd2 = d2w;
+                s.bidx = wm.idx;
+                s.bpos = wp;
+                icpb_nn_refresh_bound(s);
+            }
+            far = icpb_nn_run(g, s, &runs[0][threadIdx.x], SEARCH_THREADS) > 0 ? 1u : 0u;
+            found = search_finish<EAN>(i, s.bpos, s.bd2, icpb_nn_lower_bound(g, s), true, d_box, M, ean, nn_pos, nn_d, nn_lb);
         }
-        const QRec r = rec[slot];
-        NNState s;
-        icpb_nn_init(g, r.qx, r.qy, r.qz, dbox2s, s, (double)r.rs * (double)r.rs);
-        if (r.wpos != ICPB_NONE) {
-            s.bd2 = r.bd2;
-            s.bidx = r.widx;
-            s.bpos = r.wpos;
-            icpb_nn_refresh_bound(s);
-        }
-        icpb_nn_run(g, s);
-        finish(tile0 + slot, s.bpos, s.bd2, icpb_nn_lower_bound(g, s));
     }
+    // counters: per block in shared memory, flushed by the block's last warp (thousands of same-address global atomics
+    // per launch were a third of the launch once most queries skip); no block barrier: a finished warp frees its slot
     found = __reduce_add_sync(0xFFFFFFFFu, found);
+    far = __reduce_add_sync(0xFFFFFFFFu, far);
     nskip = __reduce_add_sync(0xFFFFFFFFu, nskip);
-    if ((threadIdx.x & 31) == 0) { // no block barrier here: a finished warp frees its slot at once
-        if (found) atomicAdd(&st->found, (unsigned long long)found);
-        if (nskip) atomicAdd(&st->skipped, (unsigned long long)nskip);
+    ndefer = __reduce_add_sync(0xFFFFFFFFu, ndefer);
+    if ((threadIdx.x & 31) == 0) {
+        if (found) atomicAdd(&sm_cnt[0], found);
+        if (far) atomicAdd(&sm_cnt[1], far);
+        if (nskip) atomicAdd(&sm_cnt[2], nskip);
+        if (ndefer) atomicAdd(&sm_cnt[3], ndefer);
+        __threadfence_block();
+        if (atomicAdd(&sm_ticket, 1u) == SEARCH_THREADS / 32 - 1) {
+            const unsigned f = atomicAdd(&sm_cnt[0], 0u), w = atomicAdd(&sm_cnt[1], 0u), k = atomicAdd(&sm_cnt[2], 0u),
+                           e = atomicAdd(&sm_cnt[3], 0u);
+            if (f) atomicAdd(&st->found, (unsigned long long)f);
+            if (w) atomicAdd(&st->far, (unsigned long long)w);
+            if (k) atomicAdd(&st->skipped, (unsigned long long)k);
+            if (e) atomicAdd(&st->deferred, (unsigned long long)e);
+        }
     }
-    if (threadIdx.x == 0 && nw) atomicAdd(&st->far, (unsigned long long)nw);
 }
 
 // stand-alone form for icpb_find_pairs(): queries already in the global frame (AoS)
@@ -1065,9 +1063,9 @@ __global__ void pose_kernel(IcpState *st, double *trace, int trace_cap)
 __global__ void init_state_kernel(IcpState *st, Aff12 Cl2g, unsigned long long max_iter, double min_mse,
                                   double min_mse_diff, double overlap, unsigned long long n_po,
                                   unsigned long long n_local, unsigned long long n_offset,
-                                  cudaGraphConditionalHandle cond, int use_cond)
+                                  cudaGraphConditionalHandle cond, int use_cond, double lazy_margin)
 {
-    icpb_state_init(*st, Cl2g.a, max_iter, min_mse, min_mse_diff, overlap, n_po);
+    icpb_state_init(*st, Cl2g.a, max_iter, min_mse, min_mse_diff, overlap, n_po, lazy_margin);
     st->n_local = n_local;
     st->n_global_offset = n_offset;
     st->sel_prefix = st->sel_krem = st->sel_k = 0;
@@ -1102,7 +1100,8 @@ __global__ void compact_kept_kernel(const double *__restrict__ nn_d, const uint3
     if (keep) out_keys[base + __popc(m & ((1u << lane) - 1u))] = (unsigned long long)__double_as_longlong(d);
 }
 
-__global__ void debug_pairs_kernel(const GridView g, const uint32_t *__restrict__ nn_pos,
+__global__ void debug_pairs_kernel(const GridView g, const double *__restrict__ sx, const double *__restrict__ sy,
+                                   const double *__restrict__ sz, const uint32_t *__restrict__ nn_pos,
                                    const double *__restrict__ nn_d, const uint32_t *__restrict__ perm, uint32_t n,
                                    const IcpState *st, uint32_t *__restrict__ idx_out,
                                    double *__restrict__ d_out, uint8_t *__restrict__ kept_out)
@@ -1111,10 +1110,21 @@ __global__ void debug_pairs_kernel(const GridView g, const uint32_t *__restrict_
     if (i >= n) return;
     const uint32_t pos = nn_pos[i];
     const uint32_t o = perm[i]; // back to the adapter's visiting order
-    // nn_pos keeps the nearest neighbour as such; it is a pair only when its distance is finite (within d_box, filter passed)
-    idx_out[o] = (pos == ICPB_NONE || !(nn_d[i] < icpb_inf())) ? ICPB_NONE : (uint32_t)g.pts[pos].idx;
-    d_out[o] = nn_d[i];
-    kept_out[o] = (st->sel_k > 0 && pair_kept(nn_d[i], o, st->tau, st->p_cut)) ? 1 : 0;
+    const double d = nn_d[i];
+    // nn_pos keeps the nearest neighbour as such; it is a pair only when its distance is finite (within d_box, filter
+    // passed).  A finite distance that is not the distance to nn_pos is the stand-in of a deferred query (lazy search).
+    uint32_t idx = (pos == ICPB_NONE || !(d < icpb_inf())) ? ICPB_NONE : (uint32_t)g.pts[pos].idx;
+    if (idx != ICPB_NONE) {
+        const double *Ml = st->early ? st->M : st->Mprev; // the transform the last search used
+        double qx, qy, qz;
+        icpb_aff_apply(Ml, sx[i], sy[i], sz[i], qx, qy, qz);
+        const MPoint m = g.pts[pos];
+        const double dx = qx - m.x, dy = qy - m.y, dz = qz - m.z;
+        if (sqrt((dx * dx + dy * dy) + dz * dz) != d) idx = 0xFFFFFFFEu; // ICPB_DEFERRED
+    }
+    idx_out[o] = idx;
+    d_out[o] = d;
+    kept_out[o] = (st->sel_k > 0 && pair_kept(d, o, st->tau, st->p_cut)) ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------

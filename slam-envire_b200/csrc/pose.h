@@ -33,6 +33,12 @@ struct IcpState {
     unsigned long long found; // pairs found by K3 (all ranks after the collective)
     unsigned long long far;   // queries that started above level 0 (diagnostic)
     unsigned long long skipped; // queries answered by the skip test, without a search (diagnostic)
+    unsigned long long deferred; // queries whose search was deferred: a pair exists, but beyond what the trim keeps (diagnostic)
+    // lazy search: a query whose nearest neighbour provably is farther than tau_guard (and provably has a pair within
+    // d_box) is not searched; its distance entry is a lower bound.  The trim result is exact as long as the new tau does
+    // not exceed tau_guard -- otherwise the loop body is run again with force_exact (icpb_iteration_finish)
+    double tau_guard, lazy_margin; // lazy_margin <= -1: lazy search off
+    int force_exact, redone;
     double sums[ICPB_NSUMS];
     // trim (K4)
     unsigned long long sel_prefix, sel_krem, sel_k;
@@ -49,6 +55,8 @@ struct IcpState {
     int executed; // loop bodies executed so far (== trace rows)
     int warm;     // nn_pos[] of the previous iteration is valid
     unsigned int tickets[16];
+    unsigned int q_count[2]; // search queue of this loop body: fast entries (from the front), walk entries (from the back)
+    unsigned int q_cursor;   // next queue entry to hand out
     unsigned int comm_seq;   // collectives completed on the peer-memory path (same on every rank)
     unsigned int comm_error; // a peer did not show up within the spin budget
 };
@@ -161,8 +169,9 @@ ICPB_HD int icpb_loop_continues(const IcpState &s)
 }
 
 ICPB_HD void icpb_state_init(IcpState &s, const double *Cl2g, unsigned long long max_iter, double min_mse,
-                             double min_mse_diff, double overlap, unsigned long long n_po)
+                             double min_mse_diff, double overlap, unsigned long long n_po, double lazy_margin = -1.0)
 {
+    s.lazy_margin = lazy_margin;
     icpb_aff_identity(s.C);
     for (int i = 0; i < 12; ++i) s.Cl2g[i] = Cl2g[i];
     for (int i = 0; i < 12; ++i) s.M[i] = s.Mprev[i] = Cl2g[i]; // C_local2globalnew = C_local2global (icp/icp.hpp:118)
@@ -178,6 +187,11 @@ ICPB_HD void icpb_state_init(IcpState &s, const double *Cl2g, unsigned long long
     s.found = 0;
     s.far = 0;
     s.skipped = 0;
+    s.deferred = 0;
+    s.tau_guard = icpb_inf(); // nothing is deferred in the first loop body
+    s.force_exact = 0;
+    s.redone = 0;
+    s.q_count[0] = s.q_count[1] = s.q_cursor = 0;
     s.early = 0;
     s.executed = 0;
     s.warm = 0;
@@ -195,6 +209,19 @@ ICPB_HD void icpb_iteration_finish(IcpState &s, double *trace_row)
 {
     const double old_mse = s.mse;
     const unsigned long long kept = s.sel_k;
+    // Lazy search: the distance entries of deferred queries are lower bounds, all above tau_guard.  The n_po smallest
+    // entries -- hence tau, the kept set and the sums -- are exact iff the new tau stays at or below tau_guard; if it
+    // does not, this loop body did not happen: it is run again with every query searched (or skipped) properly.
+    if (s.tau_guard < icpb_inf() && kept > 0 && !(s.tau <= s.tau_guard)) {
+        s.force_exact = 1;
+        s.tau_guard = icpb_inf();
+        s.redone += 1;
+        s.found = 0;
+        s.far = 0;
+        s.skipped = 0;
+        s.deferred = 0;
+        return;
+    }
     // d_box = pairs.trim(n_po) * 2.0 ; trim returns NaN when no pair is left (icp/icp.cpp:33-40)
     const double tau = kept > 0 ? s.tau : __builtin_nan("");
     s.d_box = tau * 2.0;
@@ -207,7 +234,9 @@ ICPB_HD void icpb_iteration_finish(IcpState &s, double *trace_row)
         trace_row[4] = s.d_box;
         trace_row[7] = (double)s.far;
         trace_row[24] = (double)s.skipped;
-        trace_row[25] = trace_row[26] = trace_row[27] = 0.0;
+        trace_row[25] = (double)s.deferred;
+        trace_row[26] = (double)s.redone;
+        trace_row[27] = 0.0;
     }
     if (kept < 3) { // Pairs::MIN_PAIRS (icp/icp.hpp:475-476): return result as is
         s.early = 1;
@@ -236,4 +265,9 @@ ICPB_HD void icpb_iteration_finish(IcpState &s, double *trace_row)
     s.found = 0;
     s.far = 0;
     s.skipped = 0;
+    s.deferred = 0;
+    s.force_exact = 0;
+    // what the next loop body may defer: everything provably farther than this loop body's tau plus a margin
+    s.tau_guard = (s.lazy_margin > -1.0 && kept > 0) ? tau * (1.0 + s.lazy_margin) : icpb_inf();
+    s.q_count[0] = s.q_count[1] = s.q_cursor = 0;
 }

@@ -78,7 +78,7 @@ class Harness:
         M[:3, :] = T.reshape(3, 4)
         return M, mse.value
 
-    def skip_sequence(self, model, h, q_steps, d_box, kappa=4.0, floor_cells=0.05):
+    def skip_sequence(self, model, h, q_steps, d_box, reach_cells=0.25, floor_cells=0.05):
         """q_steps: (steps, nq, 3) positions of the same queries over time; d_box: one per step."""
         model = np.ascontiguousarray(model, dtype=np.float64)
         q = np.ascontiguousarray(q_steps, dtype=np.float64)
@@ -88,12 +88,12 @@ class Harness:
         d = np.zeros((steps, nq))
         sk = np.zeros((steps, nq), np.uint8)
         self.L.hs_skip_sequence(self._p(model), C.c_size_t(len(model)), C.c_double(h), self._p(q), C.c_size_t(nq),
-                                C.c_int(steps), self._p(db), C.c_double(kappa), C.c_double(floor_cells),
+                                C.c_int(steps), self._p(db), C.c_double(reach_cells), C.c_double(floor_cells),
                                 self._p(idx, C.c_uint32), self._p(d), self._p(sk, C.c_uint8))
         return idx, d, sk.astype(bool)
 
     def align(self, model, h, src, T=None, density=1.0, max_iter=10, min_mse=1e-4, min_mse_diff=1e-5, overlap=1.0,
-              warm=1, skip=1, kappa=4.0, floor_cells=0.05):
+              warm=1, skip=1, reach_cells=0.25, floor_cells=0.05, lazy_margin=0.05):
         model = np.ascontiguousarray(model, dtype=np.float64)
         src = np.ascontiguousarray(src, dtype=np.float64)
         res = np.zeros(32)
@@ -102,8 +102,8 @@ class Harness:
         ex = self.L.hs_align(self._p(model), C.c_size_t(len(model)), C.c_double(h), self._p(src),
                              C.c_size_t(len(src)), C.c_size_t(int(len(src) * density)), self._p(Tcm),
                              C.c_size_t(max_iter), C.c_double(min_mse), C.c_double(min_mse_diff), C.c_double(overlap),
-                             C.c_int(warm), self._p(res), self._p(trace), C.c_size_t(len(trace)), C.c_int(skip), C.c_double(kappa),
-                             C.c_double(floor_cells))
+                             C.c_int(warm), self._p(res), self._p(trace), C.c_size_t(len(trace)), C.c_int(skip), C.c_double(reach_cells),
+                             C.c_double(floor_cells), C.c_double(lazy_margin))
         return dict(C=res[:16].reshape(4, 4).T.copy(), iter=int(res[16]), pairs=int(res[17]), mse=res[18],
                     mse_diff=res[19], d_box=res[20], early=bool(res[21]), trace=trace[:ex])
 

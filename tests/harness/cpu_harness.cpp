@@ -19,6 +19,7 @@ static HsCounters g_cnt;
 #include "../../slam-envire_b200/csrc/grid_view.h"
 #include "../../slam-envire_b200/csrc/pose.h"
 
+static int g_block_levels = 1;
 namespace {
 struct HostGrid {
     GridView g;
@@ -147,10 +148,12 @@ void build(HostGrid &G, const double *model, size_t n, double h)
     g.pts = G.pts.data();
     g.ptsf = G.ptsf.data();
     g.n = (uint32_t)n;
+    g.block_levels = g_block_levels;
 }
 } // namespace
 
 extern "C" {
+void hs_set_block_levels(int v) { g_block_levels = v; }
 void hs_counters(unsigned long long *out, int reset)
 {
     out[0] = g_cnt.cells; out[1] = g_cnt.cands; out[2] = g_cnt.pops; out[3] = g_cnt.nodes; out[4] = g_cnt.exact; out[5] = g_cnt.expands;
@@ -186,7 +189,8 @@ void hs_transform_from_sums(const double *sums, double *T12, double *mse) { icpb
 // trace: rows of 24 doubles.  Returns the number of executed loop bodies.
 int hs_align(const double *model, size_t nm, double h, const double *src, size_t ns, size_t adapter_size,
              const double *T_l2g_cm, size_t max_iter, double min_mse, double min_mse_diff, double overlap,
-             int use_warm, double *result, double *trace, size_t trace_cap, int skip, double kappa, double floor_cells)
+             int use_warm, double *result, double *trace, size_t trace_cap, int skip, double reach_cells, double floor_cells,
+             double lazy_margin)
 {
     HostGrid G;
     build(G, model, nm, h);
@@ -198,12 +202,12 @@ int hs_align(const double *model, size_t nm, double h, const double *src, size_t
         Cl2g[r * 4 + 3] = T_l2g_cm[12 + r];
     }
     const size_t n_po = (size_t)((double)adapter_size * overlap);
-    icpb_state_init(st, Cl2g, max_iter, min_mse, min_mse_diff, overlap, n_po);
+    icpb_state_init(st, Cl2g, max_iter, min_mse, min_mse_diff, overlap, n_po, (skip && use_warm) ? lazy_margin : -1.0);
     std::vector<uint32_t> nn_pos(ns, ICPB_NONE);
     std::vector<double> nn_d(ns, 0.0);
     std::vector<float> nn_lb(ns, 0.0f);
     NNTune tune;
-    tune.kappa = (float)kappa;
+    tune.reach_cells = (float)reach_cells;
     tune.floor_cells = (float)floor_cells;
     while (!st.done) {
         // the set-up / search phases of search_kernel (kernels.cuh), one query after the other
@@ -225,13 +229,20 @@ int hs_align(const double *model, size_t nm, double h, const double *src, size_t
             double d2;
             int lvl = 0;
             const int sk = icpb_nn_skip(G.g, qx, qy, qz, st.d_box, wpos, lbp, delta, d2w, lb);
+            double standin;
             if (sk) {
                 pos = wpos;
                 d2 = d2w;
                 st.skipped += 1;
+            } else if (tn.skip && icpb_nn_defer(d2w, lb, st.d_box, st.tau_guard, standin)) {
+                nn_d[i] = standin;
+                nn_lb[i] = lb;
+                st.found += 1;
+                st.deferred += 1;
+                continue;
             } else {
                 const double need2 = dbox2s < d2w ? dbox2s : d2w;
-                const float rs = (float)std::sqrt(icpb_cover_radius2(G.g, need2, d2w <= dbox2s, delta, tn));
+                const float rs = icpb_cover_radius(G.g, need2, delta, tn);
                 icpb_nn_search(G.g, qx, qy, qz, dbox2s, wpos, pos, d2, lvl, (double)rs * (double)rs, &lb);
             }
             const double d = std::sqrt(d2);
@@ -295,14 +306,14 @@ int hs_align(const double *model, size_t nm, double h, const double *src, size_t
 // from set to set).  Every set is answered with icpb_nn_skip / icpb_nn_search exactly like search_kernel does,
 // delta = the true displacement rounded up.  out_idx/out_d: answers of every set; out_skipped: 1 where no search ran.
 int hs_skip_sequence(const double *model, size_t nm, double h, const double *q, size_t nq, int steps, const double *d_box,
-                     double kappa, double floor_cells, uint32_t *out_idx, double *out_d, uint8_t *out_skipped)
+                     double reach_cells, double floor_cells, uint32_t *out_idx, double *out_d, uint8_t *out_skipped)
 {
     HostGrid G;
     build(G, model, nm, h);
     std::vector<uint32_t> nn_pos(nq, ICPB_NONE);
     std::vector<float> nn_lb(nq, 0.0f);
     NNTune tn;
-    tn.kappa = (float)kappa;
+    tn.reach_cells = (float)reach_cells;
     tn.floor_cells = (float)floor_cells;
     for (int t = 0; t < steps; ++t) {
         tn.skip = t > 0;
@@ -325,7 +336,7 @@ int hs_skip_sequence(const double *model, size_t nm, double h, const double *q, 
                 d2 = d2w;
             } else {
                 const double need2 = dbox2s < d2w ? dbox2s : d2w;
-                const float rs = (float)std::sqrt(icpb_cover_radius2(G.g, need2, d2w <= dbox2s, delta, tn));
+                const float rs = icpb_cover_radius(G.g, need2, delta, tn);
                 icpb_nn_search(G.g, c[0], c[1], c[2], dbox2s, t > 0 ? nn_pos[i] : ICPB_NONE, pos, d2, lvl, (double)rs * (double)rs, &lb);
             }
             nn_pos[i] = pos;

@@ -184,10 +184,23 @@ def test_align_cfg1_full_gui_defaults(icp, oracle, synth):
     i_ref, d_ref = run.last_pairs()
     d_ref = np.where(i_ref == 0xFFFFFFFF, np.inf, d_ref)
     assert np.array_equal(np.isinf(d_gpu), np.isinf(d_ref))
-    fin = np.isfinite(d_ref)
+    # lazy search (default): pairs that the trim does not keep may be left unresolved -- a pair exists, its distance
+    # entry is a lower bound above tau; everything else is the exact nearest neighbour
+    lazy = i_gpu == 0xFFFFFFFE
+    assert not kept[lazy].any() and np.all(np.isfinite(d_ref[lazy])) and np.all(d_gpu[lazy] <= d_ref[lazy] + 1e-9)
+    assert lazy.sum() == icp.trace()[-1]["deferred"]
+    fin = np.isfinite(d_ref) & ~lazy
     assert np.allclose(d_gpu[fin], d_ref[fin], rtol=0, atol=1e-9)
-    assert (i_gpu != i_ref).sum() <= 5
+    assert (i_gpu[~lazy] != i_ref[~lazy]).sum() <= 5
     assert kept.sum() == r.pairs
+    # the strict mode resolves every pair
+    icp.set_option("lazy", 0)
+    r2, _, _ = _align_both(icp, oracle, m, s, **prm)
+    icp.set_option("lazy", 1)
+    i2, d2, kept2 = icp.debug_pairs()
+    assert r2.iter == r.iter and r2.pairs == r.pairs and np.array_equal(r2.matrix(), r.matrix()) and r2.mse == r.mse
+    assert not (i2 == 0xFFFFFFFE).any() and np.array_equal(kept2, kept)
+    assert np.allclose(d2[np.isfinite(d_ref)], d_ref[np.isfinite(d_ref)], rtol=0, atol=1e-9) and (i2 != i_ref).sum() <= 5
     # First iteration (C = identity exactly): bit-exact distances and indices
     r, r_ref, run = _align_both(icp, oracle, m, s, **dict(prm, max_iter=1))
     i_gpu, d_gpu, kept = icp.debug_pairs()
@@ -197,6 +210,34 @@ def test_align_cfg1_full_gui_defaults(icp, oracle, synth):
     ref_kept = np.zeros(len(d_ref), bool)
     ref_kept[order] = True
     assert np.array_equal(kept, ref_kept)
+
+
+def test_lazy_search_rerun_path(icp, oracle, synth):
+    """Lazy search defers queries that lie beyond tau_guard = (previous tau) * (1 + margin); when the new tau exceeds the
+    guard the loop body is run again exactly.  A negative margin puts the guard below the previous tau, so that most
+    bodies are run twice: every result must equal the strict mode's bit for bit, and the oracle's."""
+    m, s, T, prm = synth.config("cfg1", scale=0.2)
+    prm = dict(prm, max_iter=25)
+    icp.set_option("lazy", 0)
+    r0, r_ref, run = _align_both(icp, oracle, m, s, **prm)
+    t0 = icp.trace()
+    out = {}
+    for margin in (0.05, 0.0, -0.3):
+        icp.set_option("lazy", 1)
+        icp.set_option("lazy_margin", margin)
+        for graph in (1, 0):
+            icp.set_option("graph", graph)
+            r, _, _ = _align_both(icp, oracle, m, s, **prm)
+            t = icp.trace()
+            assert r.iter == r0.iter == r_ref.iter and r.pairs == r0.pairs and r.mse == r0.mse
+            assert np.array_equal(r.matrix(), r0.matrix())
+            assert [(a["found"], a["kept"], a["tau"]) for a in t] == [(a["found"], a["kept"], a["tau"]) for a in t0]
+            out[margin] = (sum(a["deferred"] for a in t), t[-1]["redone"])
+    icp.set_option("graph", 1)
+    icp.set_option("lazy_margin", 0.05)
+    assert out[0.05][0] > 0 and out[0.05][1] == 0  # queries are deferred, every trim verifies
+    assert out[-0.3][1] > 0                         # bodies were run again
+    _check_align(icp, r0, r_ref, run, 20.0)
 
 
 def test_align_cfg2_scaled_noise_and_source_frame(icp, oracle, synth):

@@ -21,6 +21,13 @@ from conftest import ROOT, assert_transform_close
     (4998, 1500, 40.0, np.inf, 12),  # one cell holds everything
 ])
 def test_grid_search_exact(harness, oracle, nm, nq, h, d_box, seed):
+    for bl in (1, 0, -1):  # flat block scan for start levels <= 1 / 0 only / never (fast path + pyramid walk)
+        harness.L.hs_set_block_levels(bl)
+        _grid_search_exact(harness, oracle, nm, nq, h, d_box, seed)
+    harness.L.hs_set_block_levels(1)
+
+
+def _grid_search_exact(harness, oracle, nm, nq, h, d_box, seed):
     rng = np.random.default_rng(seed)
     m = rng.uniform(-10, 10, (nm, 3))
     q = rng.uniform(-14, 14, (nq, 3))
@@ -88,11 +95,11 @@ def test_pose_step_matches_oracle(harness, oracle):
     assert np.allclose(T, T_ref, rtol=0, atol=1e-12) and abs(mse - mse_ref) <= 1e-14 * mse_ref
 
 
-@pytest.mark.parametrize("h,d_box,step,kappa,floor", [
-    (0.5, np.inf, 0.01, 4.0, 0.05), (0.5, 0.6, 0.02, 4.0, 0.05), (0.25, 0.3, 0.004, 0.0, 0.0), (1.5, 0.2, 0.03, 8.0, 0.4),
-    (0.5, 0.05, 0.001, 4.0, 0.05),
+@pytest.mark.parametrize("h,d_box,step,reach,floor", [
+    (0.5, np.inf, 0.01, 0.25, 0.05), (0.5, 0.6, 0.02, 1.0, 0.2), (0.25, 0.3, 0.004, 0.0, 0.0), (1.5, 0.2, 0.03, 8.0, 0.4),
+    (0.5, 0.05, 0.001, 0.25, 0.05),
 ])
-def test_search_skipping_is_exact(harness, oracle, synth, h, d_box, step, kappa, floor):
+def test_search_skipping_is_exact(harness, oracle, synth, h, d_box, step, reach, floor):
     """Search skipping (icpb_nn_skip, grid_view.h): queries drift a little from step to step, as the source of an align
     does; every step's answers -- searched or skipped -- must be the exact nearest neighbours the oracle finds, with
     bit-identical distances.  The model is a surface scene plus exact duplicates and a lattice patch (ties)."""
@@ -109,7 +116,7 @@ def test_search_skipping_is_exact(harness, oracle, synth, h, d_box, step, kappa,
     drift *= step / np.linalg.norm(drift)
     q = np.stack([q0 + t * drift + (rng.normal(0, step * 0.1, q0.shape) if t else 0) for t in range(steps)])
     dbs = np.full(steps, d_box) * np.linspace(1.0, 0.7, steps)                 # d_box shrinks like 2*tau does
-    idx, d, sk = harness.skip_sequence(m, h, q, dbs, kappa, floor)
+    idx, d, sk = harness.skip_sequence(m, h, q, dbs, reach, floor)
     M = oracle.Model()
     M.add(m)
     for t in range(steps):
@@ -117,20 +124,26 @@ def test_search_skipping_is_exact(harness, oracle, synth, h, d_box, step, kappa,
         d0 = np.where(i0 == 0xFFFFFFFF, dbs[t], d0)
         assert np.array_equal(i0, idx[t]) and np.array_equal(d0, d[t]), t
     assert not sk[0].any()
-    if floor > 0:
-        assert sk[1:].mean() > 0.3  # the rule does fire
+    if floor > 0 and 1.5 * step <= 0.25 * floor * h:  # slow enough for the searches to widen their reach
+        assert sk[1:].mean() > 0.1  # the rule does fire
 
 
-@pytest.mark.parametrize("warm,skip", [(0, 0), (1, 0), (1, 1)])
-def test_emulated_device_loop_matches_oracle(harness, oracle, synth, warm, skip):
+@pytest.mark.parametrize("warm,skip,lazy", [(0, 0, -1), (1, 0, -1), (1, 1, -1), (1, 1, 0.05), (1, 1, 0.0), (1, 1, -0.3)])
+def test_emulated_device_loop_matches_oracle(harness, oracle, synth, warm, skip, lazy):
+    """lazy > -1: lazy search with that margin.  -0.3 puts the guard BELOW the previous tau: most trims fail to verify and
+    their loop bodies run twice -- the results must not change."""
     m, s, T, prm = synth.config("cfg1", 0.1)
     M = oracle.Model()
     M.add(m)
     run = oracle.Run()
     r = M.align(s, run=run, **prm)
-    e = harness.align(m, 0.5, s, warm=warm, skip=skip, **prm)
+    e = harness.align(m, 0.5, s, warm=warm, skip=skip, lazy_margin=lazy, **prm)
     if skip:
         assert e["trace"][:, 24].sum() > 0 and e["trace"][0, 24] == 0
+    if lazy >= 0:
+        assert e["trace"][:, 25].sum() > 0  # queries were deferred
+    if lazy == -0.3:
+        assert e["trace"][-1, 26] > 0  # loop bodies were run again
     assert e["iter"] == r.iter and e["pairs"] == r.pairs and not e["early"]
     assert_transform_close(e["C"], r.matrix(), 20.0)
     assert abs(e["mse"] - r.mse) <= 1e-5 * r.mse
