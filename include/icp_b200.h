@@ -28,7 +28,7 @@ extern "C" {
 #define ICPB_OK 0
 #define ICPB_ERR_CUDA 1         /* CUDA runtime error / no device            */
 #define ICPB_ERR_ARG 2          /* bad argument                              */
-#define ICPB_ERR_NO_MODEL 3     /* align() before any addToModel()           */
+#define ICPB_ERR_NO_MODEL 3     /* reserved (aligning against an empty model is legal, as in the reference: no pairs) */
 #define ICPB_ERR_NO_SOURCE 4    /* align_resident() before source upload     */
 #define ICPB_ERR_NCCL 5         /* NCCL missing / collective failed          */
 #define ICPB_ERR_CAPACITY 6     /* output buffer too small                   */
@@ -136,7 +136,8 @@ int icpb_align(icpb_ctx *, const double *xyz_aos, size_t n_vertices, const doubl
 
 /* Replaces: Trimmed::getPairsDistance (icp/icp.hpp:439, filled at :500-504):
  * kept distances of the last executed iteration, ascending.  With
- * out == NULL only *n_out is written. */
+ * out == NULL only *n_out is written (the count of all ranks' kept pairs).  After a sharded (multi-GPU) align every
+ * rank returns the kept distances of ITS shard (*n_out = their number): concatenate and merge for the full list. */
 int icpb_pairs_distance(icpb_ctx *, double *out_sorted, size_t capacity, size_t *n_out);
 /* Parity hook: correspondences of the last executed iteration, one entry per
  * visited source vertex: model index in insertion order (ICPB_NO_PAIR if

@@ -179,7 +179,7 @@ struct icpb_ctx {
     std::string err;
     // options
     double opt_cell_size = 0.0, opt_target = 12.0, opt_max_cells = 64.0 * 1024 * 1024, opt_run_ahead = 2.0,
-           opt_warm = 1.0, opt_skip = 1.0, opt_skip_reach = 0.25, opt_skip_floor = 0.05, opt_lazy = 1.0, opt_lazy_margin = 0.05, opt_block_levels = 1.0, opt_profile = 0.0, opt_sort = 1.0, opt_margin = 0.0, opt_merge = 1.0, opt_graph = 1.0, opt_trim_bpsm = 2.0, opt_mom_bpsm = 2.0;
+           opt_warm = 1.0, opt_skip = 1.0, opt_skip_reach = 0.25, opt_skip_floor = 0.05, opt_lazy = 1.0, opt_lazy_margin = 0.05, opt_fail_build = 0.0, opt_block_levels = 1.0, opt_profile = 0.0, opt_sort = 1.0, opt_margin = 0.0, opt_merge = 1.0, opt_graph = 1.0, opt_trim_bpsm = 2.0, opt_mom_bpsm = 2.0;
     // model
     DevBuf<double> model_raw, model_nrm;
     DevBuf<uint8_t> model_edge;
@@ -427,6 +427,7 @@ static double *opt_slot(icpb_ctx *ctx, const char *key)
     if (!strcmp(key, "block_levels")) return &ctx->opt_block_levels;
     if (!strcmp(key, "lazy")) return &ctx->opt_lazy;
     if (!strcmp(key, "lazy_margin")) return &ctx->opt_lazy_margin;
+    if (!strcmp(key, "test_fail_next_build")) return &ctx->opt_fail_build;
     if (!strcmp(key, "profile")) return &ctx->opt_profile;
     if (!strcmp(key, "sort_source")) return &ctx->opt_sort;
     if (!strcmp(key, "growth_margin")) return &ctx->opt_margin;
@@ -593,7 +594,10 @@ static int model_add(icpb_ctx *ctx, const double *xyz, const double *normals, co
     bool merged = false;
     {
         int rc = try_merge_append(ctx, n_old, m, &merged);
-        if (rc != ICPB_OK) return rc;
+        if (rc != ICPB_OK) {
+            ctx->grid_dirty = true; // the index may be half merged: the points are in model_raw, rebuild before the next use
+            return rc;
+        }
     }
     if (!merged) ctx->grid_dirty = true;
     return ICPB_OK;
@@ -680,8 +684,11 @@ static int build_grid(icpb_ctx *ctx)
     cudaStream_t s = ctx->stream;
     memset(&ctx->ginfo, 0, sizeof(ctx->ginfo));
     ctx->gv.n = 0;
-    ctx->grid_dirty = false;
-    if (n == 0) return ICPB_OK;
+    ctx->grid_dirty = true; // cleared at the very end: a build that fails half-way is repeated (and fails again) next time
+    if (n == 0) {
+        ctx->grid_dirty = false;
+        return ICPB_OK;
+    }
     cudaEvent_t e0 = ctx->ev_up0, e1 = ctx->ev_up1;
     CK(cudaEventRecord(e0, s));
     // bounding box
@@ -702,6 +709,11 @@ static int build_grid(icpb_ctx *ctx)
     for (int a = 0; a < 3; ++a) {
         ext[a] = mx[a] - mn[a];
         if (!(ext[a] >= 0.0) || !isfinite(ext[a])) return ICPB_ERR_ARG; // NaN / inf vertices
+    }
+    if (ctx->opt_fail_build != 0.0) { // fault injection for the tests: this build fails after its first steps
+        ctx->opt_fail_build = 0.0;
+        ctx->err = "injected build failure (test_fail_next_build)";
+        return ICPB_ERR_CUDA;
     }
     double se[3] = {ext[0], ext[1], ext[2]};
     std::sort(se, se + 3);
@@ -838,6 +850,7 @@ static int build_grid(icpb_ctx *ctx)
     gi.build_ms = ms;
     gi.merges = ctx->merges;
     ctx->last_valid = false; // nn_pos of an earlier align refers to the old layout
+    ctx->grid_dirty = false;
     return ICPB_OK;
 }
 
@@ -1352,10 +1365,10 @@ int icpb_pairs_distance(icpb_ctx *ctx, double *out, size_t capacity, size_t *n_o
     if (!ctx->last_valid || ctx->last_early) return ICPB_OK;
     cudaStream_t s = ctx->stream;
     const uint32_t n = (uint32_t)ctx->src_n;
-    const size_t kept = (size_t)ctx->h_state->pairs;
-    *n_out = kept;
+    size_t kept = (size_t)ctx->h_state->pairs;
+    *n_out = kept; // sharded align: an upper bound until the rank-local count is known (below)
     if (!out) return ICPB_OK;
-    if (capacity < kept) return ICPB_ERR_CAPACITY;
+    if (ctx->n_ranks == 1 && capacity < kept) return ICPB_ERR_CAPACITY;
     if (kept == 0) return ICPB_OK;
     CK(ctx->kd0.ensure(n));
     CK(ctx->kd1.ensure(n));
@@ -1367,7 +1380,14 @@ int icpb_pairs_distance(icpb_ctx *ctx, double *out, size_t capacity, size_t *n_o
     unsigned int h_cnt = 0;
     CK(cudaMemcpyAsync(&h_cnt, cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    if ((size_t)h_cnt != kept) {
+    if (ctx->n_ranks > 1) {
+        // sharded align: `kept` counts the pairs of all ranks, this context holds its own shard's -- the rank-local kept
+        // distances are returned (ascending); the caller concatenates / merges the ranks' lists if it wants them all
+        kept = (size_t)h_cnt;
+        *n_out = kept;
+        if (capacity < kept) return ICPB_ERR_CAPACITY;
+        if (kept == 0) return ICPB_OK;
+    } else if ((size_t)h_cnt != kept) {
         ctx->err = "internal: kept-pair count mismatch";
         return ICPB_ERR_CUDA;
     }

@@ -94,8 +94,12 @@ ICPB_HD void icpb_pose_quat(const double *s, double *q)
     const double tr = (s[0] + s[4]) + s[8];
     const double dn = sqrt((d0 * d0 + d1 * d1) + d2 * d2);
     if (dn == 0.0) {
-        q[0] = 1.0;
-        q[1] = q[2] = q[3] = 0.0;
+        // symmetric cross-covariance: Q = diag(t, -t, -t, -t).  t >= 0: the identity.  t < 0: the largest eigenvalue -t is
+        // triple, its eigenvectors span (x,y,z): some rotation by pi -- which one the reference's EigenSolver returns is
+        // not determined; the x axis is taken here (measure-zero case, listed among the deviations in DESIGN.md)
+        q[0] = tr >= 0.0 ? 1.0 : 0.0;
+        q[1] = tr >= 0.0 ? 0.0 : 1.0;
+        q[2] = q[3] = 0.0;
         return;
     }
     const double lambda = sqrt(tr * tr + dn * dn);

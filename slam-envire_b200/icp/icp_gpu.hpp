@@ -244,11 +244,16 @@ public:
     }
     void addToModel(_Adapter model)
     {
+        fetchPairsDistance(minResult_); // the kept distances of the last align live in device scratch: secure them first
         double T[16];
         toColMajor(model.local2global(), T);
         check(detail::modelAdd(ctx_, model, T));
     }
-    void clearModel() { check(icpb_model_clear(ctx_)); }
+    void clearModel()
+    {
+        fetchPairsDistance(minResult_);
+        check(icpb_model_clear(ctx_));
+    }
 
     size_t getNumIterations() { return minResult_.iter; }
     double getMeanSquareError() { return minResult_.mse; }

@@ -107,3 +107,21 @@ def test_ref_align_random_clouds(oracle, synth):
         fn = oracle.apply_transform(np.eye(4), np.eye(4), o.matrix())
         assert np.allclose(fn, g["fn_T"], rtol=0, atol=1e-10)
         assert np.allclose(run.pairs_distance(), g["pairs_distance"], rtol=1e-9, atol=1e-13)
+
+
+def test_oracle_reproduces_device_trace_at_full_size(oracle):
+    """BASELINE configs[1] at FULL size (1M vs 1M): tests/golden/cfg2_poses.npz holds, for every loop body of the align
+    as the B200 path ran it (tools/make_cfg2_poses.py), the pose it started from and its found / kept / tau / mse.  The
+    oracle evaluates two of those loop bodies on the same input and must reproduce the recorded numbers: found and kept
+    exactly, tau bit for bit (the same distance), mse to 1e-9 (the 17 sums are reduced in a different order)."""
+    import os
+    import bench
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "cfg2_poses.npz"))
+    model, src, _ = bench.workload(0)
+    ref = bench.CpuReference(model)
+    n_po = int(len(src) * bench.ALIGN["overlap"])
+    for k in (len(z["tau"]) // 2, len(z["tau"]) - 1):
+        r = ref.iteration(src, z["C_in"][k], float(z["d_box_in"][k]), n_po, 0)
+        assert r["found"] == z["found"][k] and r["kept"] == z["kept"][k]
+        assert r["tau"] == z["tau"][k]
+        assert abs(r["mse"] - z["mse"][k]) <= 1e-9 * z["mse"][k]

@@ -404,6 +404,25 @@ def test_c_abi_error_paths(pkg):
     icp.close()
 
 
+def test_failed_build_is_repeated(pkg, oracle, synth):
+    """A grid build that fails half-way (injected) must not leave a context that silently aligns against an empty
+    model: the next call repeats the build.  The same for an addToModel whose merge into the built grid fails."""
+    m, s, T, prm = synth.config("cfg1", 0.05)
+    prm = dict(prm, max_iter=6)
+    M = oracle.Model()
+    M.add(m)
+    r_ref = M.align(s, **prm)
+    ctx = pkg.Icp(0)
+    ctx.add_to_model(m)
+    ctx.set_option("test_fail_next_build", 1)
+    with pytest.raises(pkg.IcpError):
+        ctx.align(s, **prm)
+    r = ctx.align(s, **prm)  # the build is repeated, now succeeds
+    assert r.iter == r_ref.iter and r.pairs == r_ref.pairs and r.pairs > 0
+    assert np.abs(r.matrix() - r_ref.matrix()).max() < 1e-9
+    ctx.close()
+
+
 def test_pairs_transform_stage(icp, oracle, pkg):
     """K4+K5+K6 in isolation against Pairs::trim + Pairs::getTransform of the oracle (and, in the dev container, of the
     reference itself): the non-Horn pose solve, the moments, the trim threshold."""
