@@ -179,7 +179,7 @@ struct icpb_ctx {
     std::string err;
     // options
     double opt_cell_size = 0.0, opt_target = 12.0, opt_max_cells = 64.0 * 1024 * 1024, opt_run_ahead = 2.0,
-           opt_warm = 1.0, opt_skip = 1.0, opt_skip_reach = 0.25, opt_skip_floor = 0.05, opt_lazy = 1.0, opt_lazy_margin = 0.05, opt_fail_build = 0.0, opt_block_levels = 1.0, opt_profile = 0.0, opt_sort = 1.0, opt_margin = 0.0, opt_merge = 1.0, opt_graph = 1.0, opt_trim_bpsm = 2.0, opt_mom_bpsm = 2.0;
+           opt_warm = 1.0, opt_skip = 1.0, opt_skip_reach = 0.25, opt_skip_floor = 0.05, opt_lazy = 1.0, opt_lazy_margin = 0.05, opt_fail_build = 0.0, opt_linear_trim = 1.0, opt_block_levels = 1.0, opt_profile = 0.0, opt_sort = 1.0, opt_margin = 0.0, opt_merge = 1.0, opt_graph = 1.0, opt_trim_bpsm = 2.0, opt_mom_bpsm = 2.0;
     // model
     DevBuf<double> model_raw, model_nrm;
     DevBuf<uint8_t> model_edge;
@@ -216,6 +216,7 @@ struct icpb_ctx {
     IcpState *h_state = nullptr; // pinned
     int *h_flags = nullptr;      // pinned
     uint32_t *d_ghist = nullptr;
+    uint32_t *d_lhist = nullptr; // linear histogram of the pair distances (search epilogue -> trim_linear_kernel)
     unsigned long long *d_counter = nullptr;
     DevBuf<double> partials;
     DevBuf<double> trace;
@@ -329,6 +330,8 @@ int icpb_create(icpb_ctx **out, int device_id)
     CK(cudaMallocHost((void **)&ctx->h_flags, FLAG_RING * sizeof(int)));
     CK(cudaMalloc((void **)&ctx->d_ghist, (SEL_MAX_BINS + 64) * sizeof(uint32_t)));
     CK(cudaMemset(ctx->d_ghist, 0, (SEL_MAX_BINS + 64) * sizeof(uint32_t)));
+    CK(cudaMalloc((void **)&ctx->d_lhist, (LIN_BINS * LIN_STRIDE + 64) * sizeof(uint32_t)));
+    CK(cudaMemset(ctx->d_lhist, 0, (LIN_BINS * LIN_STRIDE + 64) * sizeof(uint32_t)));
     CK(cudaMalloc((void **)&ctx->d_counter, 8 * sizeof(unsigned long long)));
     CK(cudaMemset(ctx->d_counter, 0, 8 * sizeof(unsigned long long)));
     CK(cudaMalloc((void **)&ctx->d_gather, 64 * sizeof(unsigned long long)));
@@ -402,6 +405,7 @@ void icpb_destroy(icpb_ctx *ctx)
     if (ctx->h_state) cudaFreeHost(ctx->h_state);
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     if (ctx->d_ghist) cudaFree(ctx->d_ghist);
+    if (ctx->d_lhist) cudaFree(ctx->d_lhist);
     if (ctx->d_counter) cudaFree(ctx->d_counter);
     if (ctx->d_gather) cudaFree(ctx->d_gather);
     for (auto e : ctx->events) cudaEventDestroy(e);
@@ -427,6 +431,7 @@ static double *opt_slot(icpb_ctx *ctx, const char *key)
     if (!strcmp(key, "block_levels")) return &ctx->opt_block_levels;
     if (!strcmp(key, "lazy")) return &ctx->opt_lazy;
     if (!strcmp(key, "lazy_margin")) return &ctx->opt_lazy_margin;
+    if (!strcmp(key, "linear_trim")) return &ctx->opt_linear_trim;
     if (!strcmp(key, "test_fail_next_build")) return &ctx->opt_fail_build;
     if (!strcmp(key, "profile")) return &ctx->opt_profile;
     if (!strcmp(key, "sort_source")) return &ctx->opt_sort;
@@ -1031,11 +1036,20 @@ __global__ void tie_quota_kernel(IcpState *st, const unsigned long long *gathere
     }
 }
 
-static int launch_trim(icpb_ctx *ctx, uint32_t n)
+static int launch_trim(icpb_ctx *ctx, uint32_t n, bool linear = false)
 {
     cudaStream_t s = ctx->stream;
     const unsigned blocks = std::max(1u, std::min(grid_for(n, SEL_THREADS * 4), 148u * (unsigned)std::max(1.0, std::min(ctx->opt_trim_bpsm, 32.0))));
     const int fused = (ctx->n_ranks == 1 || ctx->use_p2p) ? 1 : 0;
+    if (linear) { // the search kernel has binned the distances over [0, d_box]: one launch
+        CK(ctx->cand_key.ensure(std::max<size_t>(n, 1)));
+        CK(ctx->cand_idx.ensure(std::max<size_t>(n, 1)));
+        trim_linear_kernel<<<blocks, SEL_THREADS, 0, s>>>(ctx->nn_d.p, ctx->src_perm.p, n, ctx->d_state, ctx->d_lhist,
+                                                          ctx->cand_key.p, ctx->cand_idx.p, (unsigned int *)(ctx->d_counter + 2));
+        CKL();
+        ctx->launches += 1;
+        return ICPB_OK;
+    }
     if (fused) {
         // two grid-wide digit passes, then collect the few remaining candidates and finish on them in one block
         CK(ctx->cand_key.ensure(std::max<size_t>(n, 1)));
@@ -1135,15 +1149,19 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
     // lazy search needs the skip state (winner + bound per query); the edge/normal filter decides pairs per winner
     const double lazy_margin = (tune.skip && ctx->opt_lazy != 0.0 && !ean.on) ? std::max(-0.9, ctx->opt_lazy_margin) : -1.0;
     const unsigned search_blocks = grid_for(std::max<uint32_t>(n, 1), SEARCH_THREADS);
-    auto enqueue_iteration = [&]() -> int {
+    // loop bodies after the first trim in ONE launch on the histogram the search kernel fills (single GPU; the
+    // multi-GPU transports keep the radix passes with their exchanges)
+    const bool linear_ok = ctx->n_ranks == 1 && ctx->opt_linear_trim != 0.0;
+    auto enqueue_iteration = [&](bool linear) -> int {
+        uint32_t *lh = linear ? ctx->d_lhist : nullptr;
         if (ean.on)
             search_kernel<true><<<search_blocks, SEARCH_THREADS, 0, s>>>(ctx->gv, ctx->sx.p, ctx->sy.p, ctx->sz.p, n,
                                                                          ctx->d_state, ctx->nn_pos.p, ctx->nn_d.p,
-                                                                         ctx->nn_lb.p, use_warm, tune, ean);
+                                                                         ctx->nn_lb.p, use_warm, tune, ean, lh);
         else
             search_kernel<false><<<search_blocks, SEARCH_THREADS, 0, s>>>(ctx->gv, ctx->sx.p, ctx->sy.p, ctx->sz.p, n,
                                                                           ctx->d_state, ctx->nn_pos.p, ctx->nn_d.p,
-                                                                          ctx->nn_lb.p, use_warm, tune, ean);
+                                                                          ctx->nn_lb.p, use_warm, tune, ean, lh);
         CKL();
         ctx->launches += 1;
         return ICPB_OK;
@@ -1157,7 +1175,7 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
         std::vector<unsigned char> key;
         auto add_key = [&](const void *p, size_t bytes) { key.insert(key.end(), (const unsigned char *)p, (const unsigned char *)p + bytes); };
         const void *ptrs[] = {ctx->sx.p, ctx->sy.p, ctx->sz.p, ctx->nn_pos.p, ctx->nn_d.p, ctx->nn_lb.p, ctx->src_perm.p, ctx->partials.p,
-                              ctx->trace.p, ctx->cand_key.p, ctx->cand_idx.p, ctx->d_state, ctx->d_ghist};
+                              ctx->trace.p, ctx->cand_key.p, ctx->cand_idx.p, ctx->d_state, ctx->d_ghist, ctx->d_lhist};
         add_key(&n, sizeof(n));
         add_key(&ctx->gv, sizeof(ctx->gv));
         add_key(ptrs, sizeof(ptrs));
@@ -1166,9 +1184,10 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
         add_key(&ctx->trace_cap, sizeof(ctx->trace_cap));
         add_key(&use_warm, sizeof(use_warm));
         add_key(&tune, sizeof(tune));
+        add_key(&linear_ok, sizeof(linear_ok));
         add_key(&mom_blocks, sizeof(mom_blocks));
         add_key(&ctx->opt_trim_bpsm, sizeof(double));
-        void *init_args[12];
+        void *init_args[13];
         unsigned long long a_max_iter = max_iter, a_n_po = n_po, a_n = n, a_off = 0;
         double a_mse = prm->min_mse, a_diff = prm->min_mse_diff, a_ov = prm->overlap, a_lazy = lazy_margin;
         int one = 1;
@@ -1182,33 +1201,53 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
             CK(cudaGraphConditionalHandleCreate(&ctx->graph_cond, ctx->graph, 1, cudaGraphCondAssignDefault));
             init_args[0] = &ctx->d_state; init_args[1] = &A; init_args[2] = &a_max_iter; init_args[3] = &a_mse;
             init_args[4] = &a_diff; init_args[5] = &a_ov; init_args[6] = &a_n_po; init_args[7] = &a_n; init_args[8] = &a_off;
-            init_args[9] = &ctx->graph_cond; init_args[10] = &one; init_args[11] = &a_lazy;
+            init_args[9] = &ctx->graph_cond; init_args[10] = &one; init_args[11] = &a_lazy; init_args[12] = &ctx->d_lhist;
             cudaKernelNodeParams kp;
             memset(&kp, 0, sizeof(kp));
             kp.func = (void *)init_state_kernel;
             kp.gridDim = dim3(1);
-            kp.blockDim = dim3(1);
+            kp.blockDim = dim3(256);
             kp.kernelParams = init_args;
             CK(cudaGraphAddKernelNode(&ctx->graph_init_node, ctx->graph, nullptr, 0, &kp));
+            cond = ctx->graph_cond;
+            use_cond = 1;
+            auto capture_body = [&](bool linear) -> int {
+                int rc = enqueue_iteration(linear);
+                if (rc == ICPB_OK) rc = launch_trim(ctx, n, linear);
+                if (rc == ICPB_OK) {
+                    moments_kernel<<<mom_blocks, MOM_THREADS, 0, s>>>(ctx->gv, ctx->sx.p, ctx->sy.p, ctx->sz.p, n, ctx->d_state,
+                                                                      ctx->nn_pos.p, ctx->nn_d.p, ctx->src_perm.p,
+                                                                      ctx->partials.p, ctx->trace.p, ctx->trace_cap, fused,
+                                                                      ctx->p2p, cond, use_cond);
+                }
+                return rc;
+            };
+            // the first loop body (d_box = inf: radix trim) as plain nodes behind the init node, when the later bodies differ
+            cudaGraphNode_t while_dep = ctx->graph_init_node;
+            if (linear_ok) {
+                CK(cudaStreamBeginCaptureToGraph(s, ctx->graph, &ctx->graph_init_node, nullptr, 1, cudaStreamCaptureModeThreadLocal));
+                int rc0 = capture_body(false);
+                cudaStreamCaptureStatus cst;
+                const cudaGraphNode_t *deps = nullptr;
+                size_t ndeps = 0;
+                cudaError_t ci = cudaStreamGetCaptureInfo(s, &cst, nullptr, nullptr, &deps, &ndeps);
+                if (ci == cudaSuccess && ndeps >= 1) while_dep = deps[ndeps - 1];
+                cudaGraph_t cap0 = nullptr;
+                cudaError_t ce0 = cudaStreamEndCapture(s, &cap0);
+                if (rc0 != ICPB_OK) return rc0;
+                if (ci != cudaSuccess || ndeps != 1) return ctx->fail(ci != cudaSuccess ? ci : cudaErrorUnknown, "capture of the first loop body", __LINE__);
+                if (ce0 != cudaSuccess) return ctx->fail(ce0, "cudaStreamEndCapture", __LINE__);
+            }
             cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
             cp.type = cudaGraphNodeTypeConditional;
             cp.conditional.handle = ctx->graph_cond;
             cp.conditional.type = cudaGraphCondTypeWhile;
             cp.conditional.size = 1;
             cudaGraphNode_t cond_node;
-            CK(cudaGraphAddNode(&cond_node, ctx->graph, &ctx->graph_init_node, 1, &cp));
+            CK(cudaGraphAddNode(&cond_node, ctx->graph, &while_dep, 1, &cp));
             cudaGraph_t body = cp.conditional.phGraph_out[0];
             CK(cudaStreamBeginCaptureToGraph(s, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-            cond = ctx->graph_cond;
-            use_cond = 1;
-            int rc = enqueue_iteration();
-            if (rc == ICPB_OK) rc = launch_trim(ctx, n);
-            if (rc == ICPB_OK) {
-                moments_kernel<<<mom_blocks, MOM_THREADS, 0, s>>>(ctx->gv, ctx->sx.p, ctx->sy.p, ctx->sz.p, n, ctx->d_state,
-                                                                  ctx->nn_pos.p, ctx->nn_d.p, ctx->src_perm.p,
-                                                                  ctx->partials.p, ctx->trace.p, ctx->trace_cap, fused,
-                                                                  ctx->p2p, cond, use_cond);
-            }
+            int rc = capture_body(linear_ok);
             cudaGraph_t captured = nullptr;
             cudaError_t ce = cudaStreamEndCapture(s, &captured);
             if (rc != ICPB_OK) return rc;
@@ -1219,20 +1258,20 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
         // this align's parameters go into the init node
         init_args[0] = &ctx->d_state; init_args[1] = &A; init_args[2] = &a_max_iter; init_args[3] = &a_mse;
         init_args[4] = &a_diff; init_args[5] = &a_ov; init_args[6] = &a_n_po; init_args[7] = &a_n; init_args[8] = &a_off;
-        init_args[9] = &ctx->graph_cond; init_args[10] = &one; init_args[11] = &a_lazy;
+        init_args[9] = &ctx->graph_cond; init_args[10] = &one; init_args[11] = &a_lazy; init_args[12] = &ctx->d_lhist;
         cudaKernelNodeParams kp;
         memset(&kp, 0, sizeof(kp));
         kp.func = (void *)init_state_kernel;
         kp.gridDim = dim3(1);
-        kp.blockDim = dim3(1);
+        kp.blockDim = dim3(256);
         kp.kernelParams = init_args;
         CK(cudaGraphExecKernelNodeSetParams(ctx->graph_exec, ctx->graph_init_node, &kp));
         CK(cudaEventRecord(ctx->ev_begin, s));
         CK(cudaGraphLaunch(ctx->graph_exec, s));
     } else {
     CK(cudaEventRecord(ctx->ev_begin, s));
-    init_state_kernel<<<1, 1, 0, s>>>(ctx->d_state, A, max_iter, prm->min_mse, prm->min_mse_diff, prm->overlap, n_po,
-                                      n, 0ull, 0, 0, lazy_margin);
+    init_state_kernel<<<1, 256, 0, s>>>(ctx->d_state, A, max_iter, prm->min_mse, prm->min_mse_diff, prm->overlap, n_po,
+                                        n, 0ull, 0, 0, lazy_margin, ctx->d_lhist);
     CKL();
     ++ctx->launches;
     for (int k = 0; k < FLAG_RING; ++k) ctx->h_flags[k] = -1;
@@ -1255,13 +1294,14 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
         const bool timed = profile && it < (size_t)EVENT_ITERS;
         cudaEvent_t *ev = timed ? &ctx->events[it * 4] : nullptr;
         if (timed) CK(cudaEventRecord(ev[0], s));
+        const bool linear = linear_ok && it > 0; // the first body's d_box is inf
         {
-            int rc = enqueue_iteration();
+            int rc = enqueue_iteration(linear);
             if (rc != ICPB_OK) return rc;
         }
         if (timed) CK(cudaEventRecord(ev[1], s));
         {
-            int rc = launch_trim(ctx, n);
+            int rc = launch_trim(ctx, n, linear);
             if (rc != ICPB_OK) return rc;
         }
         if (timed) CK(cudaEventRecord(ev[2], s));
@@ -1325,7 +1365,8 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
         ctx->iter_ms[k * 3 + 2] = c;
     }
     ctx->timing.iterations = use_graph ? (unsigned long long)hs.executed : exec_timed;
-    if (use_graph) ctx->launches = launches0 + 1ull + 5ull * (unsigned long long)hs.executed; // init + the kernels of every executed body
+    if (use_graph) // init + the kernels of every body that ran (first body: 5; later ones 3 with the one-launch trim)
+        ctx->launches = launches0 + 1ull + (hs.executed + hs.redone > 0 ? 5ull + (linear_ok ? 3ull : 5ull) * (unsigned long long)(hs.executed + hs.redone - 1) : 0ull);
     ctx->timing.kernels_launched = ctx->launches - launches0;
     return ICPB_OK;
 }

@@ -339,11 +339,32 @@ __global__ void node_levelN_kernel(const uint32_t *__restrict__ below, int nx, i
 // ---------------------------------------------------------------------------
 // K2 + K3: transform the source vertex and find its exact nearest model point
 // ---------------------------------------------------------------------------
+// linear binning of the pair distances over [0, d_box] (fused first step of the trim, see trim_linear_kernel)
+constexpr int LIN_BINS = 2048;
+#ifndef ICPB_LIN_STRIDE
+#define ICPB_LIN_STRIDE 8
+#endif
+constexpr int LIN_STRIDE = ICPB_LIN_STRIDE; // words between bins: one 32-byte sector per bin spreads the atomics over the L2 slices
+__device__ __forceinline__ double lin_scale(double d_box) { return d_box > 0.0 ? (double)LIN_BINS / d_box : 0.0; }
+// monotone in d; the search epilogue and the trim use this very expression
+__device__ __forceinline__ unsigned lin_bin(double d, double scale)
+{
+    const double b = d * scale;
+    return b >= (double)(LIN_BINS - 1) ? (unsigned)(LIN_BINS - 1) : (unsigned)b;
+}
+// second-level split of bin `bin` into LIN_BINS sub-bins, monotone in d as well
+constexpr int LIN_FINAL_CAP = 512;
+__device__ __forceinline__ unsigned lin_sub_bin(double d, double scale, unsigned bin)
+{
+    const double b = (d * scale - (double)bin) * (double)LIN_BINS;
+    return !(b > 0.0) ? 0u : (b >= (double)(LIN_BINS - 1) ? (unsigned)(LIN_BINS - 1) : (unsigned)b);
+}
+
 // answer of one query: inclusive ball (find_nearest(val, max)), then the optional edge/normal pair filter
 template <bool EAN>
 __device__ __forceinline__ unsigned search_finish(uint32_t i, uint32_t pos, double d2, float lb, bool pos_changed, double d_box,
                                                   const double *M, const EanView &ean, uint32_t *__restrict__ nn_pos,
-                                                  double *__restrict__ nn_d, float *__restrict__ nn_lb)
+                                                  double *__restrict__ nn_d, float *__restrict__ nn_lb, double &d_stored)
 {
     const double d = sqrt(d2);
     bool ok = (pos != ICPB_NONE) && (d <= d_box);
@@ -361,7 +382,8 @@ __device__ __forceinline__ unsigned search_finish(uint32_t i, uint32_t pos, doub
         ok = !edge && (normal_angle < 3.14159265358979323846 / 8.0);
     }
     if (pos_changed) nn_pos[i] = pos; // the nearest neighbour as such (warm start / skip test of the next iteration) ...
-    nn_d[i] = ok ? d : icpb_inf();    // ... a pair only when this is finite
+    d_stored = ok ? d : icpb_inf();
+    nn_d[i] = d_stored; // ... a pair only when this is finite
     nn_lb[i] = lb;
     return ok ? 1u : 0u;
 }
@@ -385,7 +407,8 @@ template <bool EAN>
 __global__ void __launch_bounds__(SEARCH_THREADS, ICPB_SEARCH_MIN_BLOCKS)
     search_kernel(const GridView g, const double *__restrict__ sx, const double *__restrict__ sy,
                   const double *__restrict__ sz, uint32_t n, IcpState *st, uint32_t *__restrict__ nn_pos,
-                  double *__restrict__ nn_d, float *__restrict__ nn_lb, int use_warm, const NNTune tune, const EanView ean)
+                  double *__restrict__ nn_d, float *__restrict__ nn_lb, int use_warm, const NNTune tune, const EanView ean,
+                  uint32_t *__restrict__ lhist /* null: no fused histogram */)
 {
     if (st->done) return;
     __shared__ double M[12]; // C_local2globalnew: broadcast reads instead of per-thread global loads
@@ -401,6 +424,8 @@ __global__ void __launch_bounds__(SEARCH_THREADS, ICPB_SEARCH_MIN_BLOCKS)
     __syncthreads();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned found = 0, far = 0, nskip = 0, ndefer = 0;
+    double dq = icpb_inf(); // the distance entry this thread writes (inf: no pair)
+    const double d_box_h = st->d_box;
     if (i < n) {
         const double d_box = st->d_box;
         const double dbox2s = d_box * d_box * (1.0 + 1e-12);
@@ -424,10 +449,10 @@ __global__ void __launch_bounds__(SEARCH_THREADS, ICPB_SEARCH_MIN_BLOCKS)
         const int sk = icpb_nn_skip_pt(qx, qy, qz, d_box, has_w, wm, lbp, delta, d2w, lbn);
         double standin;
         if (sk) {
-            found = search_finish<EAN>(i, wp, d2w, lbn, false, d_box, M, ean, nn_pos, nn_d, nn_lb);
+            found = search_finish<EAN>(i, wp, d2w, lbn, false, d_box, M, ean, nn_pos, nn_d, nn_lb, dq);
             nskip = 1;
         } else if (!EAN && tn.skip && icpb_nn_defer(d2w, lbn, d_box, st->tau_guard, standin)) {
-            nn_d[i] = standin; // a pair exists (the old winner is within d_box); the trim will not keep it
+            nn_d[i] = dq = standin; // a pair exists (the old winner is within d_box); the trim will not keep it
             nn_lb[i] = lbn;
             found = 1;
             ndefer = 1;
@@ -443,8 +468,15 @@ __global__ void __launch_bounds__(SEARCH_THREADS, ICPB_SEARCH_MIN_BLOCKS)
                 icpb_nn_refresh_bound(s);
             }
             far = icpb_nn_run(g, s, &runs[0][threadIdx.x], SEARCH_THREADS) > 0 ? 1u : 0u;
-            found = search_finish<EAN>(i, s.bpos, s.bd2, icpb_nn_lower_bound(g, s), true, d_box, M, ean, nn_pos, nn_d, nn_lb);
+            found = search_finish<EAN>(i, s.bpos, s.bd2, icpb_nn_lower_bound(g, s), true, d_box, M, ean, nn_pos, nn_d, nn_lb, dq);
         }
+    }
+    // K4's first step, fused: the linear histogram of the pair distances over [0, d_box] (trim_linear_kernel); one atomic
+    // per distinct bin and warp.  Not in the first loop body (d_box = inf), which is trimmed by the radix passes.
+    if (lhist && d_box_h < icpb_inf()) {
+        const unsigned bin = dq < icpb_inf() ? lin_bin(dq, lin_scale(d_box_h)) : ICPB_NONE;
+        const unsigned peers = __match_any_sync(0xFFFFFFFFu, bin);
+        if (bin != ICPB_NONE && (peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0) atomicAdd(&lhist[bin * LIN_STRIDE], (unsigned)__popc(peers));
     }
     // counters: per block in shared memory, flushed by the block's last warp (thousands of same-address global atomics
     // per launch were a third of the launch once most queries skip); no block barrier: a finished warp frees its slot
@@ -559,7 +591,8 @@ __constant__ int c_sel_t_bits[SEL_T_PASSES] = {11, 11, 10};
 // the last block of a pass (or a stand-alone 1-block launch after the histogram
 // all-reduce) picks the bucket holding the k-th smallest key and narrows the prefix
 __device__ void select_pick(IcpState *st, uint32_t *ghist, int pass, bool tie_mode, uint32_t *smem /* >= 34 */,
-                            const uint32_t *rows = nullptr, int world = 1, int rank = 0)
+                            const uint32_t *rows = nullptr, int world = 1, int rank = 0,
+                            unsigned long long krem0 = ~0ull /* pass 0 selects this rank of the keys histogrammed, not min(n_po, found) */)
 {
     const int bits = tie_mode ? c_sel_t_bits[pass] : c_sel_d_bits[pass];
     const int shift = tie_mode ? c_sel_t_shift[pass] : c_sel_d_shift[pass];
@@ -570,7 +603,9 @@ __device__ void select_pick(IcpState *st, uint32_t *ghist, int pass, bool tie_mo
     if (tie_mode)
         krem = (pass == 0) ? st->quota : st->tie_krem;
     else {
-        if (pass == 0) {
+        if (pass == 0 && krem0 != ~0ull) {
+            krem = krem0;
+        } else if (pass == 0) {
             const unsigned long long k = st->n_po < st->found ? st->n_po : st->found; // min(n_po, found)
             if (threadIdx.x == 0) st->sel_k = k;
             krem = k;
@@ -920,6 +955,196 @@ __global__ void __launch_bounds__(SEL_THREADS)
     }
 }
 
+// ---------------------------------------------------------------------------
+// K4, loop bodies after the first: every pair distance lies in [0, d_box] with d_box = 2 * (previous tau) finite, so
+// the search kernel bins the distances of the pairs it finds LINEARLY over that interval in its epilogue (2048 bins,
+// one warp-aggregated global atomic per distinct bin and warp) and the whole trim is this one launch:
+//   every block  scans the histogram (8 KB) and finds the bin that holds the n_po-th smallest distance,
+//                then collects the pairs of that bin from its share of nn_d (a few hundred to a few thousand of 10^6),
+//   last block   selects exactly among the collected keys (six 11-bit digits of the distance bits in shared memory,
+//                then -- only if fewer equidistant pairs are kept than exist -- three digits of the pair index).
+// The first loop body (d_box = inf) and the stand-alone icpb_trim keep the radix passes above.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(SEL_THREADS)
+    trim_linear_kernel(const double *__restrict__ nn_d, const uint32_t *__restrict__ perm, uint32_t n, IcpState *st,
+                       uint32_t *__restrict__ lhist, unsigned long long *__restrict__ cand_key,
+                       uint32_t *__restrict__ cand_idx, unsigned int *__restrict__ cand_count)
+{
+    if (st->done) return;
+    __shared__ uint32_t fhist[SEL_MAX_BINS];
+    __shared__ uint32_t scan_smem[34];
+    __shared__ int is_last;
+    __shared__ unsigned s_bin;
+    __shared__ unsigned long long s_krem;
+    static_assert(LIN_BINS == SEL_THREADS * 8, "eight bins per thread");
+    const unsigned long long k = st->n_po < st->found ? st->n_po : st->found; // min(n_po, found)
+    if (threadIdx.x == 0) s_bin = ICPB_NONE;
+    // which bin holds the k-th smallest distance (every block finds the same one)
+    uint32_t c[8], local = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        c[j] = __ldcg(lhist + (threadIdx.x * 8 + j) * LIN_STRIDE);
+        local += c[j];
+    }
+    uint32_t total;
+    const uint32_t before = block_exclusive_scan(local, scan_smem, total);
+    if (k > 0 && k <= (unsigned long long)total) {
+        unsigned long long run = before;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (run < k && k <= run + c[j]) {
+                s_bin = threadIdx.x * 8 + j;
+                s_krem = k - run;
+            }
+            run += c[j];
+        }
+    }
+    for (int b = threadIdx.x; b < SEL_MAX_BINS; b += SEL_THREADS) fhist[b] = 0u;
+    __syncthreads();
+    const unsigned bin = s_bin;
+    if (bin != ICPB_NONE) {
+        const double scale = lin_scale(st->d_box);
+        const int lane = threadIdx.x & 31;
+        const uint32_t T = gridDim.x * blockDim.x;
+        for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += 4u * T) { // warp-uniform trip count
+            double d[4];
+            uint32_t idx[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                idx[u] = base + (uint32_t)u * T + threadIdx.x;
+                d[u] = (idx[u] < n && idx[u] >= base) ? nn_d[idx[u]] : icpb_inf();
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool hit = d[u] < icpb_inf() && lin_bin(d[u], scale) == bin;
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
+                if (!m) continue;
+                unsigned pos = 0;
+                if (lane == __ffs(m) - 1) pos = atomicAdd(cand_count, (unsigned)__popc(m));
+                pos = __shfl_sync(0xFFFFFFFFu, pos, __ffs(m) - 1) + __popc(m & ((1u << lane) - 1u));
+                if (hit) {
+                    cand_key[pos] = (unsigned long long)__double_as_longlong(d[u]);
+                    cand_idx[pos] = idx[u];
+                }
+            }
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(&st->tickets[7], 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int b = threadIdx.x; b < LIN_BINS; b += SEL_THREADS) lhist[b * LIN_STRIDE] = 0u; // for the next loop body's search
+    const unsigned cnt = *((volatile unsigned int *)cand_count);
+    if (threadIdx.x == 0) st->sel_k = k;
+    // Exact selection among the collected pairs: the s_krem-th smallest by (distance, pair index) -- tau is its distance
+    // and p_cut its pair index (pair_kept: d < tau, or d == tau with an index <= p_cut: a stable order, like the oracle).
+    // One more linear split of the bin into 2048 sub-bins leaves a handful of pairs, ranked by brute force.
+    __shared__ unsigned long long f_key[LIN_FINAL_CAP];
+    __shared__ uint32_t f_perm[LIN_FINAL_CAP];
+    __shared__ unsigned f_cnt, f_sub;
+    __shared__ unsigned long long f_krem;
+    bool done_fast = false;
+    if (bin != ICPB_NONE) {
+        const double scale = lin_scale(st->d_box);
+        const unsigned long long krem = s_krem;
+        if (threadIdx.x == 0) f_cnt = 0u, f_sub = ICPB_NONE;
+        for (unsigned j = threadIdx.x; j < cnt; j += blockDim.x)
+            atomicAdd(&fhist[lin_sub_bin(__longlong_as_double((long long)__ldcg(cand_key + j)), scale, bin)], 1u);
+        __syncthreads();
+        uint32_t c2[8], local2 = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            c2[j] = fhist[threadIdx.x * 8 + j];
+            local2 += c2[j];
+        }
+        uint32_t total2;
+        const uint32_t before2 = block_exclusive_scan(local2, scan_smem, total2);
+        {
+            unsigned long long run = before2;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (run < krem && krem <= run + c2[j]) {
+                    f_sub = threadIdx.x * 8 + j;
+                    f_krem = krem - run;
+                }
+                run += c2[j];
+            }
+        }
+        __syncthreads();
+        for (int b = threadIdx.x; b < SEL_MAX_BINS; b += SEL_THREADS) fhist[b] = 0u;
+        const unsigned sub = f_sub;
+        if (sub != ICPB_NONE) {
+            for (unsigned j = threadIdx.x; j < cnt; j += blockDim.x) {
+                const unsigned long long key = __ldcg(cand_key + j);
+                if (lin_sub_bin(__longlong_as_double((long long)key), scale, bin) != sub) continue;
+                const unsigned at = atomicAdd(&f_cnt, 1u);
+                if (at < LIN_FINAL_CAP) {
+                    f_key[at] = key;
+                    f_perm[at] = perm[__ldcg(cand_idx + j)];
+                }
+            }
+        }
+        __syncthreads();
+        const unsigned m = f_cnt;
+        if (sub != ICPB_NONE && m <= LIN_FINAL_CAP) {
+            const unsigned long long want = f_krem - 1ull; // rank (0-based) inside the sub-bin
+            for (unsigned t = threadIdx.x; t < m; t += blockDim.x) {
+                const unsigned long long kt = f_key[t];
+                const uint32_t pt = f_perm[t];
+                unsigned rank = 0;
+                for (unsigned j = 0; j < m; ++j) rank += (f_key[j] < kt || (f_key[j] == kt && f_perm[j] < pt)) ? 1u : 0u;
+                if ((unsigned long long)rank == want) {
+                    st->tau = __longlong_as_double((long long)kt);
+                    st->p_cut = (long long)pt;
+                    st->need_tie = 0;
+                    st->sel_krem = 1;
+                }
+            }
+            done_fast = true;
+        }
+        __syncthreads();
+    }
+    // nothing to select (tau = NaN), or too many pairs in one sub-bin (masses of equal distances): the general radix
+    // selection over all collected keys, then the tie-break on the pair index
+    if (!done_fast) {
+    for (int pass = 0; pass < SEL_D_PASSES; ++pass) {
+        const int bits = c_sel_d_bits[pass], shift = c_sel_d_shift[pass], hsp = shift + bits;
+        const unsigned bin_mask = (1u << bits) - 1u;
+        const unsigned long long prefix = pass == 0 ? 0ull : st->sel_prefix;
+        if (pass > 0 && st->sel_krem == 0) break;
+        for (unsigned j = threadIdx.x; j < cnt; j += blockDim.x) {
+            const unsigned long long key = __ldcg(cand_key + j);
+            if (pass == 0 || (key >> hsp) == (prefix >> hsp)) atomicAdd(&fhist[(unsigned)(key >> shift) & bin_mask], 1u);
+        }
+        __syncthreads();
+        select_pick(st, fhist, pass, false, scan_smem, nullptr, 1, 0, bin != ICPB_NONE ? s_krem : 0ull);
+        __syncthreads();
+    }
+    if (st->need_tie) { // which of the equidistant pairs survive: the lowest pair indices
+        const unsigned long long tau_bits = (unsigned long long)__double_as_longlong(st->tau);
+        for (int pass = 0; pass < SEL_T_PASSES; ++pass) {
+            const int bits = c_sel_t_bits[pass], shift = c_sel_t_shift[pass], hst = shift + bits;
+            const unsigned bin_mask = (1u << bits) - 1u;
+            const unsigned prefix = pass == 0 ? 0u : st->tie_prefix;
+            for (unsigned j = threadIdx.x; j < cnt; j += blockDim.x) {
+                if (__ldcg(cand_key + j) != tau_bits) continue;
+                const uint32_t pi = perm[__ldcg(cand_idx + j)];
+                if (pass == 0 || hst >= 32 || (pi >> hst) == (prefix >> hst)) atomicAdd(&fhist[(pi >> shift) & bin_mask], 1u);
+            }
+            __syncthreads();
+            select_pick(st, fhist, pass, true, scan_smem);
+            __syncthreads();
+        }
+    }
+    }
+    if (threadIdx.x == 0) {
+        *cand_count = 0;
+        st->tickets[7] = 0;
+    }
+}
+
 __device__ __forceinline__ bool pair_kept(double d, uint32_t i, double tau, long long p_cut)
 {
     return d < tau || (d == tau && (long long)i <= p_cut);
@@ -1063,8 +1288,10 @@ __global__ void pose_kernel(IcpState *st, double *trace, int trace_cap)
 __global__ void init_state_kernel(IcpState *st, Aff12 Cl2g, unsigned long long max_iter, double min_mse,
                                   double min_mse_diff, double overlap, unsigned long long n_po,
                                   unsigned long long n_local, unsigned long long n_offset,
-                                  cudaGraphConditionalHandle cond, int use_cond, double lazy_margin)
+                                  cudaGraphConditionalHandle cond, int use_cond, double lazy_margin, uint32_t *lhist)
 {
+    for (int b = threadIdx.x; b < LIN_BINS; b += blockDim.x) lhist[b * LIN_STRIDE] = 0u; // the fused trim histogram starts empty
+    if (threadIdx.x != 0) return;
     icpb_state_init(*st, Cl2g.a, max_iter, min_mse, min_mse_diff, overlap, n_po, lazy_margin);
     st->n_local = n_local;
     st->n_global_offset = n_offset;
