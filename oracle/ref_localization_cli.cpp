@@ -1,10 +1,15 @@
-// Drives envire::icp::ICPLocalization (host mirror over TrimmedGPU) like a Rock component would:
-// loadEnvironment(model), scan lines -> generatePointcloud -> doScanMatch.  Prints one JSON object.
-//   icp_localization_cli <model.bin> <cov_mode 0|1|2> <measurement_density>
+// Drives the REFERENCE's own envire::icp::ICPLocalization (icp/icpLocalization.hpp + icpLocalization.cpp, compiled
+// unmodified where they lie under /root/reference by oracle/Makefile) on top of the drop-in: the build pre-includes
+// slam-envire_b200/icp/icp_gpu.hpp with -DICP_B200_REPLACE_TRIMMEDKD (envire::icp::TrimmedKD = TrimmedGPU) and defines the
+// include guard of the reference's icp.hpp, which is the one-line switch INTEGRATION.md asks a maintainer to make.
+// Scenario, like a Rock component: the model is written as an envire scene directory (scene.yml + PLY),
+// loadEnvironment(path) reads it back, scan lines -> generatePointcloud -> doScanMatch.  Prints one JSON object.
+// TEST infrastructure (binary in oracle/_ref/, never shipped): the product holds no copy of the reference's caller.
+//   ref_localization_cli <model.bin> <cov_mode 0|1|2> <measurement_density> <cloud_out.bin> <scene_dir>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
-#include "icp/icpLocalization.hpp"
+#include <icpLocalization.hpp> // the reference's (-I$(REF)/icp)
 
 static std::vector<double> read_bin(const char *path)
 {
@@ -24,13 +29,20 @@ int main(int argc, char **argv)
     if (argc < 4) return 2;
     using namespace envire::icp;
     const std::vector<double> mv = read_bin(argv[1]);
-    envire::Environment *env = new envire::Environment();
-    envire::Pointcloud *model = new envire::Pointcloud();
-    env->attachItem(model);
-    envire::FrameNode *fm = new envire::FrameNode();
-    env->addChild(env->getRootNode(), fm);
-    model->setFrameNode(fm);
-    for (size_t i = 0; i + 2 < mv.size(); i += 3) model->vertices.push_back(Eigen::Vector3d(mv[i], mv[i + 1], mv[i + 2]));
+    if (argc < 6) return 2;
+    {
+        // the model as an envire scene on disk: root -> frame node (a non-trivial pose) -> point cloud in that frame
+        envire::Environment env;
+        const Eigen::Affine3d model2World(Eigen::Translation3d(0.5, -0.25, 0.0) * Eigen::AngleAxisd(0.1, Eigen::Vector3d::UnitZ()));
+        envire::Pointcloud *model = new envire::Pointcloud();
+        env.attachItem(model);
+        envire::FrameNode *fm = new envire::FrameNode(model2World);
+        env.addChild(env.getRootNode(), fm);
+        model->setFrameNode(fm);
+        const Eigen::Affine3d world2Model = model2World.inverse();
+        for (size_t i = 0; i + 2 < mv.size(); i += 3) model->vertices.push_back(world2Model * Eigen::Vector3d(mv[i], mv[i + 1], mv[i + 2]));
+        env.serialize(argv[5]);
+    }
 
     ICPConfiguration conf;
     conf.model_density = 1.0;
@@ -52,7 +64,7 @@ int main(int argc, char **argv)
         ICPLocalization loc;
         loc.loadIcpConfiguration(conf);
         loc.initializePointCloud(pcc);
-        loc.loadEnvironment(env, conf.model_density);
+        loc.loadEnvironment(argv[5], conf.model_density); // Environment::unserialize + addToModel per point cloud
 
         // a tilting planar laser 1 m above the ground of the model scene sweeps 60 lines while the body creeps forward;
         // the believed pose is off by a small rigid error that the scan match has to remove

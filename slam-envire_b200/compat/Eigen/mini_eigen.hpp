@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cassert>
 #include <cmath>
+#include <cstdlib>
 #include <iostream>
 #include <limits>
 #include <stdexcept>
@@ -72,6 +73,7 @@ public:
 
     static Matrix Zero() { return Matrix(); }
     static Matrix Ones() { Matrix m; for (int i = 0; i < R * C; ++i) m.d[i] = T(1); return m; }
+    static Matrix Random() { Matrix m; for (int i = 0; i < R * C; ++i) m.d[i] = T(2.0 * rand() / (double)RAND_MAX - 1.0); return m; } // uniform in [-1, 1]
     static Matrix Identity() { Matrix m; for (int i = 0; i < (R < C ? R : C); ++i) m(i, i) = T(1); return m; }
     static Matrix UnitX() { Matrix m; m.d[0] = T(1); return m; }
     static Matrix UnitY() { Matrix m; m.d[1] = T(1); return m; }
@@ -298,6 +300,6 @@ inline Affine3d operator*(const Translation3d &t, const AngleAxisd &a) { return 
 inline Affine3d operator*(const Translation3d &t, const Affine3d &a) { return Affine3d(t) * a; }
 inline Affine3d operator*(const AngleAxisd &a, const Affine3d &b) { return Affine3d(a) * b; }
 
-template <typename T> class aligned_allocator : public std::allocator<T> {};
+template <typename T> using aligned_allocator = std::allocator<T>; // plain new is aligned enough for these doubles
 
 } // namespace Eigen

@@ -19,6 +19,15 @@ public:
     enum attr_flag { SCAN_EDGE = 0x01 };
 
     std::vector<Eigen::Vector3d> vertices;
+    std::string getClassName() const { return "envire::Pointcloud"; }
+    /** a detached copy of the vertices and their metadata (reference: EnvironmentItem::clone via the copy constructor) */
+    Pointcloud *clone() const
+    {
+        Pointcloud *c = new Pointcloud();
+        c->vertices = vertices;
+        c->data_ = data_; // shared, immutable in the ICP path
+        return c;
+    }
 
     template <typename T> std::vector<T> &getVertexData(const std::string &key)
     {

@@ -21,6 +21,8 @@
 #include <envire/maps/Pointcloud.hpp>
 
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <functional>
 #include <limits>
 #include <stdexcept>
@@ -36,9 +38,32 @@ namespace icp {
  * n_po closest and returns the largest kept distance, getTransform() returns the reference's (non-Horn) rigid fit of p onto
  * x.  Same public members (x, p, mse) and methods; the sort / sums / pose solve run on the device through
  * icpb_trim / icpb_pairs_transform (used e.g. by icp/ransac.hpp:40-50 on 3-point samples). */
+namespace detail {
+/** one context per process for Pairs objects that are default-constructed, as the reference's callers do
+ * (icp/ransac.hpp:40); created on first use on device 0 */
+inline icpb_ctx *sharedPairsContext()
+{
+    struct Holder {
+        icpb_ctx *ctx;
+        Holder() : ctx(0)
+        {
+            if (icpb_create(&ctx, 0) != ICPB_OK) {
+                if (ctx) icpb_destroy(ctx);
+                ctx = 0;
+                throw std::runtime_error("envire::icp::Pairs: no CUDA device (there is no CPU fallback)");
+            }
+        }
+        ~Holder() { if (ctx) icpb_destroy(ctx); }
+    };
+    static Holder h;
+    return h.ctx;
+}
+} // namespace detail
+
 class Pairs {
 public:
     const static unsigned int MIN_PAIRS = 3;
+    Pairs() : mse(0), ctx_(0), n_po_(static_cast<size_t>(-1)) {}
     explicit Pairs(icpb_ctx *ctx) : mse(0), ctx_(ctx), n_po_(static_cast<size_t>(-1)) {}
     void add(const Eigen::Vector3d &a, const Eigen::Vector3d &b, double dist)
     {
@@ -51,6 +76,7 @@ public:
         n_po_ = n_po;
         double tau = std::numeric_limits<double>::quiet_NaN();
         size_t kept = 0, ties = 0;
+        if (!ctx_) ctx_ = detail::sharedPairsContext();
         if (icpb_trim(ctx_, dist_.data(), dist_.size(), n_po, &tau, &kept, &ties) != ICPB_OK) throw std::runtime_error(icpb_last_error(ctx_));
         kept_ = kept;
         return tau;
@@ -60,6 +86,7 @@ public:
         if (size() < MIN_PAIRS) throw std::runtime_error("not enough pairs to get transform");
         double T[16], tau;
         size_t kept;
+        if (!ctx_) ctx_ = detail::sharedPairsContext();
         const int rc = icpb_pairs_transform(ctx_, x.empty() ? 0 : x[0].data(), p.empty() ? 0 : p[0].data(), dist_.data(), dist_.size(),
                                             n_po_ < dist_.size() ? n_po_ : dist_.size(), T, &mse, &tau, &kept);
         if (rc == ICPB_ERR_NOT_ENOUGH_PAIRS) throw std::runtime_error("not enough pairs to get transform");
@@ -234,6 +261,7 @@ public:
         std::function<Result(double)> eval = [&](double overlap) { return alignResident(max_iter, min_mse, min_mse_diff, overlap, true); };
         minResult_ = GoldenSection<Result>::minimise(eval, alpha, (alpha + beta) / 2.0, beta, eps);
         measurement.applyTransform(minResult_.C_global2globalnew);
+        traceResult();
     }
     /** fixed overlap (icp/icp.hpp:413-418) */
     void align(_Adapter measurement, size_t max_iter, double min_mse, double min_mse_diff, double overlap)
@@ -241,6 +269,7 @@ public:
         upload(measurement);
         minResult_ = alignResident(max_iter, min_mse, min_mse_diff, overlap, false);
         measurement.applyTransform(minResult_.C_global2globalnew);
+        traceResult();
     }
     void addToModel(_Adapter model)
     {
@@ -276,6 +305,14 @@ private:
     Result minResult_;
     bool pd_pending_ = false;
 
+    /** ICP_B200_TRACE=1: one line per align on stderr (the reference keeps such a trace commented out, icp/icp.hpp:487-495) */
+    void traceResult()
+    {
+        const char *t = getenv("ICP_B200_TRACE");
+        if (!t || !*t || *t == '0') return;
+        fprintf(stderr, "[icp_b200] align: iter %zu pairs %zu overlap %.17g mse %.17g mse_diff %.17g\n", minResult_.iter,
+                minResult_.pairs, minResult_.overlap, minResult_.mse, minResult_.mse_diff);
+    }
     void check(int rc)
     {
         if (rc != ICPB_OK) throw std::runtime_error(std::string("TrimmedGPU: ") + icpb_strerror(rc) + " / " + icpb_last_error(ctx_));

@@ -120,3 +120,25 @@ def test_host_mirror_pairs_class(cli, tmp_path, oracle):
     T, mse = oracle.get_transform(p, x, d, order)
     assert out["size"] == n_po and out["tau"] == tau
     assert np.allclose(np.array(out["T"]), T, atol=1e-10) and abs(out["mse"] - mse) <= 1e-12 * mse
+
+
+@pytest.mark.gpu
+def test_reference_unit_test_runs_on_the_drop_in():
+    """Drop-in proof: the reference's own unit test of this path, test/unit/icp.cpp (icp_test2: golden-section align of the
+    sine-wave fixture through envire::icp::TrimmedKD; ransac_test: envire::icp::Pairs through icp/ransac.hpp), compiled
+    UNMODIFIED by oracle/Makefile against icp/icp_gpu.hpp with TrimmedKD = TrimmedGPU (oracle/_ref/ref_unit_icp).  The test
+    cases hold no assertions; ICP_B200_TRACE=1 makes the drop-in print each align's outcome, which must be what the
+    reference's own Trimmed<> produces on the same fixture (tests/golden/golden.json, generated by oracle/_ref)."""
+    import json, os, re, subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_unit_icp")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_unit_icp was not built (needs /root/reference: make -C oracle dropin)")
+    pr = subprocess.run([exe], env=dict(os.environ, ICP_B200_TRACE="1"), capture_output=True, text=True, timeout=300)
+    assert pr.returncode == 0, pr.stderr
+    assert "icp_test2: ok" in pr.stderr and "ransac_test: ok" in pr.stderr
+    m = re.search(r"align: iter (\d+) pairs (\d+) overlap (\S+) mse (\S+)", pr.stderr)
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))["cases"]["icp_test2_sine_golden_section"]
+    assert int(m.group(1)) == g["iter"] and int(m.group(2)) == g["pairs"]
+    assert abs(float(m.group(3)) - g["overlap"]) < 1e-12 and abs(float(m.group(4)) - g["mse"]) <= 1e-9 * g["mse"]
+    assert os.path.exists("/tmp/test/scene.yml")  # the test serializes its environment at the end

@@ -13,7 +13,7 @@ PK = os.path.join(ROOT, "slam-envire_b200")
 
 
 def _build(src, exe, link=True):
-    deps = [src, os.path.join(PK, "icp", "icp_gpu.hpp"), os.path.join(PK, "icp", "icpLocalization.hpp"),
+    deps = [src, os.path.join(PK, "icp", "icp_gpu.hpp"), os.path.join(PK, "io", "scene.hpp"),
             os.path.join(PK, "io", "ply.hpp"), os.path.join(PK, "compat", "Eigen", "mini_eigen.hpp")]
     if link:
         deps.append(os.path.join(PK, "libicp_b200.so"))
@@ -111,18 +111,68 @@ def test_env_slam6d_driver_growing_model(tmp_path, synth):
     assert max(err_ref) < 0.15
 
 
+REF_LOC = os.path.join(ROOT, "oracle", "_ref", "ref_localization_cli")
+
+
+def test_scene_reader_reads_the_reference_scene(tmp_path):
+    """f3: the scene.yml the reference ships (test/scene.yml: two frame nodes, ids without the leading '/', transforms
+    spread over four lines) read by io/scene.hpp; then a scene in the reference's emitter style with links and a PLY in
+    its layout (src/tools/PlyFile.cpp:173-246); then writer -> reader."""
+    exe = _build(os.path.join(ROOT, "tests", "cpp", "scene_cli.cpp"), os.path.join(ROOT, "tests", "cpp", "scene_cli"), link=False)
+    ref_scene = "/root/reference/test"
+    if os.path.exists(os.path.join(ref_scene, "scene.yml")):
+        out = json.loads(subprocess.check_output([exe, ref_scene]).decode())
+        assert "error" not in out, out
+        assert [f["id"] for f in out["frames"]] == ["/1", "/2"] and out["clouds"] == []
+        T1 = np.array(out["frames"][0]["transform"]).reshape(4, 4)
+        assert np.array_equal(T1, np.array([[1, 0, 0, 0], [0, 1, 0, 2.5], [0, 0, 1, 0], [0, 0, 0, 1.0]]))
+        assert np.array_equal(np.array(out["frames"][1]["transform"]).reshape(4, 4), np.eye(4))
+    # a scene as FileSerialization writes it: objects (a root, a posed frame node below it, a cloud in that frame), links
+    d = tmp_path / "scene"
+    d.mkdir()
+    T = np.eye(4)
+    T[:3, :3] = [[0, -1, 0], [1, 0, 0], [0, 0, 1]]
+    T[:3, 3] = [1.5, -2.0, 0.25]
+    rows = ", \n               ".join(", ".join(repr(float(v)) for v in r) for r in T)
+    (d / "scene.yml").write_text(
+        "objects:\n - class: 'envire::FrameNode'\n   id: /0\n   label: ''\n   transform: [1, 0, 0, 0, \n               0, 1, 0, 0, \n"
+        "               0, 0, 1, 0, \n               0, 0, 0, 1]\n"
+        " - class: 'envire::FrameNode'\n   id: /1\n   label: ''\n   transform: [%s]\n"
+        " - class: 'envire::Pointcloud'\n   id: /2\n   label: 'scan'\n   sensor_origin: [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1]\n"
+        "links:\n - type: frameNodeTree\n   child: /1\n   parent: /0\n - type: cartesianMapGraph\n   map: /2\n   node: /1\n" % rows)
+    synth = __import__("importlib").import_module("slam-envire_b200.synth")
+    pts = np.random.default_rng(5).normal(0, 3, (1234, 3))
+    synth.write_ply(str(d / "envire::Pointcloud_2.ply"), pts, normals=np.tile([0.0, 0.0, 1.0], (1234, 1)))
+    d2 = tmp_path / "rewritten"
+    d2.mkdir()
+    for args in ([str(d)], [str(d), str(d2)]):
+        out = json.loads(subprocess.check_output([exe] + args).decode())
+        assert "error" not in out, out
+        assert out["root"] == "/0" and [f["id"] for f in out["frames"]] == ["/0", "/1"] and out["frames"][1]["parent"] == "/0"
+        assert np.array_equal(np.array(out["frames"][1]["transform"]).reshape(4, 4), T)
+        assert np.array_equal(np.array(out["frames"][1]["to_root"]).reshape(4, 4), T)
+        (c,) = out["clouds"]
+        assert c["id"] == "/2" and c["frame"] == "/1" and c["n"] == 1234 and c["normals"]
+        assert np.allclose(c["sum"], pts.sum(0), rtol=0, atol=1e-9)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("cov_mode,density", [(0, 1.0), (1, 1.0), (2, 0.5)])
-def test_icp_localization_do_scan_match(tmp_path, oracle, cov_mode, density):
-    """ICPLocalization over TrimmedGPU: scan-line accumulation, doScanMatch result and covariance heuristics
-    (icp/icpLocalization.cpp:188-252) against the oracle run on the very same accumulated cloud."""
-    exe = _build(os.path.join(ROOT, "tests", "cpp", "icp_localization_cli.cpp"),
-                 os.path.join(ROOT, "tests", "cpp", "icp_localization_cli"))
+def test_reference_icp_localization_on_the_drop_in(tmp_path, oracle, cov_mode, density):
+    """f1 / drop-in proof: the REFERENCE's own icp/icpLocalization.cpp + .hpp, compiled unmodified by oracle/Makefile with
+    envire::icp::TrimmedKD = TrimmedGPU (oracle/_ref/ref_localization_cli), runs loadEnvironment (scene directory ->
+    addToModel), scan-line accumulation and doScanMatch on the GPU; result and covariance heuristics
+    (icp/icpLocalization.cpp:114-130,188-252) against the oracle run on the very same accumulated cloud."""
+    exe = REF_LOC
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_localization_cli was not built (needs /root/reference: make -C oracle dropin)")
+    (tmp_path / "scene").mkdir()
     rng = np.random.default_rng(1)
     model = np.concatenate([rng.uniform(-15, 15, (60000, 2)), np.zeros((60000, 1))], 1)  # flat ground, z = 0
     mp, cp = str(tmp_path / "m.bin"), str(tmp_path / "cloud.bin")
     model.tofile(mp)
-    txt = subprocess.check_output([exe, mp, str(cov_mode), str(density), cp]).decode()
+    txt = subprocess.check_output([exe, mp, str(cov_mode), str(density), cp, str(tmp_path / "scene")]).decode()
+    txt = txt[txt.index("{"):]  # the reference's loadEnvironment prints progress lines first
     out = json.loads(txt.replace(" inf", " Infinity"))  # printf prints inf for the NO_COV covariances
     assert "error" not in out, out
     cloud = np.fromfile(cp).reshape(-1, 3)
