@@ -231,7 +231,7 @@ class Icp:
         if n.value:
             self._ck(self._L.icpb_pairs_distance(self._h, out.ctypes.data_as(C.POINTER(C.c_double)), n.value,
                                                  C.byref(n)))
-        return out
+        return out[:n.value]  # after a sharded align: this rank's kept distances (fewer than the global count)
 
     def debug_pairs(self):
         n = C.c_size_t()

@@ -330,8 +330,8 @@ int icpb_create(icpb_ctx **out, int device_id)
     CK(cudaMallocHost((void **)&ctx->h_flags, FLAG_RING * sizeof(int)));
     CK(cudaMalloc((void **)&ctx->d_ghist, (SEL_MAX_BINS + 64) * sizeof(uint32_t)));
     CK(cudaMemset(ctx->d_ghist, 0, (SEL_MAX_BINS + 64) * sizeof(uint32_t)));
-    CK(cudaMalloc((void **)&ctx->d_lhist, (LIN_BINS * LIN_STRIDE + 64) * sizeof(uint32_t)));
-    CK(cudaMemset(ctx->d_lhist, 0, (LIN_BINS * LIN_STRIDE + 64) * sizeof(uint32_t)));
+    CK(cudaMalloc((void **)&ctx->d_lhist, (LIN_BINS * LIN_STRIDE + 64 + LIN_BINS) * sizeof(uint32_t)));
+    CK(cudaMemset(ctx->d_lhist, 0, (LIN_BINS * LIN_STRIDE + 64 + LIN_BINS) * sizeof(uint32_t)));
     CK(cudaMalloc((void **)&ctx->d_counter, 8 * sizeof(unsigned long long)));
     CK(cudaMemset(ctx->d_counter, 0, 8 * sizeof(unsigned long long)));
     CK(cudaMalloc((void **)&ctx->d_gather, 64 * sizeof(unsigned long long)));
@@ -1044,8 +1044,10 @@ static int launch_trim(icpb_ctx *ctx, uint32_t n, bool linear = false)
     if (linear) { // the search kernel has binned the distances over [0, d_box]: one launch
         CK(ctx->cand_key.ensure(std::max<size_t>(n, 1)));
         CK(ctx->cand_idx.ensure(std::max<size_t>(n, 1)));
-        trim_linear_kernel<<<blocks, SEL_THREADS, 0, s>>>(ctx->nn_d.p, ctx->src_perm.p, n, ctx->d_state, ctx->d_lhist,
-                                                          ctx->cand_key.p, ctx->cand_idx.p, (unsigned int *)(ctx->d_counter + 2));
+        trim_linear_kernel<<<std::min(blocks, 296u), SEL_THREADS, 0, s>>>(ctx->nn_d.p, ctx->src_perm.p, n, ctx->d_state, ctx->d_lhist,
+                                                                          ctx->cand_key.p, ctx->cand_idx.p,
+                                                                          (unsigned int *)(ctx->d_counter + 2), ctx->p2p,
+                                                                          ctx->xscratch.p, ctx->d_lhist + LIN_BINS * LIN_STRIDE + 64);
         CKL();
         ctx->launches += 1;
         return ICPB_OK;
@@ -1149,9 +1151,9 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
     // lazy search needs the skip state (winner + bound per query); the edge/normal filter decides pairs per winner
     const double lazy_margin = (tune.skip && ctx->opt_lazy != 0.0 && !ean.on) ? std::max(-0.9, ctx->opt_lazy_margin) : -1.0;
     const unsigned search_blocks = grid_for(std::max<uint32_t>(n, 1), SEARCH_THREADS);
-    // loop bodies after the first trim in ONE launch on the histogram the search kernel fills (single GPU; the
-    // multi-GPU transports keep the radix passes with their exchanges)
-    const bool linear_ok = ctx->n_ranks == 1 && ctx->opt_linear_trim != 0.0;
+    // loop bodies after the first trim in ONE launch on the histogram the search kernel fills (one GPU, or several over
+    // peer memory: two exchanges inside that launch; the NCCL transport keeps the radix passes)
+    const bool linear_ok = (ctx->n_ranks == 1 || ctx->use_p2p) && ctx->opt_linear_trim != 0.0;
     auto enqueue_iteration = [&](bool linear) -> int {
         uint32_t *lh = linear ? ctx->d_lhist : nullptr;
         if (ean.on)

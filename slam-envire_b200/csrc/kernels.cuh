@@ -529,8 +529,9 @@ __global__ void __launch_bounds__(SEARCH_THREADS)
 // of a peer, because it needs that peer's contribution to finish).
 // ---------------------------------------------------------------------------
 constexpr int P2P_MAX_RANKS = 8;
-constexpr int P2P_ROW_WORDS = 2112; // 2048 histogram bins + 64 spare words (found count, ...)
-constexpr int P2P_CAND_CAP = (P2P_ROW_WORDS - 1) / 2; // candidate keys (u64) one row carries next to their count
+constexpr int P2P_ROW_WORDS = 12352; // a histogram (2048 bins + found count) or the candidates of the trim's bin: (key lo, key hi, pair index) each
+constexpr int P2P_LIN_CAP = (P2P_ROW_WORDS - 4) / 3; // candidates one row carries in trim_linear_kernel
+constexpr int P2P_CAND_CAP = 1055; // candidate keys (u64) one row carries next to their count (radix path)
 constexpr size_t P2P_DATA_WORDS = 2ull * P2P_MAX_RANKS * P2P_ROW_WORDS;
 constexpr size_t P2P_BUFFER_WORDS = P2P_DATA_WORDS + 2 * P2P_MAX_RANKS + 64;
 struct P2PView {
@@ -955,6 +956,197 @@ __global__ void __launch_bounds__(SEL_THREADS)
     }
 }
 
+// Exact selection across ranks (last block of trim_linear_kernel, source sharded over several GPUs): the s_krem-th
+// smallest of ALL ranks' pairs of the chosen bin in the order (distance, rank, pair index) -- "lower ranks first, then
+// local position", the global pair order of a contiguous sharding.  Exchange #2 of the loop body carries every rank's
+// candidates (key lo, key hi, pair index) to every rank, so all of them finish on the union with identical arithmetic:
+// sub-bin split + brute-force ranking when the sub-bin holds a handful, else a bit-by-bit search over the 98-bit
+// combined key.  If some rank holds more candidates than a row carries, the bit-by-bit search runs distributed, one
+// one-word exchange per bit (masses of equal distances only).
+__device__ __forceinline__ bool lin_key_matches(unsigned long long hi, unsigned long long lo, unsigned long long phi,
+                                                unsigned long long plo, int pass)
+{
+    // passes 0..62 decide bits 62..0 of the distance, passes 63..97 bits 34..0 of (rank << 32 | pair index)
+    if (pass < 63) {
+        const int b = 62 - pass;
+        return b == 62 ? true : (hi >> (b + 1)) == (phi >> (b + 1));
+    }
+    const int b = 97 - pass;
+    return hi == phi && (b == 34 ? true : (lo >> (b + 1)) == (plo >> (b + 1)));
+}
+__device__ __forceinline__ unsigned lin_key_bit(unsigned long long hi, unsigned long long lo, int pass)
+{
+    return pass < 63 ? (unsigned)(hi >> (62 - pass)) & 1u : (unsigned)(lo >> (97 - pass)) & 1u;
+}
+
+__device__ void trim_linear_finish_multi(const double *__restrict__ nn_d, const uint32_t *__restrict__ perm, IcpState *st,
+                                         const unsigned long long *cand_key, const uint32_t *cand_idx, unsigned cnt, unsigned bin,
+                                         unsigned long long krem, const P2PView &p2p, uint32_t *xb, uint32_t *fhist,
+                                         uint32_t *scan_smem, unsigned long long *f_key, uint32_t *f_perm)
+{
+    __shared__ unsigned m_cnt, m_sub, m_allfit, m_zero;
+    __shared__ unsigned long long m_krem, m_phi, m_plo;
+    __shared__ uint32_t f_rank[LIN_FINAL_CAP];
+    const double scale = lin_scale(st->d_box);
+    const bool fits = cnt <= (unsigned)P2P_LIN_CAP;
+    if (threadIdx.x == 0) xb[0] = cnt;
+    if (fits)
+        for (unsigned j = threadIdx.x; j < cnt; j += blockDim.x) {
+            const unsigned long long key = __ldcg(cand_key + j);
+            xb[1 + 3 * j] = (uint32_t)key;
+            xb[2 + 3 * j] = (uint32_t)(key >> 32);
+            xb[3 + 3 * j] = perm[__ldcg(cand_idx + j)];
+        }
+    __threadfence();
+    __syncthreads();
+    const uint32_t *crow = p2p_exchange(p2p, st, xb, fits ? 1 + 3 * (int)cnt : 1);
+    if (threadIdx.x == 0) {
+        unsigned ok = 1;
+        for (int q = 0; q < p2p.world; ++q)
+            if (__ldcv(crow + (size_t)q * P2P_ROW_WORDS) > (uint32_t)P2P_LIN_CAP) ok = 0;
+        m_allfit = ok;
+        m_cnt = 0u;
+        m_sub = ICPB_NONE;
+    }
+    __syncthreads();
+    unsigned long long w_key = 0, w_lo = 0; // the selected pair: distance bits, (rank << 32 | pair index)
+    bool have = false;
+    if (m_allfit) {
+        // sub-bin split over the union
+        for (int q = 0; q < p2p.world; ++q) {
+            const uint32_t *r = crow + (size_t)q * P2P_ROW_WORDS;
+            const unsigned cq = __ldcv(r);
+            for (unsigned j = threadIdx.x; j < cq; j += blockDim.x) {
+                const unsigned long long key = (unsigned long long)__ldcv(r + 1 + 3 * j) | ((unsigned long long)__ldcv(r + 2 + 3 * j) << 32);
+                atomicAdd(&fhist[lin_sub_bin(__longlong_as_double((long long)key), scale, bin)], 1u);
+            }
+        }
+        __syncthreads();
+        uint32_t c2[8], local2 = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            c2[j] = fhist[threadIdx.x * 8 + j];
+            local2 += c2[j];
+        }
+        uint32_t total2;
+        const uint32_t before2 = block_exclusive_scan(local2, scan_smem, total2);
+        {
+            unsigned long long run = before2;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (run < krem && krem <= run + c2[j]) {
+                    m_sub = threadIdx.x * 8 + j;
+                    m_krem = krem - run;
+                }
+                run += c2[j];
+            }
+        }
+        __syncthreads();
+        for (int b = threadIdx.x; b < SEL_MAX_BINS; b += SEL_THREADS) fhist[b] = 0u;
+        const unsigned sub = m_sub;
+        for (int q = 0; q < p2p.world && sub != ICPB_NONE; ++q) {
+            const uint32_t *r = crow + (size_t)q * P2P_ROW_WORDS;
+            const unsigned cq = __ldcv(r);
+            for (unsigned j = threadIdx.x; j < cq; j += blockDim.x) {
+                const unsigned long long key = (unsigned long long)__ldcv(r + 1 + 3 * j) | ((unsigned long long)__ldcv(r + 2 + 3 * j) << 32);
+                if (lin_sub_bin(__longlong_as_double((long long)key), scale, bin) != sub) continue;
+                const unsigned at = atomicAdd(&m_cnt, 1u);
+                if (at < LIN_FINAL_CAP) {
+                    f_key[at] = key;
+                    f_rank[at] = (uint32_t)q;
+                    f_perm[at] = __ldcv(r + 3 + 3 * j);
+                }
+            }
+        }
+        __syncthreads();
+        const unsigned m = m_cnt;
+        if (sub != ICPB_NONE && m <= LIN_FINAL_CAP) {
+            if (threadIdx.x == 0) m_zero = 0u;
+            __syncthreads();
+            const unsigned long long want = m_krem - 1ull;
+            for (unsigned t = threadIdx.x; t < m; t += blockDim.x) {
+                const unsigned long long kt = f_key[t], lt = ((unsigned long long)f_rank[t] << 32) | f_perm[t];
+                unsigned rank = 0;
+                for (unsigned j = 0; j < m; ++j) {
+                    const unsigned long long lj = ((unsigned long long)f_rank[j] << 32) | f_perm[j];
+                    rank += (f_key[j] < kt || (f_key[j] == kt && lj < lt)) ? 1u : 0u;
+                }
+                if ((unsigned long long)rank == want) {
+                    m_phi = kt;
+                    m_plo = lt;
+                    m_zero = 1u;
+                }
+            }
+            __syncthreads();
+            have = m_zero != 0u;
+            w_key = m_phi;
+            w_lo = m_plo;
+        }
+    }
+    if (!have) {
+        // bit-by-bit search for the krem-th smallest combined key: over the union when every rank's candidates arrived,
+        // else over the local candidates with the counts summed across the ranks (one exchange per bit)
+        const bool uni = m_allfit != 0u;
+        if (threadIdx.x == 0) m_phi = 0ull, m_plo = 0ull, m_krem = krem;
+        __syncthreads();
+        for (int pass = 0; pass < 98; ++pass) {
+            if (threadIdx.x == 0) m_zero = 0u;
+            __syncthreads();
+            const unsigned long long phi = m_phi, plo = m_plo;
+            unsigned zeros = 0;
+            if (uni) {
+                for (int q = 0; q < p2p.world; ++q) {
+                    const uint32_t *r = crow + (size_t)q * P2P_ROW_WORDS;
+                    const unsigned cq = __ldcv(r);
+                    for (unsigned j = threadIdx.x; j < cq; j += blockDim.x) {
+                        const unsigned long long hi = (unsigned long long)__ldcv(r + 1 + 3 * j) | ((unsigned long long)__ldcv(r + 2 + 3 * j) << 32);
+                        const unsigned long long lo = ((unsigned long long)q << 32) | __ldcv(r + 3 + 3 * j);
+                        if (lin_key_matches(hi, lo, phi, plo, pass) && lin_key_bit(hi, lo, pass) == 0u) ++zeros;
+                    }
+                }
+            } else {
+                for (unsigned j = threadIdx.x; j < cnt; j += blockDim.x) {
+                    const unsigned long long hi = __ldcg(cand_key + j);
+                    const unsigned long long lo = ((unsigned long long)p2p.rank << 32) | perm[__ldcg(cand_idx + j)];
+                    if (lin_key_matches(hi, lo, phi, plo, pass) && lin_key_bit(hi, lo, pass) == 0u) ++zeros;
+                }
+            }
+            zeros = __reduce_add_sync(0xFFFFFFFFu, zeros);
+            if ((threadIdx.x & 31) == 0 && zeros) atomicAdd(&m_zero, zeros);
+            __syncthreads();
+            unsigned long long z = m_zero;
+            if (!uni) {
+                if (threadIdx.x == 0) xb[0] = m_zero;
+                __threadfence();
+                __syncthreads();
+                const uint32_t *rr = p2p_exchange(p2p, st, xb, 1);
+                z = 0;
+                for (int q = 0; q < p2p.world; ++q) z += __ldcv(rr + (size_t)q * P2P_ROW_WORDS);
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) {
+                if (m_krem > z) { // the wanted key has this bit set
+                    m_krem -= z;
+                    if (pass < 63) m_phi |= 1ull << (62 - pass);
+                    else m_plo |= 1ull << (97 - pass);
+                }
+            }
+            __syncthreads();
+        }
+        w_key = m_phi;
+        w_lo = m_plo;
+    }
+    if (threadIdx.x == 0) {
+        const int q_w = (int)(w_lo >> 32);
+        st->tau = __longlong_as_double((long long)w_key);
+        st->p_cut = p2p.rank < q_w ? 0x100000000ll : (p2p.rank == q_w ? (long long)(w_lo & 0xFFFFFFFFull) : -1ll);
+        st->need_tie = 0;
+        st->sel_krem = 1;
+    }
+    for (int b = threadIdx.x; b < SEL_MAX_BINS; b += SEL_THREADS) fhist[b] = 0u;
+    __syncthreads();
+}
+
 // ---------------------------------------------------------------------------
 // K4, loop bodies after the first: every pair distance lies in [0, d_box] with d_box = 2 * (previous tau) finite, so
 // the search kernel bins the distances of the pairs it finds LINEARLY over that interval in its epilogue (2048 bins,
@@ -968,7 +1160,8 @@ __global__ void __launch_bounds__(SEL_THREADS)
 __global__ void __launch_bounds__(SEL_THREADS)
     trim_linear_kernel(const double *__restrict__ nn_d, const uint32_t *__restrict__ perm, uint32_t n, IcpState *st,
                        uint32_t *__restrict__ lhist, unsigned long long *__restrict__ cand_key,
-                       uint32_t *__restrict__ cand_idx, unsigned int *__restrict__ cand_count)
+                       uint32_t *__restrict__ cand_idx, unsigned int *__restrict__ cand_count, const P2PView p2p,
+                       uint32_t *xscratch /* P2P_ROW_WORDS words */, uint32_t *lsum /* LIN_BINS words: the histogram of all ranks */)
 {
     if (st->done) return;
     __shared__ uint32_t fhist[SEL_MAX_BINS];
@@ -977,13 +1170,58 @@ __global__ void __launch_bounds__(SEL_THREADS)
     __shared__ unsigned s_bin;
     __shared__ unsigned long long s_krem;
     static_assert(LIN_BINS == SEL_THREADS * 8, "eight bins per thread");
-    const unsigned long long k = st->n_po < st->found ? st->n_po : st->found; // min(n_po, found)
+    const bool multi = p2p.world > 1;
+    const uint32_t *hist = lhist;
+    int hstride = LIN_STRIDE;
+    if (multi) {
+        // Several ranks (source sharded): exchange #1 of the loop body.  Block 0 sends this rank's histogram and pair count
+        // to every peer over NVLink peer memory, sums what it receives and publishes the sums; the other blocks (all
+        // co-resident: the grid is at most two blocks per SM) wait for that flag.  lin_epoch is advanced by the last
+        // block at the very end of the kernel, so every block reads the same value here.
+        const unsigned target = *((volatile unsigned int *)&st->lin_epoch) + 1u;
+        if (blockIdx.x == 0) {
+            for (int b = threadIdx.x; b < LIN_BINS; b += SEL_THREADS) xscratch[b] = __ldcg(lhist + b * LIN_STRIDE);
+            if (threadIdx.x == 0) xscratch[LIN_BINS] = (uint32_t)st->found;
+            __threadfence();
+            __syncthreads();
+            const uint32_t *rows = p2p_exchange(p2p, st, xscratch, LIN_BINS + 1);
+            for (int b = threadIdx.x; b < LIN_BINS; b += SEL_THREADS) {
+                uint32_t v = 0;
+                for (int q = 0; q < p2p.world; ++q) v += __ldcv(rows + (size_t)q * P2P_ROW_WORDS + b);
+                lsum[b] = v;
+            }
+            if (threadIdx.x == 0) {
+                unsigned long long f = 0;
+                for (int q = 0; q < p2p.world; ++q) f += __ldcv(rows + (size_t)q * P2P_ROW_WORDS + LIN_BINS);
+                st->found = f;
+            }
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) atomicExch(&st->lin_ready, target);
+        } else {
+            if (threadIdx.x == 0) {
+                const long long t0 = clock64();
+                while (*((volatile unsigned int *)&st->lin_ready) != target) {
+                    if (clock64() - t0 > 24000000000ll) { // ~12 s: block 0 never got its peers' rows
+                        st->comm_error = 1u;
+                        break;
+                    }
+                }
+            }
+            __syncthreads();
+            __threadfence();
+        }
+        hist = lsum;
+        hstride = 1;
+    }
+    const unsigned long long found_all = *((volatile unsigned long long *)&st->found);
+    const unsigned long long k = st->n_po < found_all ? st->n_po : found_all; // min(n_po, found)
     if (threadIdx.x == 0) s_bin = ICPB_NONE;
     // which bin holds the k-th smallest distance (every block finds the same one)
     uint32_t c[8], local = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        c[j] = __ldcg(lhist + (threadIdx.x * 8 + j) * LIN_STRIDE);
+        c[j] = __ldcg(hist + (threadIdx.x * 8 + j) * hstride);
         local += c[j];
     }
     uint32_t total;
@@ -1046,7 +1284,10 @@ __global__ void __launch_bounds__(SEL_THREADS)
     __shared__ unsigned f_cnt, f_sub;
     __shared__ unsigned long long f_krem;
     bool done_fast = false;
-    if (bin != ICPB_NONE) {
+    if (multi && bin != ICPB_NONE) {
+        done_fast = true;
+        trim_linear_finish_multi(nn_d, perm, st, cand_key, cand_idx, cnt, bin, s_krem, p2p, xscratch, fhist, scan_smem, f_key, f_perm);
+    } else if (bin != ICPB_NONE) {
         const double scale = lin_scale(st->d_box);
         const unsigned long long krem = s_krem;
         if (threadIdx.x == 0) f_cnt = 0u, f_sub = ICPB_NONE;
@@ -1142,6 +1383,7 @@ __global__ void __launch_bounds__(SEL_THREADS)
     if (threadIdx.x == 0) {
         *cand_count = 0;
         st->tickets[7] = 0;
+        if (multi) st->lin_epoch = st->lin_epoch + 1u;
     }
 }
 

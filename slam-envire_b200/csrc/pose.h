@@ -57,6 +57,7 @@ struct IcpState {
     unsigned int tickets[16];
     unsigned int q_count[2]; // search queue of this loop body: fast entries (from the front), walk entries (from the back)
     unsigned int q_cursor;   // next queue entry to hand out
+    unsigned int lin_epoch, lin_ready; // multi-GPU one-launch trim: the summed histogram of body #lin_epoch+1 is published
     unsigned int comm_seq;   // collectives completed on the peer-memory path (same on every rank)
     unsigned int comm_error; // a peer did not show up within the spin budget
 };

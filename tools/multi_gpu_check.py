@@ -15,14 +15,15 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ok = True
 cases = [("cfg1", 0.2, 1.0, {}), ("cfg2", 0.05, 1.0, dict(max_iter=15)), ("cfg1", 0.1, 0.37, dict(max_iter=10, overlap=0.6)),
-         ("ties", 24, 1.0, {}), ("ties", 72, 1.0, {})]
+         ("ties", 24, 1.0, {}), ("ties", 72, 1.0, {}), ("ties", 150, 1.0, {})]
 mode = os.environ.get("ICPB_COMM", "p2p")
 icp = pkg.Icp(local)
 sharding.init_comm(icp, dist, torch.device("cuda", local), mode=mode)
 single = pkg.Icp(local)
 for name, scale, density, over in cases:
-    if name == "ties":  # lattice data: massive equidistant ties at the threshold, split across ranks; the larger lattice
-        # leaves more candidates per rank than one exchange row carries (the digit-by-digit fallback of the trim)
+    if name == "ties":  # lattice data: massive equidistant ties at the threshold, split across ranks: the trim's bit-by-bit
+        # search over the union of the ranks' candidates; the largest lattice leaves more candidates per rank than one
+        # exchange row carries (the distributed bit-by-bit search, one exchange per bit)
         g = np.arange(0, scale, dtype=np.float64)
         m = np.stack(np.meshgrid(g, g, indexing="ij"), -1).reshape(-1, 2)
         m = np.concatenate([m, np.zeros((len(m), 1))], 1)
@@ -42,6 +43,22 @@ for name, scale, density, over in cases:
             and abs(r.mse - r1.mse) <= 1e-9 * abs(r1.mse) + 1e-20)
     tr, tr1 = icp.trace(), single.trace()
     same = same and len(tr) == len(tr1) and all(a["kept"] == b["kept"] and a["found"] == b["found"] for a, b in zip(tr, tr1))
+    # getPairsDistance after a sharded align: every rank returns ITS kept distances (ascending); together they are the
+    # single-GPU list
+    pd = torch.from_numpy(np.ascontiguousarray(icp.pairs_distance())).cuda()
+    sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([len(pd)], dtype=torch.int64, device="cuda"))
+    mx = max(int(x.item()) for x in sizes)
+    padded = torch.full((max(mx, 1),), float("inf"), dtype=torch.float64, device="cuda")
+    padded[:len(pd)] = pd
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded)
+    allpd = np.sort(np.concatenate([p.cpu().numpy()[:int(n.item())] for p, n in zip(parts, sizes)]))
+    pd1 = single.pairs_distance()
+    same_pd = len(allpd) == len(pd1) == r1.pairs and np.allclose(allpd, pd1, rtol=1e-9, atol=1e-12) and bool(np.all(np.diff(pd.cpu().numpy()) >= 0))
+    if not same_pd and rank == 0:
+        print("  pairs_distance differs: gathered", len(allpd), "single", len(pd1), "pairs", r1.pairs)
+    same = same and same_pd
     ok = ok and same
     if rank == 0:
         print(mode, name, "world", world, "iter", r.iter, r1.iter, "pairs", r.pairs, r1.pairs, "mse", r.mse, r1.mse,
