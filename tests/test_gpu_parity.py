@@ -3,10 +3,12 @@
 Bars (BASELINE.json north_star): correspondence indices bit-exact except equidistant ties, distances
 bit-exact, final transform within 1e-5 rad / 1e-6 of the scene extent, final MSE within 1e-5 relative.
 """
+import os
+
 import numpy as np
 import pytest
 
-from conftest import assert_transform_close
+from conftest import ROOT, assert_transform_close
 
 pytestmark = pytest.mark.gpu
 
@@ -320,6 +322,51 @@ def test_full_size_properties_1m(icp, synth):
     assert_transform_close(r.matrix(), T, 100.0, rot_tol=1e-5, trans_tol_rel=1e-5)
     pd = icp.pairs_distance()
     assert len(pd) == 800000 and np.all(np.diff(pd) >= 0) and pd[-1] * 2.0 == r.d_box
+
+
+def test_cfg2_full_size_against_the_oracle(icp, oracle):
+    """BASELINE configs[1] at FULL size, the workload bench.py quotes: the complete align (90 loop bodies) must follow the
+    recorded trajectory (tests/golden/cfg2_poses.npz: found / kept / tau per body, which tests/test_golden.py pins to
+    the oracle at full size on the CPU tier), and the oracle, run here on three loop bodies from the device's own poses,
+    must reproduce found / kept / tau / mse; the last body's kept correspondences are compared index by index."""
+    import bench
+    z = np.load(os.path.join(ROOT, "tests", "golden", "cfg2_poses.npz"))
+    model, src, _ = bench.workload(0)
+    icp.clear_model()
+    icp.add_to_model(model)
+    r = icp.align(src, **bench.ALIGN)
+    tr = icp.trace()
+    assert r.iter == len(z["tau"]) == len(tr) and r.pairs == 800000
+    assert [t["found"] for t in tr] == list(z["found"]) and [t["kept"] for t in tr] == list(z["kept"])
+    assert np.allclose([t["tau"] for t in tr], z["tau"], rtol=1e-9, atol=0)  # same build, same sums: equal in practice
+    ref = bench.CpuReference(model)
+    parity, _, _, its = bench.check_parity(ref, src, tr, 800000, 0, count=3)
+    assert parity["ok"], parity
+    # correspondences of the last loop body: the oracle's nearest neighbours from the device's last pose
+    C_in, d_in = bench.poses_from_trace(tr)
+    p = oracle.transform_points(C_in[-1], src)
+    i_ref, d_ref = ref.M.find_pairs(p, d_box=d_in[-1])
+    i_gpu, d_gpu, kept = icp.debug_pairs()
+    lazy = i_gpu == 0xFFFFFFFE
+    assert kept.sum() == 800000 and not kept[lazy].any()
+    assert np.array_equal(i_gpu[~lazy], i_ref[~lazy])                     # bit-exact indices (no ties in noisy data)
+    assert np.array_equal(d_gpu[~lazy & (i_ref != 0xFFFFFFFF)], d_ref[~lazy & (i_ref != 0xFFFFFFFF)])
+    assert np.all(d_ref[lazy] >= d_gpu[lazy]) and np.all(d_gpu[lazy] > tr[-1]["tau"])
+
+
+def test_cfg3_and_cfg5_shaped_against_the_oracle(icp, oracle, synth):
+    """BASELINE configs[2] (half of the source replaced by a disjoint region, overlap 0.5) at 1M vs 1M for three loop
+    bodies, and a configs[4]-shaped case (source five times the model), against the oracle (OpenMP over queries)."""
+    m = synth.scene(1_000_000, 140.0, 4)
+    s, T = synth.perturbed_copy(m, 1.0, 0.3, 0.01, seed=5, replace_frac=0.5, extent=140.0)
+    r, r_ref, run = _align_both(icp, oracle, m, s, max_iter=3, min_mse=1e-10, min_mse_diff=1e-9, overlap=0.5)
+    _check_align(icp, r, r_ref, run, 140.0)
+    assert r.pairs == 500000
+    m5 = synth.scene(100_000, 60.0, 7)
+    s5 = np.concatenate([synth.perturbed_copy(synth.scene(100_000, 60.0, 60 + k), 1.0, 0.3, 0.01, seed=70 + k)[0] for k in range(5)])
+    r, r_ref, run = _align_both(icp, oracle, m5, s5, max_iter=8, min_mse=1e-10, min_mse_diff=1e-9, overlap=0.8)
+    _check_align(icp, r, r_ref, run, 60.0)
+    assert r.pairs == 400000
 
 
 def test_growing_model_merge_append(pkg, oracle, synth):
