@@ -179,7 +179,7 @@ struct icpb_ctx {
     std::string err;
     // options
     double opt_cell_size = 0.0, opt_target = 12.0, opt_max_cells = 64.0 * 1024 * 1024, opt_run_ahead = 2.0,
-           opt_warm = 1.0, opt_skip = 1.0, opt_skip_reach = 0.25, opt_skip_floor = 0.05, opt_lazy = 1.0, opt_lazy_margin = 0.05, opt_fail_build = 0.0, opt_linear_trim = 1.0, opt_block_levels = 1.0, opt_profile = 0.0, opt_sort = 1.0, opt_margin = 0.0, opt_merge = 1.0, opt_graph = 1.0, opt_trim_bpsm = 2.0, opt_mom_bpsm = 2.0;
+           opt_warm = 1.0, opt_skip = 1.0, opt_skip_reach = 0.25, opt_skip_floor = 0.05, opt_lazy = 1.0, opt_lazy_margin = 0.05, opt_fail_build = 0.0, opt_linear_trim = 1.0, opt_fuse_moments = -1.0, opt_block_levels = 1.0, opt_profile = 0.0, opt_sort = 1.0, opt_margin = 0.0, opt_merge = 1.0, opt_graph = 1.0, opt_trim_bpsm = 2.0, opt_mom_bpsm = 2.0;
     // model
     DevBuf<double> model_raw, model_nrm;
     DevBuf<uint8_t> model_edge;
@@ -216,6 +216,7 @@ struct icpb_ctx {
     IcpState *h_state = nullptr; // pinned
     int *h_flags = nullptr;      // pinned
     uint32_t *d_ghist = nullptr;
+    unsigned tm_blocks = 0; // co-resident blocks of trim_moments_kernel (0: not queried yet)
     uint32_t *d_lhist = nullptr; // linear histogram of the pair distances (search epilogue -> trim_linear_kernel)
     unsigned long long *d_counter = nullptr;
     DevBuf<double> partials;
@@ -224,8 +225,8 @@ struct icpb_ctx {
     int last_executed = 0;
     bool last_valid = false, last_early = false;
     // K7 / debug scratch
-    DevBuf<unsigned long long> kd0, kd1, cand_key;
-    DevBuf<uint32_t> cand_idx, xscratch;
+    DevBuf<unsigned long long> kd0, kd1, cand_key, seg_key; // seg_*: per-warp candidate segments of trim_moments_kernel
+    DevBuf<uint32_t> cand_idx, xscratch, seg_idx, seg_count;
     DevBuf<uint32_t> dbg_idx;
     DevBuf<uint8_t> dbg_kept;
     // timing
@@ -397,6 +398,9 @@ void icpb_destroy(icpb_ctx *ctx)
     ctx->kd0.release();
     ctx->cand_key.release();
     ctx->cand_idx.release();
+    ctx->seg_key.release();
+    ctx->seg_idx.release();
+    ctx->seg_count.release();
     ctx->xscratch.release();
     ctx->kd1.release();
     ctx->dbg_idx.release();
@@ -432,6 +436,7 @@ static double *opt_slot(icpb_ctx *ctx, const char *key)
     if (!strcmp(key, "lazy")) return &ctx->opt_lazy;
     if (!strcmp(key, "lazy_margin")) return &ctx->opt_lazy_margin;
     if (!strcmp(key, "linear_trim")) return &ctx->opt_linear_trim;
+    if (!strcmp(key, "fuse_moments")) return &ctx->opt_fuse_moments;
     if (!strcmp(key, "test_fail_next_build")) return &ctx->opt_fail_build;
     if (!strcmp(key, "profile")) return &ctx->opt_profile;
     if (!strcmp(key, "sort_source")) return &ctx->opt_sort;
@@ -1036,20 +1041,56 @@ __global__ void tie_quota_kernel(IcpState *st, const unsigned long long *gathere
     }
 }
 
-static int launch_trim(icpb_ctx *ctx, uint32_t n, bool linear = false)
+// Blocks of trim_moments_kernel that are resident together (its blocks wait for each other): what the occupancy
+// calculator grants on this device, queried once.
+static unsigned coresident_trim_blocks(icpb_ctx *ctx)
+{
+    if (ctx->tm_blocks == 0) {
+        int per_sm = 0, sms = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trim_moments_kernel, SEL_THREADS, 0) != cudaSuccess) per_sm = 1;
+        ctx->tm_blocks = (unsigned)std::min(TRIM_MAX_BLOCKS, std::max(1, std::min(per_sm, 2) * std::max(sms, 1)));
+    }
+    return ctx->tm_blocks;
+}
+
+// Moments inside the trim launch?  Measured on B200 (tools/graph_vs_stream.py, graph mode): at 100 k source points the
+// fused launch wins (79.9 vs 82.9 us per loop body), at 1 M the separate moments_kernel does (239.2 vs 244.5 us): the
+// kept pairs of the bin and the final reduction are a chain of trips to the L2 in ONE block, which a grid-wide kernel
+// overlaps better once it has enough work.  fuse_moments: 1 / 0 force it, -1 (default) decides by size.
+static bool fuse_moments_on(const icpb_ctx *ctx, uint32_t n)
+{
+    if (ctx->opt_fuse_moments < 0.0) return n <= 300000u;
+    return ctx->opt_fuse_moments != 0.0;
+}
+
+// moments_done (may be null): set when the launch also accumulated the moments and ran the pose step (loop bodies after
+// the first on the fused path) -- no moments_kernel must follow then
+static int launch_trim(icpb_ctx *ctx, uint32_t n, bool linear = false, bool *moments_done = nullptr,
+                       cudaGraphConditionalHandle cond = 0, int use_cond = 0)
 {
     cudaStream_t s = ctx->stream;
     const unsigned blocks = std::max(1u, std::min(grid_for(n, SEL_THREADS * 4), 148u * (unsigned)std::max(1.0, std::min(ctx->opt_trim_bpsm, 32.0))));
     const int fused = (ctx->n_ranks == 1 || ctx->use_p2p) ? 1 : 0;
+    if (moments_done) *moments_done = false;
     if (linear) { // the search kernel has binned the distances over [0, d_box]: one launch
         CK(ctx->cand_key.ensure(std::max<size_t>(n, 1)));
         CK(ctx->cand_idx.ensure(std::max<size_t>(n, 1)));
-        trim_linear_kernel<<<std::min(blocks, 296u), SEL_THREADS, 0, s>>>(ctx->nn_d.p, ctx->src_perm.p, n, ctx->d_state, ctx->d_lhist,
-                                                                          ctx->cand_key.p, ctx->cand_idx.p,
-                                                                          (unsigned int *)(ctx->d_counter + 2), ctx->p2p,
-                                                                          ctx->xscratch.p, ctx->d_lhist + LIN_BINS * LIN_STRIDE + 64);
+        const unsigned lin_blocks = std::min(blocks, coresident_trim_blocks(ctx));
+        const int fuse = (moments_done && fuse_moments_on(ctx, n)) ? 1 : 0;
+        CK(ctx->partials.ensure((size_t)lin_blocks * ICPB_NSUMS));
+        const size_t seg_total = (size_t)lin_blocks * (SEL_THREADS / 32) * trim_seg_cap(n, lin_blocks);
+        CK(ctx->seg_key.ensure(seg_total));
+        CK(ctx->seg_idx.ensure(seg_total));
+        CK(ctx->seg_count.ensure((size_t)TRIM_MAX_BLOCKS * (SEL_THREADS / 32)));
+        trim_moments_kernel<<<lin_blocks, SEL_THREADS, 0, s>>>(ctx->gv, ctx->sx.p, ctx->sy.p, ctx->sz.p, ctx->nn_pos.p, ctx->nn_d.p,
+                                                               ctx->src_perm.p, n, ctx->d_state, ctx->d_lhist, ctx->cand_key.p,
+                                                               ctx->cand_idx.p, ctx->seg_key.p, ctx->seg_idx.p, ctx->seg_count.p, ctx->p2p,
+                                                               ctx->xscratch.p, ctx->d_lhist + LIN_BINS * LIN_STRIDE + 64,
+                                                               ctx->partials.p, ctx->trace.p, ctx->trace_cap, cond, use_cond, fuse);
         CKL();
         ctx->launches += 1;
+        if (moments_done) *moments_done = fuse != 0;
         return ICPB_OK;
     }
     if (fused) {
@@ -1126,7 +1167,7 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
     const size_t max_iter = prm->max_iter;
 
     const unsigned mom_blocks = std::max(1u, std::min(grid_for(n, MOM_THREADS), 148u * (unsigned)std::max(1.0, std::min(ctx->opt_mom_bpsm, 32.0))));
-    CK(ctx->partials.ensure((size_t)mom_blocks * ICPB_NSUMS));
+    CK(ctx->partials.ensure((size_t)std::max(mom_blocks, coresident_trim_blocks(ctx)) * ICPB_NSUMS));
     ctx->trace_cap = (int)std::min<size_t>(std::max<size_t>(max_iter, 1), 65536);
     CK(ctx->trace.ensure((size_t)ctx->trace_cap * ICPB_TRACE_COLS_DEV));
     const bool profile = ctx->opt_profile != 0.0;
@@ -1174,10 +1215,19 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
         // ---- the whole loop as ONE graph launch: init -> WHILE(!done){search, trim, moments+pose} ----
         CK(ctx->cand_key.ensure(std::max<size_t>(n, 1)));
         CK(ctx->cand_idx.ensure(std::max<size_t>(n, 1)));
+        if (linear_ok) {
+            const unsigned tb = std::max(1u, std::min(grid_for(n, SEL_THREADS * 4), 148u * (unsigned)std::max(1.0, std::min(ctx->opt_trim_bpsm, 32.0))));
+            const unsigned lb = std::min(tb, coresident_trim_blocks(ctx));
+            const size_t seg_total = (size_t)lb * (SEL_THREADS / 32) * trim_seg_cap(n, lb);
+            CK(ctx->seg_key.ensure(seg_total));
+            CK(ctx->seg_idx.ensure(seg_total));
+            CK(ctx->seg_count.ensure((size_t)TRIM_MAX_BLOCKS * (SEL_THREADS / 32)));
+        }
         std::vector<unsigned char> key;
         auto add_key = [&](const void *p, size_t bytes) { key.insert(key.end(), (const unsigned char *)p, (const unsigned char *)p + bytes); };
         const void *ptrs[] = {ctx->sx.p, ctx->sy.p, ctx->sz.p, ctx->nn_pos.p, ctx->nn_d.p, ctx->nn_lb.p, ctx->src_perm.p, ctx->partials.p,
-                              ctx->trace.p, ctx->cand_key.p, ctx->cand_idx.p, ctx->d_state, ctx->d_ghist, ctx->d_lhist};
+                              ctx->trace.p, ctx->cand_key.p, ctx->cand_idx.p, ctx->d_state, ctx->d_ghist, ctx->d_lhist,
+                              ctx->seg_key.p, ctx->seg_idx.p, ctx->seg_count.p};
         add_key(&n, sizeof(n));
         add_key(&ctx->gv, sizeof(ctx->gv));
         add_key(ptrs, sizeof(ptrs));
@@ -1189,6 +1239,7 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
         add_key(&linear_ok, sizeof(linear_ok));
         add_key(&mom_blocks, sizeof(mom_blocks));
         add_key(&ctx->opt_trim_bpsm, sizeof(double));
+        add_key(&ctx->opt_fuse_moments, sizeof(double));
         void *init_args[13];
         unsigned long long a_max_iter = max_iter, a_n_po = n_po, a_n = n, a_off = 0;
         double a_mse = prm->min_mse, a_diff = prm->min_mse_diff, a_ov = prm->overlap, a_lazy = lazy_margin;
@@ -1215,8 +1266,9 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
             use_cond = 1;
             auto capture_body = [&](bool linear) -> int {
                 int rc = enqueue_iteration(linear);
-                if (rc == ICPB_OK) rc = launch_trim(ctx, n, linear);
-                if (rc == ICPB_OK) {
+                bool moments_done = false;
+                if (rc == ICPB_OK) rc = launch_trim(ctx, n, linear, &moments_done, cond, use_cond);
+                if (rc == ICPB_OK && !moments_done) {
                     moments_kernel<<<mom_blocks, MOM_THREADS, 0, s>>>(ctx->gv, ctx->sx.p, ctx->sy.p, ctx->sz.p, n, ctx->d_state,
                                                                       ctx->nn_pos.p, ctx->nn_d.p, ctx->src_perm.p,
                                                                       ctx->partials.p, ctx->trace.p, ctx->trace_cap, fused,
@@ -1297,21 +1349,24 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
         cudaEvent_t *ev = timed ? &ctx->events[it * 4] : nullptr;
         if (timed) CK(cudaEventRecord(ev[0], s));
         const bool linear = linear_ok && it > 0; // the first body's d_box is inf
+        bool moments_done = false;
         {
             int rc = enqueue_iteration(linear);
             if (rc != ICPB_OK) return rc;
         }
         if (timed) CK(cudaEventRecord(ev[1], s));
         {
-            int rc = launch_trim(ctx, n, linear);
+            int rc = launch_trim(ctx, n, linear, &moments_done, cond, use_cond);
             if (rc != ICPB_OK) return rc;
         }
         if (timed) CK(cudaEventRecord(ev[2], s));
-        moments_kernel<<<mom_blocks, MOM_THREADS, 0, s>>>(ctx->gv, ctx->sx.p, ctx->sy.p, ctx->sz.p, n, ctx->d_state,
-                                                          ctx->nn_pos.p, ctx->nn_d.p, ctx->src_perm.p, ctx->partials.p,
-                                                          ctx->trace.p, ctx->trace_cap, fused, ctx->p2p, cond, use_cond);
-        CKL();
-        ++ctx->launches;
+        if (!moments_done) {
+            moments_kernel<<<mom_blocks, MOM_THREADS, 0, s>>>(ctx->gv, ctx->sx.p, ctx->sy.p, ctx->sz.p, n, ctx->d_state,
+                                                              ctx->nn_pos.p, ctx->nn_d.p, ctx->src_perm.p, ctx->partials.p,
+                                                              ctx->trace.p, ctx->trace_cap, fused, ctx->p2p, cond, use_cond);
+            CKL();
+            ++ctx->launches;
+        }
         if (!fused) {
             NK(g_nccl.AllReduce(ctx->d_state->sums, ctx->d_state->sums, ICPB_NSUMS, NCCL_FLOAT64, NCCL_SUM, ctx->comm,
                                 s));
@@ -1332,6 +1387,12 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
     CK(cudaStreamSynchronize(s));
 
     const IcpState &hs = *ctx->h_state;
+#ifdef ICPB_PHASE_STAMPS
+    fprintf(stderr, "trim_moments_kernel phases (ns): block 0: hist+bin %lld, pass 1 + partial %lld | last block starts %lld after block 0's start: gather + selection %lld, kept pairs of the bin %lld, rows reduced %lld, pose %lld\n",
+            (long long)(hs.stamps[1] - hs.stamps[0]), (long long)(hs.stamps[2] - hs.stamps[1]), (long long)(hs.stamps[3] - hs.stamps[0]),
+            (long long)(hs.stamps[4] - hs.stamps[3]), (long long)(hs.stamps[6] - hs.stamps[4]), (long long)(hs.stamps[10] - hs.stamps[6]),
+            (long long)(hs.stamps[11] - hs.stamps[10]));
+#endif
     if (hs.comm_error) {
         ctx->err = "peer-memory collective timed out (a rank is missing)";
         return ICPB_ERR_NCCL;
@@ -1367,8 +1428,8 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
         ctx->iter_ms[k * 3 + 2] = c;
     }
     ctx->timing.iterations = use_graph ? (unsigned long long)hs.executed : exec_timed;
-    if (use_graph) // init + the kernels of every body that ran (first body: 5; later ones 3 with the one-launch trim)
-        ctx->launches = launches0 + 1ull + (hs.executed + hs.redone > 0 ? 5ull + (linear_ok ? 3ull : 5ull) * (unsigned long long)(hs.executed + hs.redone - 1) : 0ull);
+    if (use_graph) // init + the kernels of every body that ran (first body: 5; later ones 2 with the fused trim + moments, 3 with the one-launch trim)
+        ctx->launches = launches0 + 1ull + (hs.executed + hs.redone > 0 ? 5ull + (linear_ok ? (fuse_moments_on(ctx, n) ? 2ull : 3ull) : 5ull) * (unsigned long long)(hs.executed + hs.redone - 1) : 0ull);
     ctx->timing.kernels_launched = ctx->launches - launches0;
     return ICPB_OK;
 }

@@ -9,6 +9,7 @@
 //   K7  kept-distance compaction (+ radix sort) for getPairsDistance (icp/icp.hpp:500-504)
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 #include "grid_view.h"
 #include "pose.h"
@@ -1147,38 +1148,256 @@ __device__ void trim_linear_finish_multi(const double *__restrict__ nn_d, const 
     __syncthreads();
 }
 
+__device__ __forceinline__ bool pair_kept(double d, uint32_t i, double tau, long long p_cut)
+{
+    return d < tau || (d == tau && (long long)i <= p_cut);
+}
+
 // ---------------------------------------------------------------------------
-// K4, loop bodies after the first: every pair distance lies in [0, d_box] with d_box = 2 * (previous tau) finite, so
-// the search kernel bins the distances of the pairs it finds LINEARLY over that interval in its epilogue (2048 bins,
-// one warp-aggregated global atomic per distinct bin and warp) and the whole trim is this one launch:
-//   every block  scans the histogram (8 KB) and finds the bin that holds the n_po-th smallest distance,
-//                then collects the pairs of that bin from its share of nn_d (a few hundred to a few thousand of 10^6),
-//   last block   selects exactly among the collected keys (six 11-bit digits of the distance bits in shared memory,
-//                then -- only if fewer equidistant pairs are kept than exist -- three digits of the pair index).
+// K5 (+K6): moments over the kept pairs, deterministic two-stage reduction,
+// closed-form pose step in the last block
+// ---------------------------------------------------------------------------
+constexpr int MOM_THREADS = 256;
+
+__device__ __forceinline__ double shfl_xor_double(double v, int o)
+{
+    return __shfl_xor_sync(0xFFFFFFFFu, v, o);
+}
+
+#ifdef ICPB_PHASE_STAMPS
+__device__ __forceinline__ void phase_stamp(IcpState *st, int slot)
+{
+    if (threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        st->stamps[slot] = t;
+    }
+}
+#define ICPB_STAMP(cond, slot) do { if (cond) phase_stamp(st, slot); } while (0)
+#else
+#define ICPB_STAMP(cond, slot)
+#endif
+// one kept pair: p = the transformed source vertex (C_local2globalnew * v), m = its model point, d = their distance
+__device__ __forceinline__ void moments_add(double (&acc)[ICPB_NSUMS], const double *M, double vx, double vy, double vz,
+                                            const MPoint &m, double d)
+{
+    double px, py, pz;
+    icpb_aff_apply(M, vx, vy, vz, px, py, pz);
+    acc[0] += px;
+    acc[1] += py;
+    acc[2] += pz;
+    acc[3] += m.x;
+    acc[4] += m.y;
+    acc[5] += m.z;
+    acc[6] += px * m.x;
+    acc[7] += px * m.y;
+    acc[8] += px * m.z;
+    acc[9] += py * m.x;
+    acc[10] += py * m.y;
+    acc[11] += py * m.z;
+    acc[12] += pz * m.x;
+    acc[13] += pz * m.y;
+    acc[14] += pz * m.z;
+    acc[15] += d * d; // mu_d += d*d (icp/icp.cpp:60-61)
+    acc[16] += 1.0;
+}
+
+// The moments end in two steps.  moments_block_partial: warp shuffles -> this block's row of `partials`.
+// moments_final (the block that takes the last ticket): reduces the rows in a fixed order (run-to-run deterministic),
+// exchanges the 17 sums with the other ranks over peer memory, runs the pose step (K6) and drives the WHILE node of the
+// graph.  It works on a shared-memory copy of the loop state (one coalesced read, issued together with the loads of the
+// partials, one coalesced write-back): the pose step is a chain of ~60 state accesses by a single thread.
+#ifdef ICPB_PHASE_STAMPS
+constexpr int MOM_STATE_WORDS = (int)(offsetof(IcpState, stamps) / 4);
+#else
+constexpr int MOM_STATE_WORDS = (int)(sizeof(IcpState) / 4);
+#endif
+static_assert(sizeof(IcpState) % 4 == 0 && MOM_STATE_WORDS <= 2 * MOM_THREADS, "state copy: at most two words per thread");
+struct MomShared {
+    double sm[MOM_THREADS / 32][ICPB_NSUMS];
+    double extra[ICPB_NSUMS]; // a row added behind the block partials (trim_moments_kernel: the kept pairs of the bin)
+    IcpState st;
+    int is_last;
+};
+// all threads of the block; the row lands in dst[0..16] (global or shared)
+__device__ __forceinline__ void moments_block_partial(double (&acc)[ICPB_NSUMS], double *dst, MomShared &ms)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < ICPB_NSUMS; ++k) {
+        double v = acc[k];
+        for (int o = 16; o > 0; o >>= 1) v += shfl_xor_double(v, o);
+        if (lane == 0) ms.sm[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < ICPB_NSUMS) {
+        double v = 0.0;
+        for (int w = 0; w < MOM_THREADS / 32; ++w) v += ms.sm[w][threadIdx.x];
+        dst[threadIdx.x] = v;
+    }
+}
+// The block that took the last ticket (all threads), after a fence: requests its copy of the loop state and its share
+// of the partial rows together (one trip to the L2 for both).  Column k by warp (k % 8), lanes stride the rows.
+__device__ __forceinline__ void moments_last_begin(const IcpState *st, const double *__restrict__ partials, unsigned rows,
+                                                   double (&v)[3], MomShared &ms)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(st);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(&ms.st);
+    uint32_t w0 = 0, w1 = 0;
+    if ((int)threadIdx.x < MOM_STATE_WORDS) w0 = __ldcg(src + threadIdx.x);
+    if ((int)threadIdx.x + MOM_THREADS < MOM_STATE_WORDS) w1 = __ldcg(src + threadIdx.x + MOM_THREADS);
+    v[0] = v[1] = v[2] = 0.0;
+    for (unsigned b0 = 0; b0 < rows; b0 += 320u) {
+        double x[3][10];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int k = warp + c * (MOM_THREADS / 32);
+#pragma unroll
+            for (int j = 0; j < 10; ++j) {
+                const unsigned b = b0 + (unsigned)lane + 32u * (unsigned)j;
+                x[c][j] = (k < ICPB_NSUMS && b < rows) ? __ldcg(partials + (size_t)b * ICPB_NSUMS + k) : 0.0;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int j = 0; j < 10; ++j) v[c] += x[c][j];
+    }
+    if ((int)threadIdx.x < MOM_STATE_WORDS) dst[threadIdx.x] = w0;
+    if ((int)threadIdx.x + MOM_THREADS < MOM_STATE_WORDS) dst[threadIdx.x + MOM_THREADS] = w1;
+}
+// ... and ends the loop body on the shared-memory state ms.st: final sums (+ ms.extra), exchange with the other ranks,
+// pose step, loop condition, state written back.  v: from moments_last_begin.
+__device__ void moments_last_finish(IcpState *st, double (&v)[3], bool with_extra, double *__restrict__ trace, int trace_cap,
+                                    int fused_pose, const P2PView &p2p, cudaGraphConditionalHandle cond, int use_cond,
+                                    MomShared &ms)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads(); // ms.sm is free (moments_block_partial), ms.extra and ms.st are written
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int k = warp + c * (MOM_THREADS / 32);
+        double t = v[c];
+        for (int o = 16; o > 0; o >>= 1) t += shfl_xor_double(t, o);
+        if (lane == 0 && k < ICPB_NSUMS) ms.sm[0][k] = with_extra ? t + ms.extra[k] : t;
+    }
+    __syncthreads();
+    ICPB_STAMP(true, 10);
+    if (p2p.world > 1) {
+        // fused all-reduce of the 17 moment sums over peer memory; rows are summed in rank order on every rank
+        const uint32_t *prow = p2p_exchange(p2p, &ms.st, reinterpret_cast<const uint32_t *>(&ms.sm[0][0]), 2 * ICPB_NSUMS);
+        double t = 0.0;
+        if (threadIdx.x < ICPB_NSUMS) {
+            for (int q = 0; q < p2p.world; ++q) {
+                const uint32_t *r = prow + (size_t)q * P2P_ROW_WORDS + 2 * threadIdx.x;
+                const unsigned long long bits = (unsigned long long)__ldcv(r) | ((unsigned long long)__ldcv(r + 1) << 32);
+                t += __longlong_as_double((long long)bits);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < ICPB_NSUMS) ms.sm[0][threadIdx.x] = t;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < ICPB_NSUMS; ++k) ms.st.sums[k] = ms.sm[0][k];
+        ms.st.tickets[15] = 0;
+        if (fused_pose) {
+            const int row = ms.st.executed;
+            icpb_iteration_finish(ms.st, row < trace_cap ? trace + (size_t)row * ICPB_TRACE_COLS_DEV : nullptr);
+        }
+        ICPB_STAMP(true, 11);
+        // CUDA-graph mode: the loop condition of Trimmed::_align drives the WHILE node this kernel lives in
+        if (use_cond) cudaGraphSetConditional(cond, ms.st.done ? 0u : 1u);
+    }
+    __syncthreads();
+    {
+        uint32_t *dst = reinterpret_cast<uint32_t *>(st);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(&ms.st);
+        for (int w = threadIdx.x; w < MOM_STATE_WORDS; w += MOM_THREADS) dst[w] = src[w];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K4 + K5 + K6, loop bodies after the first, ONE launch.  Every pair distance lies in [0, d_box] with d_box = 2 *
+// (previous tau) finite, so the search kernel bins the distances of the pairs it finds LINEARLY over that interval in
+// its epilogue (2048 bins, one warp-aggregated global atomic per distinct bin and warp).  This kernel (grid = the
+// co-resident blocks of the device, so that its blocks may wait for each other):
+//   every block  scans the histogram (8 KB) and finds the bin that holds the n_po-th smallest distance; then passes
+//                over its share of the pairs once: a pair of a LOWER bin is kept whatever the exact tau is -- its
+//                moments are accumulated on the spot (Pairs::getTransform, icp/icp.cpp:55-73) --, the pairs OF the bin
+//                (a few hundred to a few thousand of 10^6) are collected;
+//   the block that arrives last selects exactly among the collected keys (one more linear split into 2048 sub-bins,
+//                brute-force ranking of the handful left; radix digits as the general fall-back) -> tau, p_cut, and
+//                releases the others;
+//   every block  adds those pairs of the bin that are kept (its own elements, in its own fixed order: the sums are
+//                run-to-run deterministic), block partials, ticket;
+//   last block   fixed-order reduction, exchange of the sums (multi-GPU), pose step, loop condition.
+// fuse == 0 stops after the selection (stand-alone trim; moments_kernel follows as a launch of its own).
 // The first loop body (d_box = inf) and the stand-alone icpb_trim keep the radix passes above.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(SEL_THREADS)
-    trim_linear_kernel(const double *__restrict__ nn_d, const uint32_t *__restrict__ perm, uint32_t n, IcpState *st,
-                       uint32_t *__restrict__ lhist, unsigned long long *__restrict__ cand_key,
-                       uint32_t *__restrict__ cand_idx, unsigned int *__restrict__ cand_count, const P2PView p2p,
-                       uint32_t *xscratch /* P2P_ROW_WORDS words */, uint32_t *lsum /* LIN_BINS words: the histogram of all ranks */)
+// candidate segments of trim_moments_kernel: one per warp, large enough for all the pairs a warp visits
+constexpr int TRIM_MAX_BLOCKS = 320;
+constexpr int TRIM_SEG_PER_THREAD = TRIM_MAX_BLOCKS * (SEL_THREADS / 32) / SEL_THREADS; // segments one thread of the selecting block gathers
+__host__ __device__ __forceinline__ uint32_t trim_seg_cap(uint32_t n, unsigned blocks)
 {
-    if (st->done) return;
+    const uint32_t share = (uint32_t)(((unsigned long long)n + blocks - 1) / blocks); // largest share of a block
+    return ((share + 4u * SEL_THREADS - 1u) / (4u * SEL_THREADS)) * 128u;                 // trips * 4 * 32 lanes
+}
+__device__ __forceinline__ bool spin_until(volatile unsigned int *flag, unsigned target, IcpState *st)
+{
+    const long long t0 = clock64();
+    while (*flag != target) {
+        if (clock64() - t0 > 24000000000ll) { // ~12 s: the block that was to publish never did; do not hang the GPU
+            st->comm_error = 1u;
+            return false;
+        }
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(SEL_THREADS, 2)
+    trim_moments_kernel(const GridView g, const double *__restrict__ sx, const double *__restrict__ sy,
+                        const double *__restrict__ sz, const uint32_t *__restrict__ nn_pos,
+                        const double *__restrict__ nn_d, const uint32_t *__restrict__ perm, uint32_t n, IcpState *st,
+                        uint32_t *__restrict__ lhist, unsigned long long *__restrict__ cand_key,
+                        uint32_t *__restrict__ cand_idx, unsigned long long *__restrict__ seg_key,
+                        uint32_t *__restrict__ seg_idx, unsigned int *__restrict__ seg_count, const P2PView p2p,
+                        uint32_t *xscratch /* P2P_ROW_WORDS words */, uint32_t *lsum /* LIN_BINS words: the histogram of all ranks */,
+                        double *__restrict__ partials, double *__restrict__ trace, int trace_cap,
+                        cudaGraphConditionalHandle cond, int use_cond, int fuse)
+{
+    // the scalars this block needs, requested together (each is a round trip to the L2)
+    const int done_in = *((volatile int *)&st->done);
+    const unsigned lin_target = *((volatile unsigned int *)&st->lin_epoch) + 1u;
+    const unsigned long long found_in = *((volatile unsigned long long *)&st->found);
+    const unsigned long long n_po = *((volatile unsigned long long *)&st->n_po);
+    const double d_box = *((volatile double *)&st->d_box);
+    const bool multi = p2p.world > 1;
+    uint32_t c[8];
+    if (!multi) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) c[j] = __ldcg(lhist + (threadIdx.x * 8 + j) * LIN_STRIDE);
+    }
+    const double m_in = threadIdx.x < 12 ? st->M[threadIdx.x] : 0.0;
+    if (done_in) return;
     __shared__ uint32_t fhist[SEL_MAX_BINS];
     __shared__ uint32_t scan_smem[34];
     __shared__ int is_last;
     __shared__ unsigned s_bin;
     __shared__ unsigned long long s_krem;
+    __shared__ MomShared ms;
+    __shared__ double M[12]; // C_local2globalnew: broadcast reads instead of 24 registers per thread
     static_assert(LIN_BINS == SEL_THREADS * 8, "eight bins per thread");
-    const bool multi = p2p.world > 1;
-    const uint32_t *hist = lhist;
-    int hstride = LIN_STRIDE;
+    static_assert(MOM_THREADS == SEL_THREADS, "one block shape for the trim and the moments");
+    ICPB_STAMP(blockIdx.x == 0, 0);
+    if (threadIdx.x < 12) M[threadIdx.x] = m_in;
     if (multi) {
         // Several ranks (source sharded): exchange #1 of the loop body.  Block 0 sends this rank's histogram and pair count
         // to every peer over NVLink peer memory, sums what it receives and publishes the sums; the other blocks (all
-        // co-resident: the grid is at most two blocks per SM) wait for that flag.  lin_epoch is advanced by the last
-        // block at the very end of the kernel, so every block reads the same value here.
-        const unsigned target = *((volatile unsigned int *)&st->lin_epoch) + 1u;
+        // co-resident) wait for that flag.  lin_epoch is advanced by the selecting block, i.e. after every block has
+        // read it (above).
+        const unsigned target = lin_target;
         if (blockIdx.x == 0) {
             for (int b = threadIdx.x; b < LIN_BINS; b += SEL_THREADS) xscratch[b] = __ldcg(lhist + b * LIN_STRIDE);
             if (threadIdx.x == 0) xscratch[LIN_BINS] = (uint32_t)st->found;
@@ -1199,31 +1418,20 @@ __global__ void __launch_bounds__(SEL_THREADS)
             __syncthreads();
             if (threadIdx.x == 0) atomicExch(&st->lin_ready, target);
         } else {
-            if (threadIdx.x == 0) {
-                const long long t0 = clock64();
-                while (*((volatile unsigned int *)&st->lin_ready) != target) {
-                    if (clock64() - t0 > 24000000000ll) { // ~12 s: block 0 never got its peers' rows
-                        st->comm_error = 1u;
-                        break;
-                    }
-                }
-            }
+            if (threadIdx.x == 0) spin_until(&st->lin_ready, target, st);
             __syncthreads();
             __threadfence();
         }
-        hist = lsum;
-        hstride = 1;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) c[j] = __ldcg(lsum + threadIdx.x * 8 + j);
     }
-    const unsigned long long found_all = *((volatile unsigned long long *)&st->found);
-    const unsigned long long k = st->n_po < found_all ? st->n_po : found_all; // min(n_po, found)
+    const unsigned long long found_all = multi ? *((volatile unsigned long long *)&st->found) : found_in;
+    const unsigned long long k = n_po < found_all ? n_po : found_all; // min(n_po, found)
     if (threadIdx.x == 0) s_bin = ICPB_NONE;
     // which bin holds the k-th smallest distance (every block finds the same one)
-    uint32_t c[8], local = 0;
+    uint32_t local = 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        c[j] = __ldcg(hist + (threadIdx.x * 8 + j) * hstride);
-        local += c[j];
-    }
+    for (int j = 0; j < 8; ++j) local += c[j];
     uint32_t total;
     const uint32_t before = block_exclusive_scan(local, scan_smem, total);
     if (k > 0 && k <= (unsigned long long)total) {
@@ -1240,42 +1448,134 @@ __global__ void __launch_bounds__(SEL_THREADS)
     for (int b = threadIdx.x; b < SEL_MAX_BINS; b += SEL_THREADS) fhist[b] = 0u;
     __syncthreads();
     const unsigned bin = s_bin;
+    const double scale = lin_scale(d_box);
+    // this block's share of the pairs: a contiguous range (equal shares to within one pair)
+    const uint32_t e_lo = (uint32_t)((unsigned long long)n * blockIdx.x / gridDim.x);
+    const uint32_t e_hi = (uint32_t)((unsigned long long)n * (blockIdx.x + 1u) / gridDim.x);
+    ICPB_STAMP(blockIdx.x == 0, 1);
+    double acc[ICPB_NSUMS];
+#pragma unroll
+    for (int q = 0; q < ICPB_NSUMS; ++q) acc[q] = 0.0;
+    // the pairs of the bin go to a segment of their own per warp, in the order the warp meets them: no atomics, and
+    // the order (hence every sum formed over them later) is the same in every run
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t seg_cap = trim_seg_cap(n, gridDim.x);
+    const size_t seg_base = ((size_t)blockIdx.x * (SEL_THREADS / 32) + (size_t)warp) * seg_cap;
+    unsigned wcnt = 0; // warp-uniform
     if (bin != ICPB_NONE) {
-        const double scale = lin_scale(st->d_box);
-        const int lane = threadIdx.x & 31;
-        const uint32_t T = gridDim.x * blockDim.x;
-        for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += 4u * T) { // warp-uniform trip count
-            double d[4];
-            uint32_t idx[4];
+        // four pairs per trip (block-uniform trip count): their coalesced loads are all in flight before the first
+        // dependent gather of a model point
+        for (uint32_t base = e_lo; base < e_hi; base += 4u * SEL_THREADS) {
+            double d[4], vx[4], vy[4], vz[4];
+            uint32_t idx[4], pos[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                idx[u] = base + (uint32_t)u * T + threadIdx.x;
-                d[u] = (idx[u] < n && idx[u] >= base) ? nn_d[idx[u]] : icpb_inf();
+                idx[u] = base + (uint32_t)u * SEL_THREADS + threadIdx.x;
+                const bool in = idx[u] < e_hi;
+                d[u] = in ? nn_d[idx[u]] : icpb_inf();
+                if (fuse) {
+                    vx[u] = in ? sx[idx[u]] : 0.0;
+                    vy[u] = in ? sy[idx[u]] : 0.0;
+                    vz[u] = in ? sz[idx[u]] : 0.0;
+                    pos[u] = in ? nn_pos[idx[u]] : ICPB_NONE;
+                }
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const bool hit = d[u] < icpb_inf() && lin_bin(d[u], scale) == bin;
+                const unsigned b = d[u] < icpb_inf() ? lin_bin(d[u], scale) : ICPB_NONE;
+                if (fuse && b < bin) moments_add(acc, M, vx[u], vy[u], vz[u], g.pts[pos[u]], d[u]); // kept whatever tau is
+                const bool hit = b == bin;
                 const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
                 if (!m) continue;
-                unsigned pos = 0;
-                if (lane == __ffs(m) - 1) pos = atomicAdd(cand_count, (unsigned)__popc(m));
-                pos = __shfl_sync(0xFFFFFFFFu, pos, __ffs(m) - 1) + __popc(m & ((1u << lane) - 1u));
                 if (hit) {
-                    cand_key[pos] = (unsigned long long)__double_as_longlong(d[u]);
-                    cand_idx[pos] = idx[u];
+                    const size_t at = seg_base + wcnt + (unsigned)__popc(m & ((1u << lane) - 1u));
+                    seg_key[at] = (unsigned long long)__double_as_longlong(d[u]);
+                    seg_idx[at] = idx[u];
                 }
+                wcnt += (unsigned)__popc(m);
             }
         }
     }
+    if (lane == 0) seg_count[blockIdx.x * (SEL_THREADS / 32) + warp] = wcnt;
+    if (fuse) moments_block_partial(acc, partials + (size_t)blockIdx.x * ICPB_NSUMS, ms);
+    ICPB_STAMP(blockIdx.x == 0, 2);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) is_last = (atomicAdd(&st->tickets[7], 1u) == gridDim.x - 1) ? 1 : 0;
     __syncthreads();
     if (!is_last) return;
+    // ---- the block that arrived last: selection, the kept pairs of the bin, final sums, pose ----
+    // It works on a shared-memory copy of the loop state (ls) from here on; everything it needs from the L2 first --
+    // the state, the segment counts, its share of the partial rows -- is requested in one go.
+    ICPB_STAMP(true, 3);
     __threadfence();
+    __shared__ uint32_t seg_off[TRIM_MAX_BLOCKS * (SEL_THREADS / 32) + 1];
+    const unsigned nseg = gridDim.x * (SEL_THREADS / 32);
+    const unsigned s0 = threadIdx.x * TRIM_SEG_PER_THREAD;
+    unsigned cn[TRIM_SEG_PER_THREAD], mine = 0;
+#pragma unroll
+    for (int i = 0; i < TRIM_SEG_PER_THREAD; ++i) cn[i] = (bin != ICPB_NONE && s0 + i < nseg) ? __ldcg(seg_count + s0 + i) : 0u;
+    double rowsum[3];
+    moments_last_begin(st, partials, fuse ? gridDim.x : 0u, rowsum, ms);
     for (int b = threadIdx.x; b < LIN_BINS; b += SEL_THREADS) lhist[b * LIN_STRIDE] = 0u; // for the next loop body's search
-    const unsigned cnt = *((volatile unsigned int *)cand_count);
-    if (threadIdx.x == 0) st->sel_k = k;
+#pragma unroll
+    for (int i = 0; i < TRIM_SEG_PER_THREAD; ++i) mine += cn[i];
+    IcpState *ls = &ms.st;
+    // the warps' segments, in segment order, form one list: candidate j lives in the segment s with seg_off[s] <= j < seg_off[s+1]
+    uint32_t total_c;
+    {
+        unsigned at = block_exclusive_scan(mine, scan_smem, total_c);
+#pragma unroll
+        for (int i = 0; i < TRIM_SEG_PER_THREAD; ++i) {
+            seg_off[s0 + i] = at;
+            at += cn[i];
+        }
+        if (threadIdx.x == SEL_THREADS - 1) seg_off[TRIM_MAX_BLOCKS * (SEL_THREADS / 32)] = at;
+        if (threadIdx.x == 0) ls->sel_k = k;
+    }
+    __syncthreads();
+    const unsigned cnt = total_c;
+    // the first 4 * 256 candidates stay in registers (rk: distance bits, ri: pair); all go to the flat list as well
+    unsigned long long rk[4];
+    uint32_t ri[4];
+    {
+        constexpr int NS = TRIM_MAX_BLOCKS * (SEL_THREADS / 32);
+        for (unsigned j0 = 0; j0 < cnt; j0 += 4u * SEL_THREADS) {
+            unsigned long long kk[4];
+            uint32_t ii[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned j = j0 + threadIdx.x + (unsigned)u * SEL_THREADS;
+                kk[u] = 0ull, ii[u] = 0u;
+                if (j < cnt) {
+                    unsigned lo = 0, hi = NS; // last s in [0, NS] with seg_off[s] <= j (seg_off[NS] = cnt > j)
+                    while (hi - lo > 1u) {
+                        const unsigned mid = (lo + hi) >> 1;
+                        if (seg_off[mid] <= j) lo = mid;
+                        else hi = mid;
+                    }
+                    const size_t src = (size_t)lo * seg_cap + (j - seg_off[lo]);
+                    kk[u] = __ldcg(seg_key + src);
+                    ii[u] = __ldcg(seg_idx + src);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned j = j0 + threadIdx.x + (unsigned)u * SEL_THREADS;
+                if (j < cnt) {
+                    cand_key[j] = kk[u];
+                    cand_idx[j] = ii[u];
+                }
+                if (j0 == 0) rk[u] = kk[u], ri[u] = ii[u];
+            }
+        }
+        if (cnt == 0) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) rk[u] = 0ull, ri[u] = 0u;
+        }
+        if (cnt > 4u * SEL_THREADS || multi) __threadfence(); // the flat list is read right away
+        __syncthreads();
+    }
     // Exact selection among the collected pairs: the s_krem-th smallest by (distance, pair index) -- tau is its distance
     // and p_cut its pair index (pair_kept: d < tau, or d == tau with an index <= p_cut: a stable order, like the oracle).
     // One more linear split of the bin into 2048 sub-bins leaves a handful of pairs, ranked by brute force.
@@ -1286,12 +1586,18 @@ __global__ void __launch_bounds__(SEL_THREADS)
     bool done_fast = false;
     if (multi && bin != ICPB_NONE) {
         done_fast = true;
-        trim_linear_finish_multi(nn_d, perm, st, cand_key, cand_idx, cnt, bin, s_krem, p2p, xscratch, fhist, scan_smem, f_key, f_perm);
+        trim_linear_finish_multi(nn_d, perm, ls, cand_key, cand_idx, cnt, bin, s_krem, p2p, xscratch, fhist, scan_smem, f_key, f_perm);
     } else if (bin != ICPB_NONE) {
-        const double scale = lin_scale(st->d_box);
         const unsigned long long krem = s_krem;
         if (threadIdx.x == 0) f_cnt = 0u, f_sub = ICPB_NONE;
-        for (unsigned j = threadIdx.x; j < cnt; j += blockDim.x)
+        uint32_t rsub[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned j = threadIdx.x + (unsigned)u * SEL_THREADS;
+            rsub[u] = lin_sub_bin(__longlong_as_double((long long)rk[u]), scale, bin);
+            if (j < cnt) atomicAdd(&fhist[rsub[u]], 1u);
+        }
+        for (unsigned j = threadIdx.x + 4u * SEL_THREADS; j < cnt; j += blockDim.x)
             atomicAdd(&fhist[lin_sub_bin(__longlong_as_double((long long)__ldcg(cand_key + j)), scale, bin)], 1u);
         __syncthreads();
         uint32_t c2[8], local2 = 0;
@@ -1317,7 +1623,17 @@ __global__ void __launch_bounds__(SEL_THREADS)
         for (int b = threadIdx.x; b < SEL_MAX_BINS; b += SEL_THREADS) fhist[b] = 0u;
         const unsigned sub = f_sub;
         if (sub != ICPB_NONE) {
-            for (unsigned j = threadIdx.x; j < cnt; j += blockDim.x) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned j = threadIdx.x + (unsigned)u * SEL_THREADS;
+                if (j >= cnt || rsub[u] != sub) continue;
+                const unsigned at = atomicAdd(&f_cnt, 1u);
+                if (at < LIN_FINAL_CAP) {
+                    f_key[at] = rk[u];
+                    f_perm[at] = perm[ri[u]];
+                }
+            }
+            for (unsigned j = threadIdx.x + 4u * SEL_THREADS; j < cnt; j += blockDim.x) {
                 const unsigned long long key = __ldcg(cand_key + j);
                 if (lin_sub_bin(__longlong_as_double((long long)key), scale, bin) != sub) continue;
                 const unsigned at = atomicAdd(&f_cnt, 1u);
@@ -1337,10 +1653,10 @@ __global__ void __launch_bounds__(SEL_THREADS)
                 unsigned rank = 0;
                 for (unsigned j = 0; j < m; ++j) rank += (f_key[j] < kt || (f_key[j] == kt && f_perm[j] < pt)) ? 1u : 0u;
                 if ((unsigned long long)rank == want) {
-                    st->tau = __longlong_as_double((long long)kt);
-                    st->p_cut = (long long)pt;
-                    st->need_tie = 0;
-                    st->sel_krem = 1;
+                    ls->tau = __longlong_as_double((long long)kt);
+                    ls->p_cut = (long long)pt;
+                    ls->need_tie = 0;
+                    ls->sel_krem = 1;
                 }
             }
             done_fast = true;
@@ -1353,54 +1669,77 @@ __global__ void __launch_bounds__(SEL_THREADS)
     for (int pass = 0; pass < SEL_D_PASSES; ++pass) {
         const int bits = c_sel_d_bits[pass], shift = c_sel_d_shift[pass], hsp = shift + bits;
         const unsigned bin_mask = (1u << bits) - 1u;
-        const unsigned long long prefix = pass == 0 ? 0ull : st->sel_prefix;
-        if (pass > 0 && st->sel_krem == 0) break;
+        const unsigned long long prefix = pass == 0 ? 0ull : ls->sel_prefix;
+        if (pass > 0 && ls->sel_krem == 0) break;
         for (unsigned j = threadIdx.x; j < cnt; j += blockDim.x) {
             const unsigned long long key = __ldcg(cand_key + j);
             if (pass == 0 || (key >> hsp) == (prefix >> hsp)) atomicAdd(&fhist[(unsigned)(key >> shift) & bin_mask], 1u);
         }
         __syncthreads();
-        select_pick(st, fhist, pass, false, scan_smem, nullptr, 1, 0, bin != ICPB_NONE ? s_krem : 0ull);
+        select_pick(ls, fhist, pass, false, scan_smem, nullptr, 1, 0, bin != ICPB_NONE ? s_krem : 0ull);
         __syncthreads();
     }
-    if (st->need_tie) { // which of the equidistant pairs survive: the lowest pair indices
-        const unsigned long long tau_bits = (unsigned long long)__double_as_longlong(st->tau);
+    if (ls->need_tie) { // which of the equidistant pairs survive: the lowest pair indices
+        const unsigned long long tau_bits = (unsigned long long)__double_as_longlong(ls->tau);
         for (int pass = 0; pass < SEL_T_PASSES; ++pass) {
             const int bits = c_sel_t_bits[pass], shift = c_sel_t_shift[pass], hst = shift + bits;
             const unsigned bin_mask = (1u << bits) - 1u;
-            const unsigned prefix = pass == 0 ? 0u : st->tie_prefix;
+            const unsigned prefix = pass == 0 ? 0u : ls->tie_prefix;
             for (unsigned j = threadIdx.x; j < cnt; j += blockDim.x) {
                 if (__ldcg(cand_key + j) != tau_bits) continue;
                 const uint32_t pi = perm[__ldcg(cand_idx + j)];
                 if (pass == 0 || hst >= 32 || (pi >> hst) == (prefix >> hst)) atomicAdd(&fhist[(pi >> shift) & bin_mask], 1u);
             }
             __syncthreads();
-            select_pick(st, fhist, pass, true, scan_smem);
+            select_pick(ls, fhist, pass, true, scan_smem);
             __syncthreads();
         }
     }
     }
+    __syncthreads();
     if (threadIdx.x == 0) {
-        *cand_count = 0;
-        st->tickets[7] = 0;
-        if (multi) st->lin_epoch = st->lin_epoch + 1u;
+        ls->tickets[7] = 0;
+        if (multi) ls->lin_epoch = ls->lin_epoch + 1u;
+        ICPB_STAMP(true, 4);
     }
-}
-
-__device__ __forceinline__ bool pair_kept(double d, uint32_t i, double tau, long long p_cut)
-{
-    return d < tau || (d == tau && (long long)i <= p_cut);
-}
-
-// ---------------------------------------------------------------------------
-// K5 (+K6): moments over the kept pairs, deterministic two-stage reduction,
-// closed-form pose step in the last block
-// ---------------------------------------------------------------------------
-constexpr int MOM_THREADS = 256;
-
-__device__ __forceinline__ double shfl_xor_double(double v, int o)
-{
-    return __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    if (!fuse) { // stand-alone trim: the state goes back, moments_kernel follows as a launch of its own
+        __syncthreads();
+        uint32_t *dst = reinterpret_cast<uint32_t *>(st);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(ls);
+        for (int w = threadIdx.x; w < MOM_STATE_WORDS; w += MOM_THREADS) dst[w] = src[w];
+        return;
+    }
+    // the pairs of the bin that are kept, in the list's order (deterministic); the first 1024 come from the registers
+    const double tau = ls->tau;
+    const long long p_cut = ls->p_cut;
+#pragma unroll
+    for (int q = 0; q < ICPB_NSUMS; ++q) acc[q] = 0.0;
+    if (bin != ICPB_NONE && k > 0) {
+        for (unsigned j0 = 0; j0 < cnt; j0 += 4u * SEL_THREADS) {
+            double d[4], vx[4], vy[4], vz[4];
+            uint32_t pos[4], pi[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned j = j0 + (unsigned)u * SEL_THREADS + threadIdx.x;
+                const bool in = j < cnt;
+                const uint32_t i = j0 == 0 ? ri[u] : (in ? __ldcg(cand_idx + j) : 0u);
+                d[u] = !in ? icpb_inf() : __longlong_as_double((long long)(j0 == 0 ? rk[u] : __ldcg(cand_key + j)));
+                const bool want = d[u] <= tau; // most of the bin's pairs on one side of tau need nothing more
+                vx[u] = want ? sx[i] : 0.0;
+                vy[u] = want ? sy[i] : 0.0;
+                vz[u] = want ? sz[i] : 0.0;
+                pos[u] = want ? nn_pos[i] : ICPB_NONE;
+                pi[u] = want ? perm[i] : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (d[u] <= tau && pair_kept(d[u], pi[u], tau, p_cut)) moments_add(acc, M, vx[u], vy[u], vz[u], g.pts[pos[u]], d[u]);
+        }
+    }
+    __syncthreads();
+    moments_block_partial(acc, ms.extra, ms);
+    ICPB_STAMP(true, 6);
+    moments_last_finish(st, rowsum, true, trace, trace_cap, 1, p2p, cond, use_cond, ms);
 }
 
 __global__ void __launch_bounds__(MOM_THREADS, 2)
@@ -1411,8 +1750,7 @@ __global__ void __launch_bounds__(MOM_THREADS, 2)
                    int trace_cap, int fused_pose, const P2PView p2p, cudaGraphConditionalHandle cond, int use_cond)
 {
     if (st->done) return;
-    __shared__ double sm[MOM_THREADS / 32][ICPB_NSUMS];
-    __shared__ int is_last;
+    __shared__ MomShared ms;
     double acc[ICPB_NSUMS];
 #pragma unroll
     for (int k = 0; k < ICPB_NSUMS; ++k) acc[k] = 0.0;
@@ -1444,79 +1782,20 @@ __global__ void __launch_bounds__(MOM_THREADS, 2)
             for (int u = 0; u < 4; ++u) {
                 if (!(d[u] <= tau)) continue; // also +inf (no pair) and the out-of-range slots
                 if (d[u] == tau && !pair_kept(d[u], perm[base + (uint32_t)u * T], tau, p_cut)) continue;
-                double px, py, pz;
-                icpb_aff_apply(M, vx[u], vy[u], vz[u], px, py, pz); // p: the transformed source vertex
-                const MPoint m = g.pts[pos[u]];                     // x: its model point
-                acc[0] += px;
-                acc[1] += py;
-                acc[2] += pz;
-                acc[3] += m.x;
-                acc[4] += m.y;
-                acc[5] += m.z;
-                acc[6] += px * m.x;
-                acc[7] += px * m.y;
-                acc[8] += px * m.z;
-                acc[9] += py * m.x;
-                acc[10] += py * m.y;
-                acc[11] += py * m.z;
-                acc[12] += pz * m.x;
-                acc[13] += pz * m.y;
-                acc[14] += pz * m.z;
-                acc[15] += d[u] * d[u]; // mu_d += d*d (icp/icp.cpp:60-61)
-                acc[16] += 1.0;
+                moments_add(acc, M, vx[u], vy[u], vz[u], g.pts[pos[u]], d[u]);
             }
         }
     }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < ICPB_NSUMS; ++k) {
-        double v = acc[k];
-        for (int o = 16; o > 0; o >>= 1) v += shfl_xor_double(v, o);
-        if (lane == 0) sm[warp][k] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < ICPB_NSUMS) {
-        double v = 0.0;
-        for (int w = 0; w < MOM_THREADS / 32; ++w) v += sm[w][threadIdx.x];
-        partials[(size_t)blockIdx.x * ICPB_NSUMS + threadIdx.x] = v;
-    }
+    moments_block_partial(acc, partials + (size_t)blockIdx.x * ICPB_NSUMS, ms);
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicAdd(&st->tickets[15], 1u) == gridDim.x - 1) ? 1 : 0;
+    if (threadIdx.x == 0) ms.is_last = (atomicAdd(&st->tickets[15], 1u) == gridDim.x - 1) ? 1 : 0;
     __syncthreads();
-    if (!is_last) return;
+    if (!ms.is_last) return;
     __threadfence();
-    // fixed-order reduction of the block partials: column k by warp (k % 8), lanes stride the blocks
-    for (int k = warp; k < ICPB_NSUMS; k += MOM_THREADS / 32) {
-        double v = 0.0;
-        for (unsigned b = lane; b < gridDim.x; b += 32) v += partials[(size_t)b * ICPB_NSUMS + k];
-        for (int o = 16; o > 0; o >>= 1) v += shfl_xor_double(v, o);
-        if (lane == 0) st->sums[k] = v;
-    }
-    __syncthreads();
-    if (p2p.world > 1) {
-        // fused all-reduce of the 17 moment sums over peer memory; rows are summed in rank order on every rank
-        const uint32_t *rows = p2p_exchange(p2p, st, reinterpret_cast<const uint32_t *>(st->sums), 2 * ICPB_NSUMS);
-        if (threadIdx.x < ICPB_NSUMS) {
-            double v = 0.0;
-            for (int q = 0; q < p2p.world; ++q) {
-                const uint32_t *r = rows + (size_t)q * P2P_ROW_WORDS + 2 * threadIdx.x;
-                const unsigned long long bits = (unsigned long long)__ldcv(r) | ((unsigned long long)__ldcv(r + 1) << 32);
-                v += __longlong_as_double((long long)bits);
-            }
-            st->sums[threadIdx.x] = v;
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        st->tickets[15] = 0;
-        if (fused_pose) {
-            const int row = st->executed;
-            icpb_iteration_finish(*st, row < trace_cap ? trace + (size_t)row * ICPB_TRACE_COLS_DEV : nullptr);
-        }
-        // CUDA-graph mode: the loop condition of Trimmed::_align drives the WHILE node this kernel lives in
-        if (use_cond) cudaGraphSetConditional(cond, st->done ? 0u : 1u);
-    }
+    double v[3];
+    moments_last_begin(st, partials, gridDim.x, v, ms);
+    moments_last_finish(st, v, false, trace, trace_cap, fused_pose, p2p, cond, use_cond, ms);
 }
 
 // stand-alone pose step (multi-GPU: after the all-reduce of the 17 sums)

@@ -60,6 +60,9 @@ struct IcpState {
     unsigned int lin_epoch, lin_ready; // multi-GPU one-launch trim: the summed histogram of body #lin_epoch+1 is published
     unsigned int comm_seq;   // collectives completed on the peer-memory path (same on every rank)
     unsigned int comm_error; // a peer did not show up within the spin budget
+#ifdef ICPB_PHASE_STAMPS
+    unsigned long long stamps[16]; // %globaltimer at the phase boundaries of trim_moments_kernel (last launch; study builds only)
+#endif
 };
 
 ICPB_HD void icpb_aff_identity(double *a)

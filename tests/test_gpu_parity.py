@@ -242,6 +242,28 @@ def test_lazy_search_rerun_path(icp, oracle, synth):
     _check_align(icp, r0, r_ref, run, 20.0)
 
 
+def test_fused_trim_moments_matches_separate(icp, oracle, synth):
+    """Loop bodies after the first end in trim_moments_kernel: the trim alone (moments_kernel follows) or trim + moments
+    + pose in the one launch (fuse_moments; the default decides by size).  Both forms, graph and stream loop: same
+    trajectory as the oracle, found / kept / tau identical between the forms, poses equal to fp64 re-association."""
+    m, s, T, prm = synth.config("cfg2", scale=0.05)
+    prm = dict(prm, max_iter=14)
+    got = {}
+    for fuse in (1, 0):
+        icp.set_option("fuse_moments", fuse)
+        for graph in (1, 0):
+            icp.set_option("graph", graph)
+            r, r_ref, run = _align_both(icp, oracle, m, s, **prm)
+            _check_align(icp, r, r_ref, run, 100.0)
+            got[fuse, graph] = (r, [(a["found"], a["kept"], a["tau"]) for a in icp.trace()])
+        assert got[fuse, 1][1] == got[fuse, 0][1] and np.array_equal(got[fuse, 1][0].matrix(), got[fuse, 0][0].matrix())
+    icp.set_option("graph", 1)
+    icp.set_option("fuse_moments", -1)
+    assert [t[:2] for t in got[1, 1][1]] == [t[:2] for t in got[0, 1][1]]
+    assert np.allclose([t[2] for t in got[1, 1][1]], [t[2] for t in got[0, 1][1]], rtol=1e-12, atol=0)
+    assert np.allclose(got[1, 1][0].matrix(), got[0, 1][0].matrix(), rtol=0, atol=1e-12)
+
+
 def test_align_cfg2_scaled_noise_and_source_frame(icp, oracle, synth):
     """1M-vs-1M config at 1/20 scale, Gaussian noise, overlap 0.8; the source cloud sits in its own frame."""
     m, s, T, prm = synth.config("cfg2", scale=0.05)

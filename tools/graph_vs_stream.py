@@ -1,4 +1,5 @@
-"""Device time of one align: stream-enqueued loop vs the CUDA-graph WHILE loop (profile=0).  usage: python tools/graph_vs_stream.py"""
+"""Device time of one align: stream-enqueued loop vs the CUDA-graph WHILE loop (profile=0).
+usage: python tools/graph_vs_stream.py [key=value ...]   (options for icpb_set_option, e.g. fuse_moments=0)"""
 import importlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -8,6 +9,8 @@ for cfg, scale, over in (("cfg1", 0.2, {}), ("cfg1", 2.0, {}), ("cfg2", 1.0, dic
     m, s, T, prm = synth.config(cfg, scale)
     prm = dict(prm, **over)
     icp = pkg.Icp(0)
+    for a in sys.argv[1:]:
+        icp.set_option(a.split("=")[0], float(a.split("=")[1]))
     icp.add_to_model(m)
     icp.upload_source(s)
     out = {}
