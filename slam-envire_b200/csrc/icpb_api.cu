@@ -9,9 +9,11 @@
 #include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -168,6 +170,35 @@ const T *density_gather_t(const T *v, size_t n, int width, double density, std::
     }
     return tmp.data();
 }
+// ICPB_VERBOSE=1: wall-clock marks (with a stream sync each) through the build / append paths, printed to stderr
+struct PhaseMarks {
+    bool on;
+    cudaStream_t s;
+    const char *what;
+    std::chrono::steady_clock::time_point t0, last;
+    std::string line;
+    PhaseMarks(const char *w, cudaStream_t st) : on(getenv("ICPB_VERBOSE") != nullptr), s(st), what(w)
+    {
+        if (on) {
+            cudaStreamSynchronize(s);
+            t0 = last = std::chrono::steady_clock::now();
+        }
+    }
+    void mark(const char *label)
+    {
+        if (!on) return;
+        cudaStreamSynchronize(s);
+        const auto now = std::chrono::steady_clock::now();
+        char buf[96];
+        snprintf(buf, sizeof(buf), " %s %.0f", label, std::chrono::duration<double, std::micro>(now - last).count());
+        line += buf;
+        last = now;
+    }
+    ~PhaseMarks()
+    {
+        if (on) fprintf(stderr, "[icpb] %s (us):%s | total %.0f\n", what, line.c_str(), std::chrono::duration<double, std::micro>(last - t0).count());
+    }
+};
 constexpr int MAX_DIM = 2048; // cells per axis (bounds the pyramid depth: the walk's trail holds 12 levels)
 constexpr int EVENT_ITERS = 512;
 constexpr int FLAG_RING = 4096;
@@ -225,8 +256,8 @@ struct icpb_ctx {
     int last_executed = 0;
     bool last_valid = false, last_early = false;
     // K7 / debug scratch
-    DevBuf<unsigned long long> kd0, kd1, cand_key, seg_key; // seg_*: per-warp candidate segments of trim_moments_kernel
-    DevBuf<uint32_t> cand_idx, xscratch, seg_idx, seg_count;
+    DevBuf<unsigned long long> kd0, kd1, cand_key, seg_key, cell_bits; // cell_bits: occupied sixteenths per level-0 cell and axis (tight boxes) // seg_*: per-warp candidate segments of trim_moments_kernel
+    DevBuf<uint32_t> cand_idx, xscratch, seg_idx, seg_count, occ_bits; // occ_bits: one bit per cell while the build tunes the cell edge
     DevBuf<uint32_t> dbg_idx;
     DevBuf<uint8_t> dbg_kept;
     // timing
@@ -378,6 +409,8 @@ void icpb_destroy(icpb_ctx *ctx)
     ctx->npts2.release();
     ctx->cell_start.release();
     ctx->cell_box.release();
+    ctx->cell_bits.release();
+    ctx->occ_bits.release();
     ctx->masks.release();
     ctx->keys0.release();
     ctx->keys1.release();
@@ -468,7 +501,7 @@ int icpb_get_option(const icpb_ctx *ctx, const char *key, double *value)
 // ---------------------------------------------------------------------------
 // model
 // ---------------------------------------------------------------------------
-static int build_masks(icpb_ctx *ctx);
+static int update_masks(icpb_ctx *ctx, const uint32_t *keys, size_t k);
 
 // Growing model: merge a freshly appended batch (model_raw[n_old, n_old + k)) into the existing index in one
 // streaming pass instead of re-sorting everything.  Falls back (returns with *done == false) when there is no
@@ -479,6 +512,7 @@ static int try_merge_append(icpb_ctx *ctx, size_t n_old, size_t k, bool *done)
     if (ctx->opt_merge == 0.0 || ctx->grid_dirty || n_old == 0 || ctx->gv.n != n_old || k == 0) return ICPB_OK;
     if (n_old + k >= 0xFFFFFFF0ull) return ICPB_OK;
     cudaStream_t s = ctx->stream;
+    PhaseMarks pm("merge-append", s);
     const GridView &g = ctx->gv;
     const unsigned nbb = std::min<unsigned>(1024u, grid_for(k, 256));
     CK(ctx->bbox_part.ensure((size_t)nbb * 6));
@@ -498,6 +532,7 @@ static int try_merge_append(icpb_ctx *ctx, size_t n_old, size_t k, bool *done)
             return ICPB_OK;
     }
     const size_t ncell = (size_t)g.dim[0][0] * g.dim[0][1] * g.dim[0][2];
+    pm.mark("bbox");
     cudaEvent_t e0 = ctx->ev_up0, e1 = ctx->ev_up1;
     CK(cudaEventRecord(e0, s));
     CK(ctx->keys0.ensure(k));
@@ -510,6 +545,7 @@ static int try_merge_append(icpb_ctx *ctx, size_t n_old, size_t k, bool *done)
     CK(ctx->ptsf2.ensure(n_old + k + ICPB_PAD));
     CK(ctx->pkey2.ensure(n_old + k));
     if (ctx->model_ean) CK(ctx->npts2.ensure(n_old + k));
+    pm.mark("alloc");
     cell_keys_kernel<<<grid_for(k, 256), 256, 0, s>>>(ctx->model_raw.p + 3 * n_old, (uint32_t)k, ctx->gdims, ctx->keys0.p,
                                                       ctx->vals0.p, (uint32_t)n_old);
     CKL();
@@ -519,11 +555,13 @@ static int try_merge_append(icpb_ctx *ctx, size_t n_old, size_t k, bool *done)
                                              ctx->sort_scratch.p, s, &ctx->launches);
     CKL();
     const uint32_t *ks = w ? ctx->keys1.p : ctx->keys0.p, *vs = w ? ctx->vals1.p : ctx->vals0.p;
+    pm.mark("sort");
     CK(cudaMemsetAsync(ctx->newpref.p, 0, (ncell + 1) * sizeof(uint32_t), s));
     key_hist_kernel<<<grid_for(k, 256), 256, 0, s>>>(ks, (uint32_t)k, ctx->newpref.p);
     CKL();
     exclusive_scan_u32(ctx->newpref.p, ctx->newpref.p, ncell + 1, ctx->newpref.p + ncell + 1, s, &ctx->launches);
     CKL();
+    pm.mark("prefix");
     merge_move_old_kernel<<<grid_for(n_old, 256), 256, 0, s>>>(ctx->pts.p, ctx->ptsf.p, ctx->pkey.p,
                                                                ctx->model_ean ? ctx->npts.p : nullptr, (uint32_t)n_old,
                                                                ctx->newpref.p, ctx->pts2.p, ctx->ptsf2.p, ctx->pkey2.p,
@@ -532,7 +570,7 @@ static int try_merge_append(icpb_ctx *ctx, size_t n_old, size_t k, bool *done)
                                                             ctx->model_ean ? ctx->model_edge.p : nullptr, ks, vs,
                                                             (uint32_t)k, ctx->gdims, ctx->cell_start.p, ctx->pts2.p,
                                                             ctx->ptsf2.p, ctx->pkey2.p,
-                                                            ctx->model_ean ? ctx->npts2.p : nullptr);
+                                                            ctx->model_ean ? ctx->npts2.p : nullptr, ctx->cell_bits.p);
     add_prefix_kernel<<<grid_for(ncell + 1, 256), 256, 0, s>>>(ctx->cell_start.p, ctx->newpref.p, ncell + 1);
     CKL();
     ctx->launches += 5;
@@ -544,10 +582,12 @@ static int try_merge_append(icpb_ctx *ctx, size_t n_old, size_t k, bool *done)
     ctx->gv.pts = ctx->pts.p;
     ctx->gv.ptsf = ctx->ptsf.p;
     ctx->gv.n = (uint32_t)(n_old + k);
+    pm.mark("move");
     {
-        int rc = build_masks(ctx);
+        int rc = update_masks(ctx, ks, k);
         if (rc != ICPB_OK) return rc;
     }
+    pm.mark("masks");
     CK(cudaEventRecord(e1, s));
     CK(cudaStreamSynchronize(s));
     float ms = 0.f;
@@ -650,14 +690,13 @@ static void dims_for(const double ext[3], double h, int d[3])
     }
 }
 
-// pyramid of node words (occupancy + tight boxes) from the level-0 prefix array (also after a merge-append)
-static int build_masks(icpb_ctx *ctx)
+// Pyramid geometry of the grid in ctx->gv (dims per level, node arrays).  The node arrays are (re)allocated only when
+// the geometry changed.
+static int layout_masks(icpb_ctx *ctx, size_t mask_off[ICPB_MAX_LEVELS])
 {
-    cudaStream_t s = ctx->stream;
     GridView &g = ctx->gv;
     int L = 0;
     size_t mask_total = 0;
-    size_t mask_off[ICPB_MAX_LEVELS] = {0};
     while (g.dim[L][0] > 1 || g.dim[L][1] > 1 || g.dim[L][2] > 1) {
         for (int a = 0; a < 3; ++a) g.dim[L + 1][a] = (g.dim[L][a] + 1) >> 1;
         ++L;
@@ -668,23 +707,53 @@ static int build_masks(icpb_ctx *ctx)
     CK(ctx->masks.ensure(mask_total + 16));
     CK(ctx->cell_box.ensure((size_t)g.dim[0][0] * g.dim[0][1] * g.dim[0][2] + 16));
     g.cell_box = ctx->cell_box.p;
-    if (L == 0) { // one single cell: no level 1 to compute its tight box along with
-        cell_box_single_kernel<<<1, 256, 0, s>>>(ctx->pts.p, g.n ? g.n : (uint32_t)ctx->model_n, ctx->gdims, ctx->cell_box.p);
-        CKL();
+    for (int l = 1; l <= L; ++l) g.node[l] = ctx->masks.p + mask_off[l];
+    return ICPB_OK;
+}
+
+// Tight boxes of all level-0 cells from cell_bits[] (filled by gather_points_kernel) and the pyramid of node words
+// (child occupancy + tight boxes) above them: one pass per level over the cells of that level.
+static int build_masks(icpb_ctx *ctx)
+{
+    cudaStream_t s = ctx->stream;
+    GridView &g = ctx->gv;
+    size_t mask_off[ICPB_MAX_LEVELS] = {0};
+    {
+        int rc = layout_masks(ctx, mask_off);
+        if (rc != ICPB_OK) return rc;
     }
-    for (int l = 1; l <= L; ++l) {
-        uint32_t *ml = ctx->masks.p + mask_off[l];
-        g.node[l] = ml;
+    const size_t ncell = (size_t)g.dim[0][0] * g.dim[0][1] * g.dim[0][2];
+    cell_words_kernel<<<grid_for(ncell, 256), 256, 0, s>>>(ctx->cell_bits.p, ncell, ctx->cell_box.p);
+    CKL();
+    for (int l = 1; l <= g.L; ++l) {
         const size_t cells = (size_t)g.dim[l][0] * g.dim[l][1] * g.dim[l][2];
-        if (l == 1)
-            node_level1_kernel<<<grid_for(cells, 256), 256, 0, s>>>(ctx->cell_start.p, ctx->pts.p, ctx->gdims, g.dim[1][0],
-                                                                    g.dim[1][1], g.dim[1][2], ml, ctx->cell_box.p);
-        else
-            node_levelN_kernel<<<grid_for(cells, 256), 256, 0, s>>>(g.node[l - 1], g.dim[l - 1][0], g.dim[l - 1][1],
-                                                                    g.dim[l - 1][2], g.dim[l][0], g.dim[l][1],
-                                                                    g.dim[l][2], ml);
+        const uint32_t *below = l == 1 ? ctx->cell_box.p : g.node[l - 1];
+        node_levelN_kernel<<<grid_for(cells, 256), 256, 0, s>>>(below, g.dim[l - 1][0], g.dim[l - 1][1], g.dim[l - 1][2],
+                                                                g.dim[l][0], g.dim[l][1], g.dim[l][2],
+                                                                const_cast<uint32_t *>(g.node[l]));
         CKL();
     }
+    ctx->launches += 1 + (unsigned long long)g.L;
+    return ICPB_OK;
+}
+
+// Growing model: only the cells a batch of k new points fell into (keys[], level-0 cell keys) and their ancestors
+// change -- boxes only grow (cell_bits[] has the new points ORed in already).  O(k * levels) instead of a pass over
+// every cell of every level.
+static int update_masks(icpb_ctx *ctx, const uint32_t *keys, size_t k)
+{
+    cudaStream_t s = ctx->stream;
+    GridView &g = ctx->gv;
+    cell_words_update_kernel<<<grid_for(k, 256), 256, 0, s>>>(ctx->cell_bits.p, keys, (uint32_t)k, ctx->cell_box.p);
+    CKL();
+    for (int l = 1; l <= g.L; ++l) {
+        const uint32_t *below = l == 1 ? ctx->cell_box.p : g.node[l - 1];
+        node_update_kernel<<<grid_for(k, 256), 256, 0, s>>>(keys, (uint32_t)k, g.dim[0][0], g.dim[0][1], l, below,
+                                                            g.dim[l - 1][0], g.dim[l - 1][1], g.dim[l - 1][2], g.dim[l][0],
+                                                            g.dim[l][1], const_cast<uint32_t *>(g.node[l]));
+        CKL();
+    }
+    ctx->launches += 1 + (unsigned long long)g.L;
     return ICPB_OK;
 }
 
@@ -699,6 +768,7 @@ static int build_grid(icpb_ctx *ctx)
         ctx->grid_dirty = false;
         return ICPB_OK;
     }
+    PhaseMarks pm("build", s);
     cudaEvent_t e0 = ctx->ev_up0, e1 = ctx->ev_up1;
     CK(cudaEventRecord(e0, s));
     // bounding box
@@ -765,11 +835,14 @@ static int build_grid(icpb_ctx *ctx)
     CK(ctx->vals0.ensure(n));
     CK(ctx->vals1.ensure(n));
     CK(ctx->sort_scratch.ensure(rs_scratch_elems(n)));
+    pm.mark("bbox+alloc");
 
     GridDims gd;
     int dim0[3];
     int sorted_in = 0;
     unsigned long long occupied = 0;
+    // The cell edge is tuned on the number of occupied cells, counted with one bit per cell (no sort): a few passes over
+    // the points at most, then ONE sort with the edge that stands.
     for (int trial = 0;; ++trial) {
         dims_for(ext, h, dim0);
         for (int a = 0; a < 3; ++a) gd.o[a] = mn[a];
@@ -779,6 +852,25 @@ static int build_grid(icpb_ctx *ctx)
         gd.ny = dim0[1];
         gd.nz = dim0[2];
         const size_t ncell = (size_t)dim0[0] * dim0[1] * dim0[2];
+        CK(ctx->occ_bits.ensure(ncell / 32 + 2));
+        CK(cudaMemsetAsync(ctx->occ_bits.p, 0, (ncell / 32 + 1) * sizeof(uint32_t), s));
+        CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), s));
+        cell_occupancy_kernel<<<std::min<unsigned>(2048u, grid_for(n, 256)), 256, 0, s>>>(ctx->model_raw.p, (uint32_t)n, gd,
+                                                                                          ctx->occ_bits.p, ctx->d_counter);
+        CKL();
+        ++ctx->launches;
+        CK(cudaMemcpyAsync(&occupied, ctx->d_counter, sizeof(occupied), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        pm.mark("trial");
+        if (!auto_h || trial >= 4 || occupied == 0) break;
+        const double avg = (double)n / (double)occupied;
+        if (avg >= 0.6 * ctx->opt_target && avg <= 1.6 * ctx->opt_target) break;
+        const double h_new = h_floor(h * sqrt(ctx->opt_target / avg));
+        if (fabs(h_new - h) <= 1e-3 * h) break; // clamped by the cell budget
+        h = h_new;
+    }
+    {
+        const size_t ncell = (size_t)dim0[0] * dim0[1] * dim0[2];
         int bits = 1;
         while (((size_t)1 << bits) < ncell) ++bits;
         cell_keys_kernel<<<grid_for(n, 256), 256, 0, s>>>(ctx->model_raw.p, (uint32_t)n, gd, ctx->keys0.p,
@@ -787,18 +879,7 @@ static int build_grid(icpb_ctx *ctx)
         sorted_in = radix_sort<uint32_t, true>(ctx->keys0.p, ctx->vals0.p, ctx->keys1.p, ctx->vals1.p, n, bits,
                                                ctx->sort_scratch.p, s, &ctx->launches);
         CKL();
-        CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), s));
-        count_unique_kernel<<<std::min<unsigned>(1024u, grid_for(n, 256)), 256, 0, s>>>(
-            sorted_in ? ctx->keys1.p : ctx->keys0.p, (uint32_t)n, ctx->d_counter);
-        CKL();
-        CK(cudaMemcpyAsync(&occupied, ctx->d_counter, sizeof(occupied), cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        if (!auto_h || trial >= 4 || occupied == 0) break;
-        const double avg = (double)n / (double)occupied;
-        if (avg >= 0.6 * ctx->opt_target && avg <= 1.6 * ctx->opt_target) break;
-        const double h_new = h_floor(h * sqrt(ctx->opt_target / avg));
-        if (fabs(h_new - h) <= 1e-3 * h) break; // clamped by the cell budget
-        h = h_new;
+        pm.mark("sort");
     }
     ctx->gdims = gd;
     const uint32_t *keys_sorted = sorted_in ? ctx->keys1.p : ctx->keys0.p;
@@ -811,8 +892,10 @@ static int build_grid(icpb_ctx *ctx)
     CK(ctx->ptsf.ensure(n + ICPB_PAD));
     CK(ctx->cell_start.ensure(ncell + 1 + scan_scratch_elems(ncell + 1)));
     CK(cudaMemsetAsync(ctx->cell_start.p, 0, (ncell + 1) * sizeof(uint32_t), s));
+    CK(ctx->cell_bits.ensure(ncell + 1));
+    CK(cudaMemsetAsync(ctx->cell_bits.p, 0, ncell * sizeof(unsigned long long), s));
     gather_points_kernel<<<grid_for(n, 256), 256, 0, s>>>(ctx->model_raw.p, keys_sorted, perm, (uint32_t)n, gd,
-                                                          ctx->pts.p, ctx->ptsf.p, ctx->cell_start.p);
+                                                          ctx->pts.p, ctx->ptsf.p, ctx->cell_start.p, ctx->cell_bits.p);
     pad_tail_kernel<<<1, 32, 0, s>>>(ctx->pts.p, ctx->ptsf.p, (uint32_t)n);
     CKL();
     exclusive_scan_u32(ctx->cell_start.p, ctx->cell_start.p, ncell + 1, ctx->cell_start.p + ncell + 1, s,
@@ -824,6 +907,7 @@ static int build_grid(icpb_ctx *ctx)
         CKL();
     }
 
+    pm.mark("gather+prefix");
     // pyramid of node words (occupancy + tight boxes) and the level-0 cell boxes
     GridView &g = ctx->gv;
     memset(&g, 0, sizeof(g));
@@ -838,6 +922,7 @@ static int build_grid(icpb_ctx *ctx)
         int rc = build_masks(ctx);
         if (rc != ICPB_OK) return rc;
     }
+    pm.mark("masks");
     const int L = g.L;
     g.cell_start = ctx->cell_start.p;
     g.pts = ctx->pts.p;

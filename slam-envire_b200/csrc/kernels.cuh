@@ -144,6 +144,23 @@ __global__ void cell_keys_kernel(const double *__restrict__ pts, uint32_t n, Gri
     vals[i] = base + i; // insertion index
 }
 
+// occupied level-0 cells for a candidate cell edge (the build tries a few): one bit per cell, no sort
+__global__ void __launch_bounds__(256) cell_occupancy_kernel(const double *__restrict__ pts, uint32_t n, GridDims g,
+                                                              uint32_t *__restrict__ bitmap, unsigned long long *__restrict__ counter)
+{
+    unsigned c = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int cx = icpb_cell_coord(pts[3 * (size_t)i], g.o[0], g.inv_h, g.nx);
+        const int cy = icpb_cell_coord(pts[3 * (size_t)i + 1], g.o[1], g.inv_h, g.ny);
+        const int cz = icpb_cell_coord(pts[3 * (size_t)i + 2], g.o[2], g.inv_h, g.nz);
+        const size_t key = ((size_t)cz * g.ny + cy) * g.nx + cx;
+        const uint32_t bit = 1u << (key & 31u);
+        if (!(atomicOr(bitmap + (key >> 5), bit) & bit)) ++c; // this thread set the bit: a cell not seen before
+    }
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(counter, (unsigned long long)c);
+}
+
 // ICPB_PAD sentinel entries behind the sorted points (grid_view.h): never the nearest neighbour of anything
 __global__ void pad_tail_kernel(MPoint *__restrict__ pts, FPoint *__restrict__ ptsf, uint32_t n)
 {
@@ -169,28 +186,84 @@ __global__ void __launch_bounds__(256) count_unique_kernel(const uint32_t *__res
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(counter, (unsigned long long)c);
 }
 
-// sorted layout: pts_sorted[j] = {model[perm[j]], perm[j]}; cell_count[key[j]]++
+// Tight boxes without a pass per cell: every level-0 cell owns 48 bits (cell_bits[]), one per sixteenth of the cell edge
+// and axis (bits 0-15 x, 16-31 y, 32-47 z); a point ORs in the three sixteenths it lies in.  The box of the cell is
+// lowest / highest set bit per axis -- and a cloud appended later only ORs its own points in (the growing model).
+__device__ __forceinline__ unsigned long long cell_point_bits(double px, double py, double pz, const GridDims &g, uint32_t key)
+{
+    const int cx = (int)(key % (uint32_t)g.nx), cy = (int)((key / (uint32_t)g.nx) % (uint32_t)g.ny),
+              cz = (int)(key / ((uint32_t)g.nx * (uint32_t)g.ny));
+    const int bx = icpb_node_nibble((px - g.o[0]) * g.inv_h, (double)cx, 0);
+    const int by = icpb_node_nibble((py - g.o[1]) * g.inv_h, (double)cy, 0);
+    const int bz = icpb_node_nibble((pz - g.o[2]) * g.inv_h, (double)cz, 0);
+    return (1ull << bx) | (1ull << (16 + by)) | (1ull << (32 + bz));
+}
+// node-word form of a cell's bits: bits 8-31 the six nibbles, low byte 1 = occupied (what node_levelN_kernel looks at)
+__device__ __forceinline__ uint32_t cell_word_from_bits(unsigned long long b)
+{
+    if (!b) return 0u;
+    const unsigned x = (unsigned)b & 0xFFFFu, y = (unsigned)(b >> 16) & 0xFFFFu, z = (unsigned)(b >> 32) & 0xFFFFu;
+    const int lo[3] = {__ffs((int)x) - 1, __ffs((int)y) - 1, __ffs((int)z) - 1};
+    const int hi[3] = {31 - __clz((int)x), 31 - __clz((int)y), 31 - __clz((int)z)};
+    return icpb_node_word(1u, lo, hi);
+}
+// all 32 lanes call; keys ascending within the warp (sorted points): one atomic per cell and warp
+__device__ __forceinline__ void cell_bits_or_sorted(unsigned long long *__restrict__ cell_bits, uint32_t key, unsigned long long v, bool valid)
+{
+    const int lane = threadIdx.x & 31;
+    if (!valid) key = 0xFFFFFFFFu, v = 0ull;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long ov = __shfl_up_sync(0xFFFFFFFFu, v, d);
+        const uint32_t ok = __shfl_up_sync(0xFFFFFFFFu, key, d);
+        if (lane >= d && ok == key) v |= ov;
+    }
+    const uint32_t nk = __shfl_down_sync(0xFFFFFFFFu, key, 1);
+    if (valid && (lane == 31 || nk != key)) atomicOr(cell_bits + key, v);
+}
+
+// sorted layout: pts_sorted[j] = {model[perm[j]], perm[j]}; cell_count[key[j]]++; cell_bits[key[j]] |= bits of the point
 __global__ void gather_points_kernel(const double *__restrict__ raw, const uint32_t *__restrict__ keys,
                                      const uint32_t *__restrict__ perm, uint32_t n, GridDims g,
                                      MPoint *__restrict__ out, FPoint *__restrict__ outf,
-                                     uint32_t *__restrict__ cell_count)
+                                     uint32_t *__restrict__ cell_count, unsigned long long *__restrict__ cell_bits)
 {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    const uint32_t src = perm[j];
-    MPoint m;
-    m.x = raw[3 * (size_t)src];
-    m.y = raw[3 * (size_t)src + 1];
-    m.z = raw[3 * (size_t)src + 2];
-    m.idx = src;
-    out[j] = m;
-    FPoint f;
-    f.x = (float)((m.x - g.o[0]) * g.inv_h);
-    f.y = (float)((m.y - g.o[1]) * g.inv_h);
-    f.z = (float)((m.z - g.o[2]) * g.inv_h);
-    f.w = 0.0f;
-    outf[j] = f;
-    atomicAdd(&cell_count[keys[j]], 1u);
+    const bool valid = j < n;
+    uint32_t key = 0;
+    unsigned long long bits = 0;
+    if (valid) {
+        const uint32_t src = perm[j];
+        key = keys[j];
+        MPoint m;
+        m.x = raw[3 * (size_t)src];
+        m.y = raw[3 * (size_t)src + 1];
+        m.z = raw[3 * (size_t)src + 2];
+        m.idx = src;
+        out[j] = m;
+        FPoint f;
+        f.x = (float)((m.x - g.o[0]) * g.inv_h);
+        f.y = (float)((m.y - g.o[1]) * g.inv_h);
+        f.z = (float)((m.z - g.o[2]) * g.inv_h);
+        f.w = 0.0f;
+        outf[j] = f;
+        atomicAdd(&cell_count[key], 1u);
+        bits = cell_point_bits(m.x, m.y, m.z, g, key);
+    }
+    cell_bits_or_sorted(cell_bits, key, bits, valid);
+}
+// cell_box[] (the walk's and the block scan's tight boxes of the level-0 cells) from the bits, all cells
+__global__ void cell_words_kernel(const unsigned long long *__restrict__ cell_bits, size_t ncell, uint32_t *__restrict__ cell_box)
+{
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < ncell) cell_box[c] = cell_word_from_bits(cell_bits[c]);
+}
+// ... and of the cells a batch of new points fell into (keys[]: their cells, any order, duplicates welcome)
+__global__ void cell_words_update_kernel(const unsigned long long *__restrict__ cell_bits, const uint32_t *__restrict__ keys,
+                                         uint32_t k, uint32_t *__restrict__ cell_box)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < k) cell_box[keys[i]] = cell_word_from_bits(cell_bits[keys[i]]);
 }
 
 // ---------------------------------------------------------------------------
@@ -221,7 +294,8 @@ __global__ void merge_place_new_kernel(const double *__restrict__ raw, const dou
                                        const uint8_t *__restrict__ raw_edge, const uint32_t *__restrict__ keys,
                                        const uint32_t *__restrict__ vals, uint32_t k, GridDims g,
                                        const uint32_t *__restrict__ cell_start_old, MPoint *__restrict__ pts2,
-                                       FPoint *__restrict__ ptsf2, uint32_t *__restrict__ pkey2, NPoint *__restrict__ npts2)
+                                       FPoint *__restrict__ ptsf2, uint32_t *__restrict__ pkey2, NPoint *__restrict__ npts2,
+                                       unsigned long long *__restrict__ cell_bits)
 {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= k) return;
@@ -240,6 +314,7 @@ __global__ void merge_place_new_kernel(const double *__restrict__ raw, const dou
     f.w = 0.0f;
     ptsf2[q] = f;
     pkey2[q] = c;
+    atomicOr(cell_bits + c, cell_point_bits(m.x, m.y, m.z, g, c));
     if (npts2) {
         NPoint np;
         np.nx = raw_nrm[3 * (size_t)src];
@@ -255,72 +330,10 @@ __global__ void add_prefix_kernel(uint32_t *__restrict__ cell_start, const uint3
     if (i < n) cell_start[i] += newpref[i];
 }
 
-// level-1 node words (child occupancy + tight box of the points below, grid_view.h) from the level-0 prefix array
-__global__ void node_level1_kernel(const uint32_t *__restrict__ cell_start, const MPoint *__restrict__ pts, GridDims g,
-                                   int mx, int my, int mz, uint32_t *__restrict__ node, uint32_t *__restrict__ cell_box)
+// level-l node word (l >= 1) of node (cx,cy,cz) from the words one level below (level 0: the cell words, cell_box[])
+__device__ __forceinline__ uint32_t node_word_from_children(const uint32_t *__restrict__ below, int nx, int ny, int nz,
+                                                            int cx, int cy, int cz)
 {
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (size_t)mx * my * mz) return;
-    const int cx = (int)(t % mx), cy = (int)((t / mx) % my), cz = (int)(t / ((size_t)mx * my));
-    unsigned m = 0;
-    int lo[3] = {15, 15, 15}, hi[3] = {0, 0, 0};
-    const double cl[3] = {2.0 * cx, 2.0 * cy, 2.0 * cz};
-    for (int ch = 0; ch < 8; ++ch) {
-        const int x = 2 * cx + (ch & 1), y = 2 * cy + ((ch >> 1) & 1), z = 2 * cz + ((ch >> 2) & 1);
-        if (x >= g.nx || y >= g.ny || z >= g.nz) continue;
-        const size_t c = ((size_t)z * g.ny + y) * g.nx + x;
-        const uint32_t s = cell_start[c], e = cell_start[c + 1];
-        if (e == s) continue;
-        m |= 1u << ch;
-        int clo[3] = {15, 15, 15}, chi[3] = {0, 0, 0}; // the child cell's own tight box (level 0)
-        const double cc[3] = {(double)x, (double)y, (double)z};
-        for (uint32_t p = s; p < e; ++p) {
-            const MPoint q = pts[p];
-            const double u[3] = {(q.x - g.o[0]) * g.inv_h, (q.y - g.o[1]) * g.inv_h, (q.z - g.o[2]) * g.inv_h};
-            for (int a = 0; a < 3; ++a) {
-                const int nb = icpb_node_nibble(u[a], cl[a], 1);
-                lo[a] = min(lo[a], nb);
-                hi[a] = max(hi[a], nb);
-                const int cb = icpb_node_nibble(u[a], cc[a], 0);
-                clo[a] = min(clo[a], cb);
-                chi[a] = max(chi[a], cb);
-            }
-        }
-        cell_box[c] = icpb_node_word(0u, clo, chi);
-    }
-    node[t] = m ? icpb_node_word(m, lo, hi) : 0u;
-}
-
-// a grid of one single cell has no level 1: its tight box is computed on its own (one block)
-__global__ void __launch_bounds__(256) cell_box_single_kernel(const MPoint *__restrict__ pts, uint32_t n, GridDims g,
-                                                              uint32_t *__restrict__ cell_box)
-{
-    __shared__ int lo[3], hi[3];
-    if (threadIdx.x < 3) {
-        lo[threadIdx.x] = 15;
-        hi[threadIdx.x] = 0;
-    }
-    __syncthreads();
-    for (uint32_t p = threadIdx.x; p < n; p += blockDim.x) {
-        const MPoint q = pts[p];
-        const double u[3] = {(q.x - g.o[0]) * g.inv_h, (q.y - g.o[1]) * g.inv_h, (q.z - g.o[2]) * g.inv_h};
-        for (int a = 0; a < 3; ++a) {
-            const int nb = icpb_node_nibble(u[a], 0.0, 0);
-            atomicMin(&lo[a], nb);
-            atomicMax(&hi[a], nb);
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) cell_box[0] = n ? icpb_node_word(0u, lo, hi) : 0u;
-}
-
-// level-l node words (l >= 2) from the words one level below
-__global__ void node_levelN_kernel(const uint32_t *__restrict__ below, int nx, int ny, int nz, int mx, int my, int mz,
-                                   uint32_t *__restrict__ node)
-{
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (size_t)mx * my * mz) return;
-    const int cx = (int)(t % mx), cy = (int)((t / mx) % my), cz = (int)(t / ((size_t)mx * my));
     unsigned m = 0;
     int lo[3] = {15, 15, 15}, hi[3] = {0, 0, 0};
     for (int ch = 0; ch < 8; ++ch) {
@@ -334,9 +347,28 @@ __global__ void node_levelN_kernel(const uint32_t *__restrict__ below, int nx, i
             hi[a] = max(hi[a], icpb_nibble_up(w, 20 + 4 * a, (ch >> a) & 1));
         }
     }
-    node[t] = m ? icpb_node_word(m, lo, hi) : 0u;
+    return m ? icpb_node_word(m, lo, hi) : 0u;
 }
-
+// growing model: the level-l ancestors of the cells a batch of new points fell into (keys[]: level-0 cell keys)
+__global__ void node_update_kernel(const uint32_t *__restrict__ keys, uint32_t k, int nx0, int ny0, int level,
+                                   const uint32_t *__restrict__ below, int nx, int ny, int nz, int mx, int my,
+                                   uint32_t *__restrict__ node)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k) return;
+    const uint32_t key = keys[i];
+    const int cx = (int)(key % (uint32_t)nx0) >> level, cy = (int)((key / (uint32_t)nx0) % (uint32_t)ny0) >> level,
+              cz = (int)(key / ((uint32_t)nx0 * (uint32_t)ny0)) >> level;
+    node[((size_t)cz * my + cy) * mx + cx] = node_word_from_children(below, nx, ny, nz, cx, cy, cz);
+}
+__global__ void node_levelN_kernel(const uint32_t *__restrict__ below, int nx, int ny, int nz, int mx, int my, int mz,
+                                   uint32_t *__restrict__ node)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)mx * my * mz) return;
+    const int cx = (int)(t % mx), cy = (int)((t / mx) % my), cz = (int)(t / ((size_t)mx * my));
+    node[t] = node_word_from_children(below, nx, ny, nz, cx, cy, cz);
+}
 // ---------------------------------------------------------------------------
 // K2 + K3: transform the source vertex and find its exact nearest model point
 // ---------------------------------------------------------------------------
