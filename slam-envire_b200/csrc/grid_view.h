@@ -413,15 +413,19 @@ ICPB_HD void icpb_nn_init(const GridView &g, double qx, double qy, double qz, do
 }
 
 // start level: smallest l with 2^l >= 2*(ru + slack), so the ball spans <= 2 cells per axis even after the fp32
-// rounding of the range arithmetic in icpb_nn_plan (which the extra slack dominates)
+// rounding of the range arithmetic in icpb_nn_plan (which the extra slack dominates).  Never above level
+// ICPB_WALK_TOP: the walk's trail holds one byte per level in 12 bytes of registers, and a grid of at most 8192 cells
+// per axis (13 levels) has at most 2 nodes per axis there anyway -- all of them are roots then.
+#define ICPB_WALK_TOP 12
 ICPB_HD int icpb_nn_start_level(const GridView &g, const NNState &s)
 {
     const float ru = sqrtf(s.boundf) * 1.000001f + s.slack;
+    const int top = g.L < ICPB_WALK_TOP ? g.L : ICPB_WALK_TOP;
     int l = 0;
     if (ru < 1.0e30f) {
-        while (l < g.L && (float)(1u << l) < 2.0f * (ru + s.slack)) ++l;
+        while (l < top && (float)(1u << l) < 2.0f * (ru + s.slack)) ++l;
     } else {
-        l = g.L;
+        l = top;
     }
     return l;
 }

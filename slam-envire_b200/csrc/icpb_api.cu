@@ -199,7 +199,7 @@ struct PhaseMarks {
         if (on) fprintf(stderr, "[icpb] %s (us):%s | total %.0f\n", what, line.c_str(), std::chrono::duration<double, std::micro>(last - t0).count());
     }
 };
-constexpr int MAX_DIM = 2048; // cells per axis (bounds the pyramid depth: the walk's trail holds 12 levels)
+constexpr int MAX_DIM = 8192; // cells per axis: 13 levels above level 0; walks start at level 12 at most (ICPB_WALK_TOP), where <= 2 nodes per axis are left
 constexpr int EVENT_ITERS = 512;
 constexpr int FLAG_RING = 4096;
 } // namespace

@@ -42,21 +42,23 @@ def test_find_pairs_random(icp, oracle, nm, nq, d_box, seed):
 
 
 def test_find_pairs_deep_pyramid(pkg, oracle):
-    """2000 cells along x, 11 pyramid levels: the walk's trail uses its second register, cold searches start at the top."""
+    """2000 cells along x, 11 pyramid levels: the walk's trail uses its second register, cold searches start at the top;
+    8000 cells along x, 13 levels: walks start at level 12 at most (ICPB_WALK_TOP), with two root nodes along x."""
     rng = np.random.default_rng(21)
     m = np.stack([rng.uniform(0, 20, 30000), rng.uniform(0, 0.05, 30000), rng.uniform(0, 0.05, 30000)], 1)
     q = np.concatenate([m[:4000] + rng.normal(0, 0.3, (4000, 3)), rng.uniform(-3, 23, (3000, 3)) * [1, 0.1, 0.1]])
     ctx = pkg.Icp(0)
     try:
-        ctx.set_option("cell_size", 0.01)
-        ctx.add_to_model(m)
-        assert ctx.build().levels == 11
         M = oracle.Model()
         M.add(m)
-        for d_box in (np.inf, 2.5, 0.2):
-            i_ref, d_ref = M.find_pairs(q, d_box=d_box)
-            i_gpu, d_gpu = ctx.find_pairs(q, d_box=d_box)
-            assert _pairs_match(i_gpu, d_gpu, i_ref, d_ref, d_box) == 0
+        ctx.add_to_model(m)
+        for cell, levels in ((0.01, 11), (0.0025, 13)):
+            ctx.set_option("cell_size", cell)
+            assert ctx.build().levels == levels
+            for d_box in (np.inf, 2.5, 0.2):
+                i_ref, d_ref = M.find_pairs(q, d_box=d_box)
+                i_gpu, d_gpu = ctx.find_pairs(q, d_box=d_box)
+                assert _pairs_match(i_gpu, d_gpu, i_ref, d_ref, d_box) == 0
     finally:
         ctx.close()
 

@@ -71,6 +71,11 @@ def test_grid_search_deep_pyramid(harness, oracle):
         assert np.array_equal(i0, i1) and np.array_equal(d0, d1)
         if d_box == np.inf:
             assert lv.max() == 11
+        # 8000 cells along x: 13 levels; walks start at level 12 at most (two root nodes along x)
+        i2, d2, lv2 = harness.search(m, 0.0025, q, d_box)
+        assert np.array_equal(i0, i2) and np.array_equal(d0, d2)
+        if d_box == np.inf:
+            assert lv2.max() == 12
 
 
 def test_grid_search_surface_scene(harness, oracle, synth):
