@@ -194,6 +194,29 @@ int icpb_p2p_connect(icpb_ctx *, int n_ranks, int rank, const uint8_t *handles /
 int icpb_source_upload_shard(icpb_ctx *, const double *xyz_aos_local, size_t n_local, size_t adapter_size_global,
                              const double T_local2global[16]);
 
+
+/* ---- several GPUs in ONE process ---------------------------------------- */
+/* The same sharding (source in contiguous ranges of the adapter's visiting order, model replicated) and the same fused
+ * exchanges, for callers that are a single process -- envire::icp::TrimmedGPU(device, n_devices): one context per
+ * device, peers reached through cudaDeviceEnablePeerAccess (n_devices <= 8, distinct devices of one NVLink box).
+ * The calls mirror the single-context ones; results equal the single-GPU ones (same pose to fp64 re-association of the
+ * 17 sums, same iteration and pair counts).  Plain (non edge-and-normal) clouds; needs the default graph loop. */
+typedef struct icpb_multi icpb_multi;
+int icpb_create_multi(icpb_multi **out, const int *device_ids, int n_devices); /* *out is set even on failure (for the error text): destroy it */
+void icpb_destroy_multi(icpb_multi *);
+const char *icpb_multi_last_error(const icpb_multi *);
+int icpb_multi_size(const icpb_multi *);
+icpb_ctx *icpb_multi_context(icpb_multi *, int i); /* the context of device i: traces, timings, grid info */
+int icpb_multi_set_option(icpb_multi *, const char *key, double value);
+int icpb_multi_model_add(icpb_multi *, const double *xyz_aos, size_t n_vertices, const double T_local2global[16], double density);
+int icpb_multi_model_clear(icpb_multi *);
+int icpb_multi_source_upload(icpb_multi *, const double *xyz_aos, size_t n_vertices, const double T_local2global[16], double density);
+int icpb_multi_align_resident(icpb_multi *, const icpb_params *, icpb_result *out);
+int icpb_multi_align(icpb_multi *, const double *xyz_aos, size_t n_vertices, const double T_local2global[16], double density,
+                     const icpb_params *, icpb_result *out);
+/* kept distances of all devices, ascending (merged on the host) */
+int icpb_multi_pairs_distance(icpb_multi *, double *out_sorted, size_t capacity, size_t *n_out);
+
 #ifdef __cplusplus
 }
 #endif

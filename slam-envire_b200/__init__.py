@@ -30,6 +30,9 @@ SYMBOLS = [
     "icpb_source_upload", "icpb_align_resident", "icpb_align", "icpb_pairs_distance", "icpb_debug_pairs",
     "icpb_trace", "icpb_last_timing", "icpb_iteration_times", "icpb_find_pairs", "icpb_trim", "icpb_pairs_transform", "icpb_nccl_unique_id", "icpb_comm_init",
     "icpb_source_upload_shard", "icpb_p2p_export", "icpb_p2p_connect",
+    "icpb_create_multi", "icpb_destroy_multi", "icpb_multi_last_error", "icpb_multi_size", "icpb_multi_context",
+    "icpb_multi_set_option", "icpb_multi_model_add", "icpb_multi_model_clear", "icpb_multi_source_upload",
+    "icpb_multi_align_resident", "icpb_multi_align", "icpb_multi_pairs_distance",
 ]
 
 

@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -247,6 +248,12 @@ struct icpb_ctx {
     IcpState *h_state = nullptr; // pinned
     int *h_flags = nullptr;      // pinned
     uint32_t *d_ghist = nullptr;
+    struct { // between align_enqueue and align_collect
+        unsigned long long launches0 = 0;
+        bool use_graph = false, linear_ok = false, pending = false;
+        uint32_t n = 0;
+        size_t timed_iters = 0;
+    } run;
     unsigned tm_blocks = 0; // co-resident blocks of trim_moments_kernel (0: not queried yet)
     uint32_t *d_lhist = nullptr; // linear histogram of the pair distances (search epilogue -> trim_linear_kernel)
     unsigned long long *d_counter = nullptr;
@@ -1224,10 +1231,14 @@ static int launch_trim(icpb_ctx *ctx, uint32_t n, bool linear = false, bool *mom
 // ---------------------------------------------------------------------------
 // align
 // ---------------------------------------------------------------------------
-int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
+// One Trimmed::_align in two steps: align_enqueue puts the whole loop on the context's stream (graph mode: one graph
+// launch, nothing waited for), align_collect waits for it and reads the result.  A single context runs them back to
+// back; icpb_multi_align_resident enqueues on every device first, so that the ranks' fused exchanges meet.
+static int align_enqueue(icpb_ctx *ctx, const icpb_params *prm, bool graph_only)
 {
-    if (!ctx || !prm || !out) return ICPB_ERR_ARG;
+    if (!ctx || !prm) return ICPB_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
+    ctx->run.pending = false;
     if (!ctx->have_source) return ICPB_ERR_NO_SOURCE;
     if (ctx->grid_dirty) {
         int rc = build_grid(ctx);
@@ -1296,6 +1307,10 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
     };
     size_t it = 0, checked = 0, timed_iters = 0;
     const bool use_graph = ctx->opt_graph != 0.0 && !profile && fused;
+    if (graph_only && !use_graph) {
+        ctx->err = "several devices in one process need the graph loop (options graph = 1, profile = 0, peer-memory transport)";
+        return ICPB_ERR_ARG;
+    }
     if (use_graph) {
         // ---- the whole loop as ONE graph launch: init -> WHILE(!done){search, trim, moments+pose} ----
         CK(ctx->cand_key.ensure(std::max<size_t>(n, 1)));
@@ -1469,6 +1484,25 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
     }
     CK(cudaMemcpyAsync(ctx->h_state, ctx->d_state, sizeof(IcpState), cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(ctx->ev_end, s));
+    ctx->run.launches0 = launches0;
+    ctx->run.use_graph = use_graph;
+    ctx->run.linear_ok = linear_ok;
+    ctx->run.n = n;
+    ctx->run.timed_iters = timed_iters;
+    ctx->run.pending = true;
+    return ICPB_OK;
+}
+
+static int align_collect(icpb_ctx *ctx, icpb_result *out)
+{
+    if (!ctx || !out || !ctx->run.pending) return ICPB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    ctx->run.pending = false;
+    cudaStream_t s = ctx->stream;
+    const unsigned long long launches0 = ctx->run.launches0;
+    const bool use_graph = ctx->run.use_graph, linear_ok = ctx->run.linear_ok;
+    const uint32_t n = ctx->run.n;
+    const size_t timed_iters = ctx->run.timed_iters;
     CK(cudaStreamSynchronize(s));
 
     const IcpState &hs = *ctx->h_state;
@@ -1517,6 +1551,14 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
         ctx->launches = launches0 + 1ull + (hs.executed + hs.redone > 0 ? 5ull + (linear_ok ? (fuse_moments_on(ctx, n) ? 2ull : 3ull) : 5ull) * (unsigned long long)(hs.executed + hs.redone - 1) : 0ull);
     ctx->timing.kernels_launched = ctx->launches - launches0;
     return ICPB_OK;
+}
+
+int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
+{
+    if (!ctx || !prm || !out) return ICPB_ERR_ARG;
+    int rc = align_enqueue(ctx, prm, false);
+    if (rc != ICPB_OK) return rc;
+    return align_collect(ctx, out);
 }
 
 int icpb_align(icpb_ctx *ctx, const double *xyz, size_t n, const double T[16], double density, const icpb_params *prm,
@@ -1852,6 +1894,209 @@ int icpb_comm_init(icpb_ctx *ctx, int n_ranks, int rank, const uint8_t id_in[ICP
     NK(g_nccl.CommInitRank(&ctx->comm, n_ranks, id, rank));
     ctx->n_ranks = n_ranks;
     ctx->rank = rank;
+    return ICPB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Several GPUs in ONE process (icpb_create(ctx, device_ids, n_devices)): one context per device, the
+// exchange buffers reached through cudaDeviceEnablePeerAccess instead of IPC handles, the same fused exchanges.
+// The source is sharded into contiguous ranges of the adapter's visiting order, the model is replicated.
+// ---------------------------------------------------------------------------
+struct icpb_multi {
+    std::vector<icpb_ctx *> ctx;
+    std::vector<double> stage; // density-stepped source (host)
+    std::string err;
+};
+
+static int multi_fail(icpb_multi *m, int i, int rc)
+{
+    m->err = "device " + std::to_string(m->ctx[i]->device) + ": " + icpb_strerror(rc) + " / " + m->ctx[i]->err;
+    return rc;
+}
+
+int icpb_create_multi(icpb_multi **out, const int *device_ids, int n_devices)
+{
+    if (!out || !device_ids || n_devices < 1 || n_devices > P2P_MAX_RANKS) return ICPB_ERR_ARG;
+    *out = nullptr;
+    for (int i = 0; i < n_devices; ++i)
+        for (int j = 0; j < i; ++j)
+            if (device_ids[i] == device_ids[j]) return ICPB_ERR_ARG;
+    icpb_multi *m = new (std::nothrow) icpb_multi;
+    if (!m) return ICPB_ERR_CUDA;
+    *out = m; // handed out even on failure, for icpb_multi_last_error; the caller destroys it
+    for (int i = 0; i < n_devices; ++i) {
+        icpb_ctx *c = nullptr;
+        const int rc = icpb_create(&c, device_ids[i]);
+        if (c) m->ctx.push_back(c);
+        if (rc != ICPB_OK) {
+            m->err = "device " + std::to_string(device_ids[i]) + ": " + icpb_strerror(rc) + (c ? " / " + c->err : std::string());
+            return rc;
+        }
+    }
+    if (n_devices == 1) return ICPB_OK;
+    for (int i = 0; i < n_devices; ++i) {
+        icpb_ctx *c = m->ctx[i];
+        if (cudaSetDevice(c->device) != cudaSuccess) return ICPB_ERR_CUDA;
+        for (int j = 0; j < n_devices; ++j) {
+            if (j == i) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, c->device, device_ids[j]);
+            if (!can) {
+                m->err = "device " + std::to_string(c->device) + " cannot map the memory of device " + std::to_string(device_ids[j]);
+                return ICPB_ERR_CUDA;
+            }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(device_ids[j], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                m->err = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e);
+                return ICPB_ERR_CUDA;
+            }
+            cudaGetLastError();
+        }
+        if (cudaMalloc((void **)&c->p2p_local, P2P_BUFFER_WORDS * sizeof(uint32_t)) != cudaSuccess ||
+            cudaMemset(c->p2p_local, 0, P2P_BUFFER_WORDS * sizeof(uint32_t)) != cudaSuccess ||
+            cudaDeviceSynchronize() != cudaSuccess) {
+            m->err = "exchange buffer allocation failed";
+            return ICPB_ERR_CUDA;
+        }
+    }
+    for (int i = 0; i < n_devices; ++i) {
+        icpb_ctx *c = m->ctx[i];
+        memset(&c->p2p, 0, sizeof(c->p2p));
+        c->p2p.world = n_devices;
+        c->p2p.rank = i;
+        for (int j = 0; j < n_devices; ++j) c->p2p.peer[j] = m->ctx[j]->p2p_local;
+        c->n_ranks = n_devices;
+        c->rank = i;
+        c->use_p2p = true;
+    }
+    return ICPB_OK;
+}
+
+void icpb_destroy_multi(icpb_multi *m)
+{
+    if (!m) return;
+    for (icpb_ctx *c : m->ctx) icpb_destroy(c);
+    delete m;
+}
+
+const char *icpb_multi_last_error(const icpb_multi *m) { return m ? m->err.c_str() : ""; }
+int icpb_multi_size(const icpb_multi *m) { return m ? (int)m->ctx.size() : 0; }
+icpb_ctx *icpb_multi_context(icpb_multi *m, int i) { return (m && i >= 0 && i < (int)m->ctx.size()) ? m->ctx[i] : nullptr; }
+
+int icpb_multi_set_option(icpb_multi *m, const char *key, double value)
+{
+    if (!m) return ICPB_ERR_ARG;
+    for (size_t i = 0; i < m->ctx.size(); ++i) {
+        const int rc = icpb_set_option(m->ctx[i], key, value);
+        if (rc != ICPB_OK) return multi_fail(m, (int)i, rc);
+    }
+    return ICPB_OK;
+}
+
+int icpb_multi_model_add(icpb_multi *m, const double *xyz, size_t n, const double T[16], double density)
+{
+    if (!m) return ICPB_ERR_ARG;
+    for (size_t i = 0; i < m->ctx.size(); ++i) {
+        const int rc = icpb_model_add(m->ctx[i], xyz, n, T, density);
+        if (rc != ICPB_OK) return multi_fail(m, (int)i, rc);
+    }
+    return ICPB_OK;
+}
+
+int icpb_multi_model_clear(icpb_multi *m)
+{
+    if (!m) return ICPB_ERR_ARG;
+    for (size_t i = 0; i < m->ctx.size(); ++i) {
+        const int rc = icpb_model_clear(m->ctx[i]);
+        if (rc != ICPB_OK) return multi_fail(m, (int)i, rc);
+    }
+    return ICPB_OK;
+}
+
+int icpb_multi_source_upload(icpb_multi *m, const double *xyz, size_t n, const double T[16], double density)
+{
+    if (!m || (!xyz && n) || !T || !(density > 0.0)) return ICPB_ERR_ARG;
+    size_t visited = 0;
+    const double *src = density_gather(xyz, n, density, m->stage, &visited);
+    const size_t adapter_size = (size_t)((double)n * density); // PointcloudAdapter::size() (icp/icp.hpp:143-146)
+    const size_t world = m->ctx.size(), base = visited / world, rem = visited % world;
+    for (size_t r = 0; r < world; ++r) { // contiguous ranges: ties at the trim threshold are kept in global pair order
+        const size_t lo = r * base + std::min(r, rem), cnt = base + (r < rem ? 1 : 0);
+        const int rc = world == 1 ? icpb_source_upload(m->ctx[r], xyz, n, T, density)
+                                  : icpb_source_upload_shard(m->ctx[r], src + 3 * lo, cnt, adapter_size, T);
+        if (rc != ICPB_OK) return multi_fail(m, (int)r, rc);
+    }
+    return ICPB_OK;
+}
+
+int icpb_multi_align_resident(icpb_multi *m, const icpb_params *prm, icpb_result *out)
+{
+    if (!m || !prm || !out) return ICPB_ERR_ARG;
+    const size_t world = m->ctx.size();
+    if (world == 1) {
+        const int rc = icpb_align_resident(m->ctx[0], prm, out);
+        return rc == ICPB_OK ? rc : multi_fail(m, 0, rc);
+    }
+    // every device gets its whole loop (one graph launch) before any is waited for: the ranks meet inside the kernels
+    int first_rc = ICPB_OK;
+    size_t launched = 0;
+    for (; launched < world; ++launched) {
+        const int rc = align_enqueue(m->ctx[launched], prm, true);
+        if (rc != ICPB_OK) {
+            first_rc = multi_fail(m, (int)launched, rc);
+            break;
+        }
+    }
+    icpb_result r0;
+    memset(&r0, 0, sizeof(r0));
+    for (size_t r = 0; r < launched; ++r) { // ranks already running give up on a missing peer after their spin budget
+        icpb_result rr;
+        const int rc = align_collect(m->ctx[r], &rr);
+        if (rc != ICPB_OK && first_rc == ICPB_OK) first_rc = multi_fail(m, (int)r, rc);
+        if (r == 0) r0 = rr;
+    }
+    if (first_rc != ICPB_OK) return first_rc;
+    *out = r0; // every rank ends with the same pose, pair count and error
+    return ICPB_OK;
+}
+
+int icpb_multi_align(icpb_multi *m, const double *xyz, size_t n, const double T[16], double density, const icpb_params *prm,
+                     icpb_result *out)
+{
+    const int rc = icpb_multi_source_upload(m, xyz, n, T, density);
+    if (rc != ICPB_OK) return rc;
+    return icpb_multi_align_resident(m, prm, out);
+}
+
+int icpb_multi_pairs_distance(icpb_multi *m, double *out_sorted, size_t capacity, size_t *n_out)
+{
+    if (!m || !n_out) return ICPB_ERR_ARG;
+    const size_t world = m->ctx.size();
+    if (world == 1) {
+        const int rc = icpb_pairs_distance(m->ctx[0], out_sorted, capacity, n_out);
+        return rc == ICPB_OK ? rc : multi_fail(m, 0, rc);
+    }
+    size_t total = 0;
+    {
+        const int rc = icpb_pairs_distance(m->ctx[0], nullptr, 0, &total); // the count of all ranks' kept pairs
+        if (rc != ICPB_OK) return multi_fail(m, 0, rc);
+    }
+    *n_out = total;
+    if (!out_sorted) return ICPB_OK;
+    if (capacity < total) return ICPB_ERR_CAPACITY;
+    std::vector<double> part(total), merged;
+    size_t have = 0;
+    for (size_t r = 0; r < world; ++r) { // every rank: the kept distances of its shard, ascending; merged on the host
+        size_t k = 0;
+        const int rc = icpb_pairs_distance(m->ctx[r], part.data(), total, &k);
+        if (rc != ICPB_OK) return multi_fail(m, (int)r, rc);
+        merged.resize(have + k);
+        std::merge(out_sorted, out_sorted + have, part.data(), part.data() + k, merged.begin());
+        have += k;
+        if (have > total) return ICPB_ERR_CUDA;
+        std::copy(merged.begin(), merged.end(), out_sorted);
+    }
+    *n_out = have;
     return ICPB_OK;
 }
 

@@ -27,6 +27,7 @@
 #include <limits>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/icp_b200.h"
@@ -241,7 +242,7 @@ template <class _Adapter> class TrimmedGPUT {
     };
 
 public:
-    explicit TrimmedGPUT(int device = 0) : ctx_(0)
+    explicit TrimmedGPUT(int device = 0) : ctx_(0), multi_(0)
     {
         const int rc = icpb_create(&ctx_, device);
         if (rc != ICPB_OK) {
@@ -250,7 +251,27 @@ public:
             throw std::runtime_error(msg);
         }
     }
-    ~TrimmedGPUT() { if (ctx_) icpb_destroy(ctx_); }
+    /** several GPUs of one NVLink box, this one process: devices first_device .. first_device + n_devices - 1; the
+     * measurement is sharded over them, the model replicated (icpb_create_multi).  Plain adapter only. */
+    TrimmedGPUT(int first_device, int n_devices) : ctx_(0), multi_(0)
+    {
+        static_assert(std::is_same<_Adapter, PointcloudAdapter>::value, "several devices: plain PointcloudAdapter only");
+        std::vector<int> ids;
+        for (int i = 0; i < n_devices; ++i) ids.push_back(first_device + i);
+        const int rc = icpb_create_multi(&multi_, ids.data(), n_devices);
+        if (rc != ICPB_OK) {
+            const std::string msg = std::string("TrimmedGPU: ") + icpb_strerror(rc) + " / " + icpb_multi_last_error(multi_);
+            icpb_destroy_multi(multi_);
+            multi_ = 0;
+            throw std::runtime_error(msg);
+        }
+        ctx_ = icpb_multi_context(multi_, 0);
+    }
+    ~TrimmedGPUT()
+    {
+        if (multi_) icpb_destroy_multi(multi_);
+        else if (ctx_) icpb_destroy(ctx_);
+    }
     TrimmedGPUT(const TrimmedGPUT &) = delete;
     TrimmedGPUT &operator=(const TrimmedGPUT &) = delete;
 
@@ -276,12 +297,13 @@ public:
         fetchPairsDistance(minResult_); // the kept distances of the last align live in device scratch: secure them first
         double T[16];
         toColMajor(model.local2global(), T);
-        check(detail::modelAdd(ctx_, model, T));
+        if (multi_) check(icpb_multi_model_add(multi_, model.vertexData(), model.vertexCount(), T, model.density()));
+        else check(detail::modelAdd(ctx_, model, T));
     }
     void clearModel()
     {
         fetchPairsDistance(minResult_);
-        check(icpb_model_clear(ctx_));
+        check(multi_ ? icpb_multi_model_clear(multi_) : icpb_model_clear(ctx_));
     }
 
     size_t getNumIterations() { return minResult_.iter; }
@@ -296,12 +318,13 @@ public:
     }
 
     /** GPU-only knobs (cell size, warm start, ...): see icpb_set_option */
-    void setOption(const char *key, double value) { check(icpb_set_option(ctx_, key, value)); }
-    icpb_ctx *handle() { return ctx_; }
+    void setOption(const char *key, double value) { check(multi_ ? icpb_multi_set_option(multi_, key, value) : icpb_set_option(ctx_, key, value)); }
+    icpb_ctx *handle() { return ctx_; } // several devices: the first device's context
     const Eigen::Affine3d &getTransform() const { return minResult_.C_global2globalnew; }
 
 private:
     icpb_ctx *ctx_;
+    icpb_multi *multi_; // several devices in this process (ctx_ then is the first device's context, owned by multi_)
     Result minResult_;
     bool pd_pending_ = false;
 
@@ -315,7 +338,8 @@ private:
     }
     void check(int rc)
     {
-        if (rc != ICPB_OK) throw std::runtime_error(std::string("TrimmedGPU: ") + icpb_strerror(rc) + " / " + icpb_last_error(ctx_));
+        if (rc != ICPB_OK)
+            throw std::runtime_error(std::string("TrimmedGPU: ") + icpb_strerror(rc) + " / " + (multi_ ? icpb_multi_last_error(multi_) : icpb_last_error(ctx_)));
     }
     static void toColMajor(const Eigen::Affine3d &a, double T[16])
     {
@@ -327,7 +351,8 @@ private:
     {
         double T[16];
         toColMajor(meas.local2global(), T);
-        check(detail::sourceUpload(ctx_, meas, T));
+        if (multi_) check(icpb_multi_source_upload(multi_, meas.vertexData(), meas.vertexCount(), T, meas.density()));
+        else check(detail::sourceUpload(ctx_, meas, T));
     }
     Result alignResident(size_t max_iter, double min_mse, double min_mse_diff, double overlap, bool eager_pairs)
     {
@@ -337,7 +362,7 @@ private:
         prm.min_mse_diff = min_mse_diff;
         prm.overlap = overlap;
         icpb_result r;
-        check(icpb_align_resident(ctx_, &prm, &r));
+        check(multi_ ? icpb_multi_align_resident(multi_, &prm, &r) : icpb_align_resident(ctx_, &prm, &r));
         Result out;
         Eigen::Matrix4d m;
         for (int c = 0; c < 4; ++c)
@@ -358,9 +383,10 @@ private:
     {
         if (!pd_pending_) return;
         size_t n = 0;
-        check(icpb_pairs_distance(ctx_, 0, 0, &n));
+        check(multi_ ? icpb_multi_pairs_distance(multi_, 0, 0, &n) : icpb_pairs_distance(ctx_, 0, 0, &n));
         res.pairs_distance.resize(n);
-        if (n) check(icpb_pairs_distance(ctx_, res.pairs_distance.data(), n, &n));
+        if (n) check(multi_ ? icpb_multi_pairs_distance(multi_, res.pairs_distance.data(), n, &n) : icpb_pairs_distance(ctx_, res.pairs_distance.data(), n, &n));
+        res.pairs_distance.resize(n);
         pd_pending_ = false;
     }
 };

@@ -1,6 +1,7 @@
 // icp_gpu_cli.cpp -- runs envire::icp::TrimmedGPU (the C++ host mirror) the way the reference's own unit test
 // drives TrimmedKD (test/unit/icp.cpp:95-159): Environment + two FrameNodes + two Pointclouds, addToModel, align.
-// Prints one JSON object; tests/test_gpu_host_mirror.py compares it with tests/golden/golden.json.
+// Prints one JSON object; tests/test_gpu_golden.py compares it with tests/golden/golden.json.
+// ICP_B200_DEVICES=N in the environment: N GPUs in this one process (tests/test_multi_gpu.py).
 //   icp_gpu_cli <model.bin> <src.bin> <T_src 16 col-major numbers> <density> fixed <max_iter> <min_mse> <min_mse_diff> <overlap>
 //   icp_gpu_cli <model.bin> <src.bin> <T_src ...>                  <density> golden <max_iter> <min_mse> <min_mse_diff> <alpha> <beta> <eps>
 // .bin = raw little-endian doubles, xyz triples.
@@ -110,7 +111,11 @@ int main(int argc, char **argv)
         return 0;
     }
     try {
-        envire::icp::TrimmedGPU icp;
+        // ICP_B200_DEVICES=N: TrimmedGPU(0, N) -- N GPUs in this one process (N = 1: the same entry points, one device)
+        const char *nd = getenv("ICP_B200_DEVICES");
+        std::unique_ptr<envire::icp::TrimmedGPU> owner(nd && atoi(nd) >= 1 ? new envire::icp::TrimmedGPU(0, atoi(nd))
+                                                                           : new envire::icp::TrimmedGPU());
+        envire::icp::TrimmedGPU &icp = *owner;
         icp.addToModel(envire::icp::PointcloudAdapter(mesh, 1.0));
         if (golden)
             icp.align(envire::icp::PointcloudAdapter(mesh2, density), max_iter, min_mse, min_mse_diff, atof(argv[24]), atof(argv[25]), atof(argv[26]));

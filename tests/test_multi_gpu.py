@@ -27,6 +27,78 @@ def test_sharded_align_matches_single_gpu(mode):
     assert "MULTI_GPU_CHECK PASS" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
 
 
+def _cli_run(exe, tmp_path, model, src, kind, prm, devices, density=1.0):
+    import json
+    mp, sp = str(tmp_path / "m.bin"), str(tmp_path / "s.bin")
+    np.ascontiguousarray(model, dtype=np.float64).tofile(mp)
+    np.ascontiguousarray(src, dtype=np.float64).tofile(sp)
+    args = [exe, mp, sp] + ["%.17g" % v for v in np.eye(4).reshape(16)] + ["%.17g" % density, kind, str(prm["max_iter"]),
+                                                                           "%.17g" % prm["min_mse"], "%.17g" % prm["min_mse_diff"]]
+    args += ["%.17g" % prm[k] for k in (("alpha", "beta", "eps") if kind == "golden" else ("overlap",))]
+    env = dict(os.environ)
+    env.pop("ICP_B200_DEVICES", None)
+    if devices is not None:
+        env["ICP_B200_DEVICES"] = str(devices)
+    out = json.loads(subprocess.check_output(args, env=env, timeout=600).decode())
+    assert "error" not in out, out
+    return out
+
+
+def _same_align(a, b, extent):
+    from conftest import assert_transform_close
+    assert a["iter"] == b["iter"] and a["pairs"] == b["pairs"] and a["n_pairs_distance"] == b["n_pairs_distance"]
+    assert_transform_close(np.array(a["fn_T"]), np.array(b["fn_T"]), extent)
+    assert abs(a["mse"] - b["mse"]) <= 1e-9 * abs(b["mse"]) + 1e-300
+    assert a["pd_sorted"] and abs(a["pd_sum"] - b["pd_sum"]) <= 1e-9 * abs(b["pd_sum"]) + 1e-12
+    assert abs(a["pd_last"] - b["pd_last"]) <= 1e-12 * abs(b["pd_last"]) + 1e-300
+
+
+@pytest.fixture(scope="module")
+def cli():
+    src = os.path.join(ROOT, "tests", "cpp", "icp_gpu_cli.cpp")
+    exe = os.path.join(ROOT, "tests", "cpp", "icp_gpu_cli")
+    pk = os.path.join(ROOT, "slam-envire_b200")
+    deps = [src, os.path.join(pk, "icp", "icp_gpu.hpp"), os.path.join(pk, "compat", "Eigen", "mini_eigen.hpp"),
+            os.path.join(pk, "libicp_b200.so")]
+    if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I" + pk, "-I" + os.path.join(pk, "compat"),
+                               "-o", exe, src, "-L" + pk, "-licp_b200", "-Wl,-rpath," + pk])
+    return exe
+
+
+@pytest.mark.gpu
+def test_one_process_entry_points_on_one_device(cli, tmp_path):
+    """TrimmedGPU(0, 1): the several-GPUs-in-one-process entry points (icpb_create_multi ...) with a single device must
+    give exactly what the plain context gives."""
+    synth = importlib.import_module("slam-envire_b200.synth")
+    m, s, T, prm = synth.config("cfg1", 0.2)
+    prm = dict(prm, max_iter=20)
+    a = _cli_run(cli, tmp_path, m, s, "fixed", prm, None, density=0.5)
+    b = _cli_run(cli, tmp_path, m, s, "fixed", prm, 1, density=0.5)
+    assert a == b
+
+
+@pytest.mark.gpu
+def test_one_process_two_gpus_matches_single_gpu(cli, tmp_path):
+    """envire::icp::TrimmedGPU(0, 2) -- two GPUs, ONE process, peers mapped with cudaDeviceEnablePeerAccess, the same
+    fused exchanges -- against TrimmedGPU on one GPU: a cfg3-shaped case (half of the source replaced, overlap 0.5), a
+    density-stepped source, and the golden-section overlap search (several aligns on one upload)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    synth = importlib.import_module("slam-envire_b200.synth")
+    m = synth.scene(200_000, 60.0, 4)
+    s, T = synth.perturbed_copy(m, 1.0, 0.3, 0.01, seed=5, replace_frac=0.5, extent=60.0)
+    prm = dict(max_iter=25, min_mse=1e-10, min_mse_diff=1e-9, overlap=0.5)
+    _same_align(_cli_run(cli, tmp_path, m, s, "fixed", prm, 2), _cli_run(cli, tmp_path, m, s, "fixed", prm, None), 60.0)
+    _same_align(_cli_run(cli, tmp_path, m, s, "fixed", prm, 2, density=0.37), _cli_run(cli, tmp_path, m, s, "fixed", prm, None, density=0.37), 60.0)
+    m1, s1, T1, p1 = synth.config("cfg1", 0.2)
+    g = dict(max_iter=15, min_mse=1e-10, min_mse_diff=1e-12, alpha=0.5, beta=1.0, eps=0.05)
+    a, b = _cli_run(cli, tmp_path, m1, s1, "golden", g, 2), _cli_run(cli, tmp_path, m1, s1, "golden", g, None)
+    assert abs(a["overlap"] - b["overlap"]) < 1e-12
+    _same_align(a, b, 20.0)
+
+
 def test_shard_bounds_and_density():
     sh = importlib.import_module("slam-envire_b200.sharding")
     from oracle import oracle as O
