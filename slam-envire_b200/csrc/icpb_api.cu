@@ -248,6 +248,10 @@ struct icpb_ctx {
     IcpState *h_state = nullptr; // pinned
     int *h_flags = nullptr;      // pinned
     uint32_t *d_ghist = nullptr;
+    bool upload_pending = false; // source copies enqueued, not waited for yet
+    DensitySeg h_dseg[ICPB_DENSITY_MAX_SEGS];
+    DevBuf<DensitySeg> d_dseg;
+    DevBuf<double> stage_full; // the whole host array of a density-stepped upload (the visited vertices are gathered from it)
     struct { // between align_enqueue and align_collect
         unsigned long long launches0 = 0;
         bool use_graph = false, linear_ok = false, pending = false;
@@ -269,7 +273,7 @@ struct icpb_ctx {
     DevBuf<uint8_t> dbg_kept;
     // timing
     std::vector<cudaEvent_t> events;
-    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_up0 = nullptr, ev_up1 = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_up0 = nullptr, ev_up1 = nullptr, ev_b0 = nullptr, ev_b1 = nullptr;
     std::vector<cudaEvent_t> ring;
     icpb_timing timing;
     std::vector<double> iter_ms;
@@ -379,6 +383,8 @@ int icpb_create(icpb_ctx **out, int device_id)
     CK(cudaEventCreate(&ctx->ev_begin));
     CK(cudaEventCreate(&ctx->ev_end));
     CK(cudaEventCreate(&ctx->ev_up0));
+    CK(cudaEventCreate(&ctx->ev_b0));
+    CK(cudaEventCreate(&ctx->ev_b1));
     CK(cudaEventCreate(&ctx->ev_up1));
     ctx->ring.resize(64);
     for (auto &e : ctx->ring) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -457,6 +463,8 @@ void icpb_destroy(icpb_ctx *ctx)
     if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
     if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
     if (ctx->ev_up0) cudaEventDestroy(ctx->ev_up0);
+    if (ctx->ev_b0) cudaEventDestroy(ctx->ev_b0);
+    if (ctx->ev_b1) cudaEventDestroy(ctx->ev_b1);
     if (ctx->ev_up1) cudaEventDestroy(ctx->ev_up1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -509,6 +517,7 @@ int icpb_get_option(const icpb_ctx *ctx, const char *key, double *value)
 // model
 // ---------------------------------------------------------------------------
 static int update_masks(icpb_ctx *ctx, const uint32_t *keys, size_t k);
+static int stage_visited(icpb_ctx *ctx, const double *xyz, size_t n, double density, size_t *m_out);
 
 // Growing model: merge a freshly appended batch (model_raw[n_old, n_old + k)) into the existing index in one
 // streaming pass instead of re-sorting everything.  Falls back (returns with *done == false) when there is no
@@ -540,7 +549,7 @@ static int try_merge_append(icpb_ctx *ctx, size_t n_old, size_t k, bool *done)
     }
     const size_t ncell = (size_t)g.dim[0][0] * g.dim[0][1] * g.dim[0][2];
     pm.mark("bbox");
-    cudaEvent_t e0 = ctx->ev_up0, e1 = ctx->ev_up1;
+    cudaEvent_t e0 = ctx->ev_b0, e1 = ctx->ev_b1;
     CK(cudaEventRecord(e0, s));
     CK(ctx->keys0.ensure(k));
     CK(ctx->keys1.ensure(k));
@@ -616,20 +625,20 @@ static int model_add(icpb_ctx *ctx, const double *xyz, const double *normals, co
     const bool ean = normals != nullptr;
     if (ean && !attrs) return ICPB_ERR_ARG;
     if (ctx->model_n > 0 && ean != ctx->model_ean) return ICPB_ERR_ARG; // all plain or all edge-and-normal
-    std::vector<double> tmp;
     size_t m = 0;
-    const double *src = density_gather(xyz, n, density, tmp, &m);
+    {
+        int rc = stage_visited(ctx, xyz, n, density, &m); // K0: the visited vertices, gathered on the device
+        if (rc != ICPB_OK) return rc;
+    }
     if (m == 0) return ICPB_OK;
     if (ctx->model_n + m >= 0xFFFFFFF0ull) return ICPB_ERR_ARG;
-    CK(ctx->stage.ensure(3 * m));
     CK(ctx->model_raw.ensure_keep(3 * (ctx->model_n + m), 3 * ctx->model_n, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->stage.p, src, 3 * m * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     Aff12 A;
     cm_to_aff12(T, A.a);
     transform_append_kernel<<<grid_for(m, 256), 256, 0, ctx->stream>>>(ctx->stage.p, m, A,
                                                                        ctx->model_raw.p + 3 * ctx->model_n);
     CKL();
-    CK(cudaStreamSynchronize(ctx->stream)); // tmp / caller buffer may go away
+    CK(cudaStreamSynchronize(ctx->stream)); // the caller's buffer may go away
     if (ean) {
         std::vector<double> tn;
         std::vector<int32_t> ta;
@@ -776,7 +785,7 @@ static int build_grid(icpb_ctx *ctx)
         return ICPB_OK;
     }
     PhaseMarks pm("build", s);
-    cudaEvent_t e0 = ctx->ev_up0, e1 = ctx->ev_up1;
+    cudaEvent_t e0 = ctx->ev_b0, e1 = ctx->ev_b1;
     CK(cudaEventRecord(e0, s));
     // bounding box
     const unsigned nbb = std::min<unsigned>(1024u, grid_for(n, 256));
@@ -971,12 +980,65 @@ int icpb_model_build(icpb_ctx *ctx, icpb_grid_info *info)
 // ---------------------------------------------------------------------------
 // source
 // ---------------------------------------------------------------------------
-static int upload_points(icpb_ctx *ctx, const double *src, size_t m)
+// the caller's host buffer may go away after an upload call returns: wait for the copies (icpb_align waits once, at the
+// end of the align)
+static int upload_wait(icpb_ctx *ctx)
+{
+    if (!ctx->upload_pending) return ICPB_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev_up0, ctx->ev_up1);
+    ctx->timing.upload_ms = ms;
+    ctx->upload_pending = false;
+    return ICPB_OK;
+}
+
+// Host vertices -> stage (device AoS) in PointcloudAdapter's visiting order (K0).  density != 1: the whole array is
+// copied and the visited vertices are gathered ON THE DEVICE from the closed form of the density stepping (density.h);
+// absurd densities (more segments than the table holds) fall back to the host loop.  *m_out = visited vertices.
+static int stage_visited(icpb_ctx *ctx, const double *xyz, size_t n, double density, size_t *m_out)
+{
+    cudaStream_t s = ctx->stream;
+    if (density == 1.0 || n == 0) {
+        CK(ctx->stage.ensure(3 * std::max<size_t>(n, 1)));
+        if (n) CK(cudaMemcpyAsync(ctx->stage.p, xyz, 3 * n * sizeof(double), cudaMemcpyHostToDevice, s));
+        *m_out = n;
+        return ICPB_OK;
+    }
+    unsigned long long visited = 0;
+    const int ns = icpb_density_segments(n, density, ctx->h_dseg, ICPB_DENSITY_MAX_SEGS, &visited);
+    if (ns < 0) {
+        std::vector<double> tmp;
+        size_t m = 0;
+        const double *src = density_gather(xyz, n, density, tmp, &m);
+        CK(ctx->stage.ensure(3 * std::max<size_t>(m, 1)));
+        if (m) CK(cudaMemcpyAsync(ctx->stage.p, src, 3 * m * sizeof(double), cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s)); // tmp goes away
+        *m_out = m;
+        return ICPB_OK;
+    }
+    const size_t m = (size_t)visited;
+    CK(ctx->stage_full.ensure(3 * n));
+    CK(ctx->stage.ensure(3 * std::max<size_t>(m, 1)));
+    CK(ctx->d_dseg.ensure(ICPB_DENSITY_MAX_SEGS));
+    CK(cudaMemcpyAsync(ctx->stage_full.p, xyz, 3 * n * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->d_dseg.p, ctx->h_dseg, (size_t)std::max(ns, 1) * sizeof(DensitySeg), cudaMemcpyHostToDevice, s));
+    if (m) {
+        density_gather_kernel<<<grid_for(m, 256), 256, 0, s>>>(ctx->stage_full.p, ctx->d_dseg.p, ns, visited, ctx->stage.p);
+        CKL();
+        ++ctx->launches;
+    }
+    *m_out = m;
+    return ICPB_OK;
+}
+
+// stage (m vertices, device AoS, visiting order) -> the resident source: Morton order of the source in its own frame
+// (rigid motions keep neighbours together, so one sort per upload serves every loop body; src_perm[] maps back to the
+// visiting order), SoA coordinates.  Nothing is read back: the bounding box stays on the device.
+static int upload_points(icpb_ctx *ctx, size_t m, bool wait)
 {
     cudaStream_t s = ctx->stream;
     if (m >= 0xFFFFFFF0ull) return ICPB_ERR_ARG;
-    CK(cudaEventRecord(ctx->ev_up0, s));
-    CK(ctx->stage.ensure(3 * std::max<size_t>(m, 1)));
     CK(ctx->sx.ensure(std::max<size_t>(m, 1)));
     CK(ctx->sy.ensure(std::max<size_t>(m, 1)));
     CK(ctx->sz.ensure(std::max<size_t>(m, 1)));
@@ -985,32 +1047,18 @@ static int upload_points(icpb_ctx *ctx, const double *src, size_t m)
     CK(ctx->nn_lb.ensure(std::max<size_t>(m, 1)));
     CK(ctx->src_perm.ensure(std::max<size_t>(m, 1)));
     if (m) {
-        CK(cudaMemcpyAsync(ctx->stage.p, src, 3 * m * sizeof(double), cudaMemcpyHostToDevice, s));
         if (ctx->opt_sort != 0.0 && m > 1024) {
-            // Morton order of the source in its own frame: rigid motions keep neighbours together, so one
-            // sort per upload serves every iteration.  src_perm[] maps back to the adapter's visiting order.
             const unsigned nbb = std::min<unsigned>(1024u, grid_for(m, 256));
-            CK(ctx->bbox_part.ensure((size_t)nbb * 6));
-            bbox_kernel<<<nbb, 256, 0, s>>>(ctx->stage.p, m, ctx->bbox_part.p);
-            CKL();
-            std::vector<double> hb((size_t)nbb * 6);
-            CK(cudaMemcpyAsync(hb.data(), ctx->bbox_part.p, hb.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
-            CK(cudaStreamSynchronize(s));
-            double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-            for (unsigned b = 0; b < nbb; ++b)
-                for (int a = 0; a < 3; ++a) {
-                    mn[a] = fmin(mn[a], hb[(size_t)b * 6 + a]);
-                    mx[a] = fmax(mx[a], hb[(size_t)b * 6 + 3 + a]);
-                }
-            double ext = fmax(fmax(mx[0] - mn[0], mx[1] - mn[1]), mx[2] - mn[2]);
-            if (!(ext > 0.0) || !isfinite(ext)) ext = 1.0;
+            CK(ctx->bbox_part.ensure((size_t)nbb * 6 + 8));
             CK(ctx->keys0.ensure(m));
             CK(ctx->keys1.ensure(m));
             CK(ctx->vals0.ensure(m));
             CK(ctx->vals1.ensure(m));
             CK(ctx->sort_scratch.ensure(rs_scratch_elems(m)));
-            morton_keys_kernel<<<grid_for(m, 256), 256, 0, s>>>(ctx->stage.p, (uint32_t)m, mn[0], mn[1], mn[2],
-                                                               1023.999 / ext, ctx->keys0.p, ctx->vals0.p);
+            double *bb = ctx->bbox_part.p + (size_t)nbb * 6;
+            bbox_kernel<<<nbb, 256, 0, s>>>(ctx->stage.p, m, ctx->bbox_part.p);
+            bbox_final_kernel<<<1, 256, 0, s>>>(ctx->bbox_part.p, nbb, bb);
+            morton_keys_kernel<<<grid_for(m, 256), 256, 0, s>>>(ctx->stage.p, (uint32_t)m, bb, ctx->keys0.p, ctx->vals0.p);
             CKL();
             const int w = radix_sort<uint32_t, true>(ctx->keys0.p, ctx->vals0.p, ctx->keys1.p, ctx->vals1.p, m, 30,
                                                      ctx->sort_scratch.p, s, &ctx->launches);
@@ -1020,7 +1068,7 @@ static int upload_points(icpb_ctx *ctx, const double *src, size_t m)
             gather_soa_kernel<<<grid_for(m, 256), 256, 0, s>>>(ctx->stage.p, ctx->src_perm.p, (uint32_t)m, ctx->sx.p,
                                                               ctx->sy.p, ctx->sz.p);
             CKL();
-            ctx->launches += 3;
+            ctx->launches += 4;
         } else {
             aos_to_soa_kernel<<<grid_for(m, 256), 256, 0, s>>>(ctx->stage.p, m, ctx->sx.p, ctx->sy.p, ctx->sz.p);
             iota_kernel<<<grid_for(m, 256), 256, 0, s>>>(ctx->src_perm.p, (uint32_t)m);
@@ -1029,27 +1077,31 @@ static int upload_points(icpb_ctx *ctx, const double *src, size_t m)
         }
     }
     CK(cudaEventRecord(ctx->ev_up1, s));
-    CK(cudaStreamSynchronize(s));
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, ctx->ev_up0, ctx->ev_up1);
-    ctx->timing.upload_ms = ms;
     ctx->src_n = m;
     ctx->have_source = true;
     ctx->src_ean = false;
     ctx->last_valid = false;
+    ctx->upload_pending = true;
+    if (wait) return upload_wait(ctx);
     return ICPB_OK;
+}
+
+static int source_upload(icpb_ctx *ctx, const double *xyz, size_t n, const double T[16], double density, bool wait)
+{
+    if (!ctx || (!xyz && n) || !T || !(density > 0.0)) return ICPB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->ev_up0, ctx->stream));
+    size_t m = 0;
+    int rc = stage_visited(ctx, xyz, n, density, &m);
+    if (rc != ICPB_OK) return rc;
+    cm_to_aff12(T, ctx->Cl2g);
+    ctx->adapter_size = (size_t)((double)n * density); // PointcloudAdapter::size() (icp/icp.hpp:143-146)
+    return upload_points(ctx, m, wait);
 }
 
 int icpb_source_upload(icpb_ctx *ctx, const double *xyz, size_t n, const double T[16], double density)
 {
-    if (!ctx || (!xyz && n) || !T || !(density > 0.0)) return ICPB_ERR_ARG;
-    CK(cudaSetDevice(ctx->device));
-    std::vector<double> tmp;
-    size_t m = 0;
-    const double *src = density_gather(xyz, n, density, tmp, &m);
-    cm_to_aff12(T, ctx->Cl2g);
-    ctx->adapter_size = (size_t)((double)n * density); // PointcloudAdapter::size() (icp/icp.hpp:143-146)
-    return upload_points(ctx, src, m);
+    return source_upload(ctx, xyz, n, T, density, true);
 }
 
 int icpb_source_upload_ean(icpb_ctx *ctx, const double *xyz, const double *normals, const int32_t *attrs, size_t n,
@@ -1092,7 +1144,11 @@ int icpb_source_upload_shard(icpb_ctx *ctx, const double *xyz, size_t n_local, s
     CK(cudaSetDevice(ctx->device));
     cm_to_aff12(T, ctx->Cl2g);
     ctx->adapter_size = adapter_size_global;
-    return upload_points(ctx, xyz, n_local);
+    CK(cudaEventRecord(ctx->ev_up0, ctx->stream));
+    size_t m = 0;
+    int rc = stage_visited(ctx, xyz, n_local, 1.0, &m);
+    if (rc != ICPB_OK) return rc;
+    return upload_points(ctx, m, true);
 }
 
 // ---------------------------------------------------------------------------
@@ -1564,9 +1620,14 @@ int icpb_align_resident(icpb_ctx *ctx, const icpb_params *prm, icpb_result *out)
 int icpb_align(icpb_ctx *ctx, const double *xyz, size_t n, const double T[16], double density, const icpb_params *prm,
                icpb_result *out)
 {
-    int rc = icpb_source_upload(ctx, xyz, n, T, density);
+    int rc = source_upload(ctx, xyz, n, T, density, false); // the align below waits once, for the copies too
     if (rc != ICPB_OK) return rc;
-    return icpb_align_resident(ctx, prm, out);
+    rc = icpb_align_resident(ctx, prm, out);
+    if (ctx->upload_pending) {
+        const int rw = upload_wait(ctx);
+        if (rc == ICPB_OK) rc = rw;
+    }
+    return rc;
 }
 
 int icpb_last_timing(const icpb_ctx *ctx, icpb_timing *out)

@@ -13,6 +13,7 @@
 #include <stdint.h>
 #include "grid_view.h"
 #include "pose.h"
+#include "density.h"
 
 namespace icpb {
 
@@ -1919,11 +1920,75 @@ __device__ __forceinline__ uint32_t spread10(uint32_t v)
     v = (v | (v << 2)) & 0x09249249u;
     return v;
 }
-__global__ void morton_keys_kernel(const double *__restrict__ aos, uint32_t n, double ox, double oy, double oz,
-                                   double inv, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
+// second stage of the bounding box, on the device: out[0..2] = min corner, out[3] = 1023.999 / largest extent (the
+// scale of the Morton keys) -- the upload path needs no trip to the host for it
+__global__ void __launch_bounds__(256) bbox_final_kernel(const double *__restrict__ part, unsigned nb, double *__restrict__ out)
+{
+    __shared__ double sm[8][6];
+    double mn[3] = {icpb_inf(), icpb_inf(), icpb_inf()}, mx[3] = {-icpb_inf(), -icpb_inf(), -icpb_inf()};
+    for (unsigned b = threadIdx.x; b < nb; b += blockDim.x)
+        for (int a = 0; a < 3; ++a) {
+            mn[a] = fmin(mn[a], part[(size_t)b * 6 + a]);
+            mx[a] = fmax(mx[a], part[(size_t)b * 6 + 3 + a]);
+        }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int a = 0; a < 3; ++a)
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[a] = fmin(mn[a], __shfl_xor_sync(0xFFFFFFFFu, mn[a], o));
+            mx[a] = fmax(mx[a], __shfl_xor_sync(0xFFFFFFFFu, mx[a], o));
+        }
+    if (lane == 0)
+        for (int a = 0; a < 3; ++a) {
+            sm[warp][a] = mn[a];
+            sm[warp][3 + a] = mx[a];
+        }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w)
+            for (int a = 0; a < 3; ++a) {
+                sm[0][a] = fmin(sm[0][a], sm[w][a]);
+                sm[0][3 + a] = fmax(sm[0][3 + a], sm[w][3 + a]);
+            }
+        double ext = fmax(fmax(sm[0][3] - sm[0][0], sm[0][4] - sm[0][1]), sm[0][5] - sm[0][2]);
+        if (!(ext > 0.0) || !(ext < icpb_inf())) ext = 1.0;
+        out[0] = sm[0][0];
+        out[1] = sm[0][1];
+        out[2] = sm[0][2];
+        out[3] = 1023.999 / ext;
+    }
+}
+// K0: the vertices PointcloudAdapter visits at this density (icp/icp.hpp:126-138), gathered in visiting order; the
+// visiting order in closed form: density.h
+__global__ void density_gather_kernel(const double *__restrict__ full, const DensitySeg *__restrict__ segs, int nseg,
+                                      unsigned long long m, double *__restrict__ out)
+{
+    __shared__ DensitySeg ss[64];
+    const int ns = nseg < 64 ? nseg : 64;
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) ss[i] = segs[i];
+    __syncthreads();
+    const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    const int si = icpb_density_find(nseg <= 64 ? ss : segs, nseg, k);
+    const unsigned long long i = icpb_density_index(nseg <= 64 ? ss[si] : segs[si], k);
+    out[3 * k] = full[3 * i];
+    out[3 * k + 1] = full[3 * i + 1];
+    out[3 * k + 2] = full[3 * i + 2];
+}
+// the same visiting order for a parallel per-vertex array of `width` 4-byte items
+__global__ void density_gather_u32_kernel(const uint32_t *__restrict__ full, const DensitySeg *__restrict__ segs, int nseg,
+                                          unsigned long long m, int width, uint32_t *__restrict__ out)
+{
+    const unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    const unsigned long long i = icpb_density_index(segs[icpb_density_find(segs, nseg, k)], k);
+    for (int w = 0; w < width; ++w) out[(size_t)width * k + w] = full[(size_t)width * i + w];
+}
+__global__ void morton_keys_kernel(const double *__restrict__ aos, uint32_t n, const double *__restrict__ bb,
+                                   uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const double ox = bb[0], oy = bb[1], oz = bb[2], inv = bb[3];
     const double fx = fmin(fmax((aos[3 * (size_t)i] - ox) * inv, 0.0), 1023.0);
     const double fy = fmin(fmax((aos[3 * (size_t)i + 1] - oy) * inv, 0.0), 1023.0);
     const double fz = fmin(fmax((aos[3 * (size_t)i + 2] - oz) * inv, 0.0), 1023.0);

@@ -48,7 +48,7 @@ class Harness:
     def __init__(self):
         src = os.path.join(ROOT, "tests", "harness", "cpu_harness.cpp")
         lib = os.path.join(ROOT, "tests", "harness", "libcpu_harness.so")
-        deps = [src] + [os.path.join(ROOT, "slam-envire_b200", "csrc", f) for f in ("grid_view.h", "pose.h")]
+        deps = [src] + [os.path.join(ROOT, "slam-envire_b200", "csrc", f) for f in ("grid_view.h", "pose.h", "density.h")]
         if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
             subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-o", lib, src])
         self.L = C.CDLL(lib)
@@ -68,6 +68,14 @@ class Harness:
                          C.c_double(d_box), self._p(w, C.c_uint32) if w is not None else None,
                          self._p(idx, C.c_uint32), self._p(d), self._p(lv, C.c_int))
         return idx, d, lv
+
+    def density_indices(self, n, density):
+        """(visited vertex indices, number of segments) from the closed form of the density stepping (csrc/density.h)."""
+        out = np.zeros(int(n * max(density, 1.0)) + 16, np.uint64)
+        ns = C.c_int()
+        self.L.hs_density_indices.restype = C.c_longlong
+        m = self.L.hs_density_indices(C.c_size_t(n), C.c_double(density), self._p(out, C.c_uint64), C.c_size_t(len(out)), C.byref(ns))
+        return (out[:m].astype(np.int64) if m >= 0 else None), ns.value
 
     def transform_from_sums(self, sums):
         s = np.ascontiguousarray(sums, dtype=np.float64)

@@ -18,6 +18,7 @@ static HsCounters g_cnt;
 #define ICPB_COUNT(what) (++g_cnt.what)
 #include "../../slam-envire_b200/csrc/grid_view.h"
 #include "../../slam-envire_b200/csrc/pose.h"
+#include "../../slam-envire_b200/csrc/density.h"
 
 static int g_block_levels = 1;
 namespace {
@@ -153,6 +154,18 @@ void build(HostGrid &G, const double *model, size_t n, double h)
 } // namespace
 
 extern "C" {
+// density stepping in closed form (csrc/density.h): the vertices PointcloudAdapter visits, and how many segments describe them
+long long hs_density_indices(size_t n, double density, unsigned long long *out, size_t capacity, int *n_segs)
+{
+    DensitySeg segs[ICPB_DENSITY_MAX_SEGS];
+    unsigned long long visited = 0;
+    const int ns = icpb_density_segments(n, density, segs, ICPB_DENSITY_MAX_SEGS, &visited);
+    *n_segs = ns;
+    if (ns < 0) return -1;
+    if (visited > capacity) return -2;
+    for (unsigned long long k = 0; k < visited; ++k) out[k] = icpb_density_index(segs[icpb_density_find(segs, ns, k)], k);
+    return (long long)visited;
+}
 void hs_set_block_levels(int v) { g_block_levels = v; }
 void hs_counters(unsigned long long *out, int reset)
 {

@@ -171,6 +171,32 @@ def test_emulated_device_loop_edge_cases(harness, oracle, synth):
         assert e["early"] == (r.pairs < 3 and prm["max_iter"] > 0)
 
 
+def test_density_stepping_closed_form(harness):
+    """K0: PointcloudAdapter visits idx = size_t(index), index += 1/density with the rounding of every fp64 addition
+    (icp/icp.hpp:126-138).  csrc/density.h restates the accumulation as a few linear segments in exact integer
+    arithmetic so that the device can gather all visits in parallel: every visited index must equal the loop's."""
+    def loop(n, density):
+        out, index, inc = [], 0.0, 1.0 / density
+        while int(index) < n:
+            out.append(int(index))
+            index += inc
+        return np.asarray(out, dtype=np.int64)
+    rng = np.random.default_rng(3)
+    cases = [(1000, 0.37), (17, 0.5), (5, 1.0), (100000, 0.3), (100000, 1.0 / 3.0), (300000, 0.999999), (250000, 0.7),
+             (1 << 18, 1.0 - 2.0 ** -20), (200000, 0.4), (200000, 2.0 / 3.0), (50000, 0.05), (3, 0.01), (40000, 1.7), (1, 0.5),
+             (0, 0.5), (2000000, 0.61803398875)]
+    cases += [(int(rng.integers(1, 400000)), float(rng.uniform(0.02, 1.0))) for _ in range(24)]
+    # step exactly half-way between grid points of a binade: 1/density = 1 + 2^-40 ... -> ties in the binade with ulp 2^-39
+    cases += [(1 << 16, 1.0 / (1.0 + 2.0 ** -40)), (1 << 16, 1.0 / (1.5 + 2.0 ** -45)), (100000, 1.0 / (2.0 + 2.0 ** -49))]
+    for n, density in cases:
+        got, nseg = harness.density_indices(n, density)
+        want = loop(n, density)
+        assert got is not None and nseg <= 200, (n, density, nseg)
+        assert len(got) == len(want) and np.array_equal(got, want), (n, density)
+    got, nseg = harness.density_indices(1000, 900.0)  # absurd densities are left to the host loop
+    assert got is None and nseg == -1
+
+
 def test_c_abi_exports_every_declared_symbol(pkg):
     """include/icp_b200.h is the boundary: every prototype in it must be exported by libicp_b200.so."""
     hdr = open(os.path.join(ROOT, "include", "icp_b200.h")).read()
