@@ -65,7 +65,8 @@ def workload(rank=0):
     synth = importlib.import_module("slam-envire_b200.synth")
     model = synth.scene(N_MODEL, 100.0, 2)
     # every rank's shard is an independent noisy observation of the same scene under the same rigid motion
-    src, T = synth.perturbed_copy(model[:N_SOURCE], 3.0, 0.3, 0.01, seed=3 + rank)
+    # (ICPB_SAME_SHARDS=1, a study switch: every rank gets rank 0's shard -- identical work per rank, no skew)
+    src, T = synth.perturbed_copy(model[:N_SOURCE], 3.0, 0.3, 0.01, seed=3 + (0 if os.environ.get("ICPB_SAME_SHARDS") else rank))
     return model, src, T
 
 

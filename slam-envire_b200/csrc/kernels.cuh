@@ -554,57 +554,145 @@ __global__ void __launch_bounds__(SEARCH_THREADS)
 }
 
 // ---------------------------------------------------------------------------
-// Fused collectives over NVLink peer memory (multi-GPU, one process per GPU).
-// Every rank owns an exchange buffer that its peers map through CUDA IPC.  A collective is "one-shot": the LAST
-// block of the producing kernel stores this rank's small vector into its row of EVERY peer's buffer (plain stores
-// over NVLink), raises a sequence flag there, waits until all rows of its own buffer carry the same sequence number
-// and sums the rows in rank order -- identical arithmetic, hence identical results, on every rank.  No separate
-// collective launch, no host involvement; two buffer halves alternate (a rank can be at most one collective ahead
-// of a peer, because it needs that peer's contribution to finish).
+// Fused collectives over NVLink peer memory (multi-GPU: one process per GPU over CUDA IPC, or one process with peer
+// access).  Every rank owns an exchange buffer that its peers map.  A collective is "one-shot" and lives inside the
+// producing kernel: ONE block per rank stores this rank's small vector into its row of EVERY peer's buffer and reads
+// the rows the peers stored into its own.  No separate collective launch, no host involvement.
+// Transport: every 32-bit data word travels as ONE 64-bit store {sequence number, data} -- 8-byte stores are single
+// transactions over NVLink, so a word is valid exactly when its upper half carries the sequence number of this
+// collective: no flags, no system-scope fences, no ordering between words (the "LL" idea of NCCL's low-latency
+// protocol).  The receiver polls word by word and copies the data into a plain local buffer that the callers read.
+// Two buffer halves alternate (a rank can be at most one collective ahead of a peer, because it needs that peer's
+// contribution to finish).  Measured on 4 B200 (cfg2, identical shards on all ranks -- no skew): per loop body the
+// fence + flag form of these exchanges cost +43 us in the trim (2 exchanges) and +11 us in the moments (1).
 // ---------------------------------------------------------------------------
 constexpr int P2P_MAX_RANKS = 8;
 constexpr int P2P_ROW_WORDS = 12352; // a histogram (2048 bins + found count) or the candidates of the trim's bin: (key lo, key hi, pair index) each
-constexpr int P2P_LIN_CAP = (P2P_ROW_WORDS - 4) / 3; // candidates one row carries in trim_linear_kernel
+constexpr int P2P_LIN_CAP = (P2P_ROW_WORDS - 4) / 3; // candidates one row carries in trim_moments_kernel
 constexpr int P2P_CAND_CAP = 1055; // candidate keys (u64) one row carries next to their count (radix path)
-constexpr size_t P2P_DATA_WORDS = 2ull * P2P_MAX_RANKS * P2P_ROW_WORDS;
-constexpr size_t P2P_BUFFER_WORDS = P2P_DATA_WORDS + 2 * P2P_MAX_RANKS + 64;
+constexpr size_t P2P_LL_WORDS = 2ull * 2ull * P2P_MAX_RANKS * P2P_ROW_WORDS; // two halves of MAX_RANKS rows of 64-bit {seq, data} entries
+constexpr size_t P2P_RECV_WORDS = (size_t)P2P_MAX_RANKS * P2P_ROW_WORDS;     // the rows of the current collective, data only
+constexpr size_t P2P_BUFFER_WORDS = P2P_LL_WORDS + P2P_RECV_WORDS + 64;
 struct P2PView {
     int world, rank;
     uint32_t *peer[P2P_MAX_RANKS]; // base of every rank's exchange buffer (peer[rank] is the local one)
 };
-__device__ __forceinline__ uint32_t *p2p_flags(uint32_t *base) { return base + P2P_DATA_WORDS; }
+__device__ __forceinline__ unsigned long long *p2p_ll_rows(uint32_t *base, int par)
+{
+    return reinterpret_cast<unsigned long long *>(base) + (size_t)par * P2P_MAX_RANKS * P2P_ROW_WORDS;
+}
+// one entry of this rank's own buffer, once it carries sequence number seq (~10 s budget: a peer that is gone turns
+// into ICPB_ERR_NCCL instead of a hung GPU)
+__device__ __forceinline__ uint32_t p2p_poll(const unsigned long long *entry, uint32_t seq, IcpState *st, bool &dead)
+{
+    unsigned long long w = *reinterpret_cast<const volatile unsigned long long *>(entry);
+    if ((uint32_t)(w >> 32) == seq || dead) return (uint32_t)w;
+    const long long t0 = clock64();
+    while ((uint32_t)(w >> 32) != seq) {
+        if (clock64() - t0 > 20000000000ll) {
+            st->comm_error = 1u;
+            st->done = 1; // every later launch of this align becomes a no-op
+            dead = true;
+            break;
+        }
+        w = *reinterpret_cast<const volatile unsigned long long *>(entry);
+    }
+    return (uint32_t)w;
+}
 
-// Called by all threads of ONE block per rank.  src: nwords 32-bit words in local global memory.
-// Returns the local rows of this collective: row q (from rank q) starts at ret + q * P2P_ROW_WORDS; read with __ldcv.
-__device__ const uint32_t *p2p_exchange(const P2PView &v, IcpState *st, const uint32_t *src, int nwords)
+// Called by all threads of ONE block per rank.  src: nwords 32-bit words (global or shared memory, written before a
+// barrier).  var_stride > 0: rows have their own lengths -- word 0 of a row is a count c and the row has
+// 1 + var_stride * c words when c <= var_cap, else just that one word.
+// Returns the local copy of the rows: row q (from rank q) starts at ret + q * P2P_ROW_WORDS; read with __ldcv.
+__device__ const uint32_t *p2p_exchange(const P2PView &v, IcpState *st, const uint32_t *src, int nwords, int var_stride = 0,
+                                        int var_cap = 0)
 {
     const uint32_t seq = st->comm_seq + 1u;
     const int par = (int)(seq & 1u);
-    __syncthreads(); // everyone has read comm_seq
-    for (int p = 0; p < v.world; ++p) {
-        uint32_t *dst = v.peer[p] + ((size_t)par * P2P_MAX_RANKS + v.rank) * P2P_ROW_WORDS;
-        for (int i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src[i];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if ((int)threadIdx.x < v.world) {
-        __threadfence_system();
-        volatile uint32_t *f = p2p_flags(v.peer[threadIdx.x]) + par * P2P_MAX_RANKS + v.rank;
-        *f = seq; // my row has landed in peer threadIdx.x
-        volatile uint32_t *mine = p2p_flags(v.peer[v.rank]) + par * P2P_MAX_RANKS + threadIdx.x;
-        const long long t0 = clock64();
-        while ((int)(*mine - seq) < 0) {
-            if (clock64() - t0 > 20000000000ll) { // ~10 s: a peer is gone; give up instead of hanging the GPU
-                st->comm_error = 1u;
-                st->done = 1; // every later launch of this align becomes a no-op
-                break;
+    __syncthreads(); // everyone has read comm_seq; the previous collective's rows are not needed any more
+    const unsigned long long tag = (unsigned long long)seq << 32;
+    // eight words per thread and trip: the loads of a trip are all in flight before the first dependent store / test
+    // (a load -> store loop over possibly aliasing pointers would take one trip to the L2 per word)
+    for (int base = 0; base < nwords; base += 8 * (int)blockDim.x) {
+        uint32_t w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = base + u * (int)blockDim.x + (int)threadIdx.x;
+            w[u] = i < nwords ? src[i] : 0u;
+        }
+        for (int p = 0; p < v.world; ++p) {
+            unsigned long long *dst = p2p_ll_rows(v.peer[p], par) + (size_t)v.rank * P2P_ROW_WORDS;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = base + u * (int)blockDim.x + (int)threadIdx.x;
+                if (i < nwords) dst[i] = tag | w[u];
             }
         }
     }
-    __threadfence_system();
+    uint32_t *recv = v.peer[v.rank] + P2P_LL_WORDS;
+    const unsigned long long *mine = p2p_ll_rows(v.peer[v.rank], par);
+    bool dead = false;
+    for (int q = 0; q < v.world; ++q) {
+        const unsigned long long *row = mine + (size_t)q * P2P_ROW_WORDS;
+        int len = nwords;
+        if (var_stride > 0) {
+            const uint32_t c = p2p_poll(row, seq, st, dead);
+            len = 1 + (c <= (uint32_t)var_cap ? var_stride * (int)c : 0);
+        }
+        for (int base = 0; base < len; base += 8 * (int)blockDim.x) {
+            unsigned long long e[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = base + u * (int)blockDim.x + (int)threadIdx.x;
+                e[u] = i < len ? *reinterpret_cast<const volatile unsigned long long *>(row + i) : tag;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = base + u * (int)blockDim.x + (int)threadIdx.x;
+                if (i >= len) continue;
+                const uint32_t d = (uint32_t)(e[u] >> 32) == seq ? (uint32_t)e[u] : p2p_poll(row + i, seq, st, dead);
+                recv[(size_t)q * P2P_ROW_WORDS + i] = d;
+            }
+        }
+    }
     __syncthreads();
     if (threadIdx.x == 0) st->comm_seq = seq;
-    return v.peer[v.rank] + (size_t)par * P2P_MAX_RANKS * P2P_ROW_WORDS;
+    return recv;
+}
+
+// All-reduce (sum) of a 2048-bin histogram held eight bins per thread, plus one extra word of thread 0, straight from
+// and to registers: the exchange that opens every trim is on the critical path of the loop body.  All threads of ONE
+// block (256) per rank; same transport and sequence numbering as p2p_exchange.
+__device__ void p2p_allreduce_hist(const P2PView &v, IcpState *st, const uint32_t (&mine)[8], uint32_t extra,
+                                   uint32_t (&sum)[8], unsigned long long &extra_sum)
+{
+    const uint32_t seq = st->comm_seq + 1u;
+    const int par = (int)(seq & 1u);
+    __syncthreads();
+    const unsigned long long tag = (unsigned long long)seq << 32;
+    for (int p = 0; p < v.world; ++p) {
+        unsigned long long *dst = p2p_ll_rows(v.peer[p], par) + (size_t)v.rank * P2P_ROW_WORDS;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[threadIdx.x * 8 + j] = tag | mine[j];
+        if (threadIdx.x == 0) dst[8 * blockDim.x] = tag | extra;
+    }
+    const unsigned long long *rows = p2p_ll_rows(v.peer[v.rank], par);
+    bool dead = false;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum[j] = 0u;
+    extra_sum = 0ull;
+    for (int q = 0; q < v.world; ++q) { // rank order: the same sums on every rank
+        const unsigned long long *row = rows + (size_t)q * P2P_ROW_WORDS;
+        unsigned long long e[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e[j] = *reinterpret_cast<const volatile unsigned long long *>(row + threadIdx.x * 8 + j);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            sum[j] += (uint32_t)(e[j] >> 32) == seq ? (uint32_t)e[j] : p2p_poll(row + threadIdx.x * 8 + j, seq, st, dead);
+        if (threadIdx.x == 0) extra_sum += p2p_poll(row + 8 * blockDim.x, seq, st, dead);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) st->comm_seq = seq;
 }
 
 // ---------------------------------------------------------------------------
@@ -694,8 +782,8 @@ __device__ void select_pick(IcpState *st, uint32_t *ghist, int pass, bool tie_mo
                     if (rows && quota < cnt) {
                         // ties are kept in global pair order = lower ranks first: this rank's share of the quota
                         unsigned long long before = 0;
-                        for (int q = 0; q < rank; ++q) before += __ldcv(rows + (size_t)q * P2P_ROW_WORDS + b);
-                        const unsigned long long local = __ldcv(rows + (size_t)rank * P2P_ROW_WORDS + b);
+                        for (int q = 0; q < rank; ++q) before += __ldcg(rows + (size_t)q * P2P_ROW_WORDS + b);
+                        const unsigned long long local = __ldcg(rows + (size_t)rank * P2P_ROW_WORDS + b);
                         quota = quota > before ? quota - before : 0ull;
                         if (quota > local) quota = local;
                         cnt = local;
@@ -772,12 +860,12 @@ __global__ void __launch_bounds__(SEL_THREADS)
         const uint32_t *rows = p2p_exchange(p2p, st, ghist, pass == 0 ? SEL_MAX_BINS + 1 : bins);
         for (int b = threadIdx.x; b < bins; b += SEL_THREADS) {
             uint32_t v = 0;
-            for (int q = 0; q < p2p.world; ++q) v += __ldcv(rows + (size_t)q * P2P_ROW_WORDS + b);
+            for (int q = 0; q < p2p.world; ++q) v += __ldcg(rows + (size_t)q * P2P_ROW_WORDS + b);
             ghist[b] = v;
         }
         if (pass == 0 && threadIdx.x == 0) {
             unsigned long long f = 0;
-            for (int q = 0; q < p2p.world; ++q) f += __ldcv(rows + (size_t)q * P2P_ROW_WORDS + SEL_MAX_BINS);
+            for (int q = 0; q < p2p.world; ++q) f += __ldcg(rows + (size_t)q * P2P_ROW_WORDS + SEL_MAX_BINS);
             st->found = f;
         }
         __syncthreads();
@@ -890,11 +978,11 @@ __global__ void __launch_bounds__(SEL_THREADS)
             }
         __threadfence();
         __syncthreads();
-        crow = p2p_exchange(p2p, st, xb, fits ? 1 + 2 * (int)cnt : 1);
+        crow = p2p_exchange(p2p, st, xb, fits ? 1 + 2 * (int)cnt : 1, 2, P2P_CAND_CAP);
         if (threadIdx.x == 0) {
             int ok = 1;
             for (int q = 0; q < p2p.world; ++q)
-                if (__ldcv(crow + (size_t)q * P2P_ROW_WORDS) > (uint32_t)P2P_CAND_CAP) ok = 0;
+                if (__ldcg(crow + (size_t)q * P2P_ROW_WORDS) > (uint32_t)P2P_CAND_CAP) ok = 0;
             all_fit = ok;
         }
         __syncthreads();
@@ -910,9 +998,9 @@ __global__ void __launch_bounds__(SEL_THREADS)
             if (st->sel_krem == 0) break;
             for (int q = 0; q < p2p.world; ++q) {
                 const uint32_t *r = crow + (size_t)q * P2P_ROW_WORDS;
-                const unsigned cq = __ldcv(r);
+                const unsigned cq = __ldcg(r);
                 for (unsigned j = threadIdx.x; j < cq; j += blockDim.x) {
-                    const unsigned long long k = (unsigned long long)__ldcv(r + 1 + 2 * j) | ((unsigned long long)__ldcv(r + 2 + 2 * j) << 32);
+                    const unsigned long long k = (unsigned long long)__ldcg(r + 1 + 2 * j) | ((unsigned long long)__ldcg(r + 2 + 2 * j) << 32);
                     if ((k >> hsp) != (prefix >> hsp)) continue;
                     const unsigned b = (unsigned)(k >> shift) & bin_mask;
                     atomicAdd(&ghist[b], 1u);
@@ -944,7 +1032,7 @@ __global__ void __launch_bounds__(SEL_THREADS)
             const uint32_t *rows = p2p_exchange(p2p, st, ghist, bins);
             for (int b = threadIdx.x; b < bins; b += blockDim.x) {
                 uint32_t v = 0;
-                for (int q = 0; q < p2p.world; ++q) v += __ldcv(rows + (size_t)q * P2P_ROW_WORDS + b);
+                for (int q = 0; q < p2p.world; ++q) v += __ldcg(rows + (size_t)q * P2P_ROW_WORDS + b);
                 ghist[b] = v;
             }
             __syncthreads();
@@ -1033,11 +1121,11 @@ __device__ void trim_linear_finish_multi(const double *__restrict__ nn_d, const 
         }
     __threadfence();
     __syncthreads();
-    const uint32_t *crow = p2p_exchange(p2p, st, xb, fits ? 1 + 3 * (int)cnt : 1);
+    const uint32_t *crow = p2p_exchange(p2p, st, xb, fits ? 1 + 3 * (int)cnt : 1, 3, P2P_LIN_CAP);
     if (threadIdx.x == 0) {
         unsigned ok = 1;
         for (int q = 0; q < p2p.world; ++q)
-            if (__ldcv(crow + (size_t)q * P2P_ROW_WORDS) > (uint32_t)P2P_LIN_CAP) ok = 0;
+            if (__ldcg(crow + (size_t)q * P2P_ROW_WORDS) > (uint32_t)P2P_LIN_CAP) ok = 0;
         m_allfit = ok;
         m_cnt = 0u;
         m_sub = ICPB_NONE;
@@ -1049,9 +1137,9 @@ __device__ void trim_linear_finish_multi(const double *__restrict__ nn_d, const 
         // sub-bin split over the union
         for (int q = 0; q < p2p.world; ++q) {
             const uint32_t *r = crow + (size_t)q * P2P_ROW_WORDS;
-            const unsigned cq = __ldcv(r);
+            const unsigned cq = __ldcg(r);
             for (unsigned j = threadIdx.x; j < cq; j += blockDim.x) {
-                const unsigned long long key = (unsigned long long)__ldcv(r + 1 + 3 * j) | ((unsigned long long)__ldcv(r + 2 + 3 * j) << 32);
+                const unsigned long long key = (unsigned long long)__ldcg(r + 1 + 3 * j) | ((unsigned long long)__ldcg(r + 2 + 3 * j) << 32);
                 atomicAdd(&fhist[lin_sub_bin(__longlong_as_double((long long)key), scale, bin)], 1u);
             }
         }
@@ -1080,15 +1168,15 @@ __device__ void trim_linear_finish_multi(const double *__restrict__ nn_d, const 
         const unsigned sub = m_sub;
         for (int q = 0; q < p2p.world && sub != ICPB_NONE; ++q) {
             const uint32_t *r = crow + (size_t)q * P2P_ROW_WORDS;
-            const unsigned cq = __ldcv(r);
+            const unsigned cq = __ldcg(r);
             for (unsigned j = threadIdx.x; j < cq; j += blockDim.x) {
-                const unsigned long long key = (unsigned long long)__ldcv(r + 1 + 3 * j) | ((unsigned long long)__ldcv(r + 2 + 3 * j) << 32);
+                const unsigned long long key = (unsigned long long)__ldcg(r + 1 + 3 * j) | ((unsigned long long)__ldcg(r + 2 + 3 * j) << 32);
                 if (lin_sub_bin(__longlong_as_double((long long)key), scale, bin) != sub) continue;
                 const unsigned at = atomicAdd(&m_cnt, 1u);
                 if (at < LIN_FINAL_CAP) {
                     f_key[at] = key;
                     f_rank[at] = (uint32_t)q;
-                    f_perm[at] = __ldcv(r + 3 + 3 * j);
+                    f_perm[at] = __ldcg(r + 3 + 3 * j);
                 }
             }
         }
@@ -1131,10 +1219,10 @@ __device__ void trim_linear_finish_multi(const double *__restrict__ nn_d, const 
             if (uni) {
                 for (int q = 0; q < p2p.world; ++q) {
                     const uint32_t *r = crow + (size_t)q * P2P_ROW_WORDS;
-                    const unsigned cq = __ldcv(r);
+                    const unsigned cq = __ldcg(r);
                     for (unsigned j = threadIdx.x; j < cq; j += blockDim.x) {
-                        const unsigned long long hi = (unsigned long long)__ldcv(r + 1 + 3 * j) | ((unsigned long long)__ldcv(r + 2 + 3 * j) << 32);
-                        const unsigned long long lo = ((unsigned long long)q << 32) | __ldcv(r + 3 + 3 * j);
+                        const unsigned long long hi = (unsigned long long)__ldcg(r + 1 + 3 * j) | ((unsigned long long)__ldcg(r + 2 + 3 * j) << 32);
+                        const unsigned long long lo = ((unsigned long long)q << 32) | __ldcg(r + 3 + 3 * j);
                         if (lin_key_matches(hi, lo, phi, plo, pass) && lin_key_bit(hi, lo, pass) == 0u) ++zeros;
                     }
                 }
@@ -1155,7 +1243,7 @@ __device__ void trim_linear_finish_multi(const double *__restrict__ nn_d, const 
                 __syncthreads();
                 const uint32_t *rr = p2p_exchange(p2p, st, xb, 1);
                 z = 0;
-                for (int q = 0; q < p2p.world; ++q) z += __ldcv(rr + (size_t)q * P2P_ROW_WORDS);
+                for (int q = 0; q < p2p.world; ++q) z += __ldcg(rr + (size_t)q * P2P_ROW_WORDS);
                 __syncthreads();
             }
             if (threadIdx.x == 0) {
@@ -1324,7 +1412,7 @@ __device__ void moments_last_finish(IcpState *st, double (&v)[3], bool with_extr
         if (threadIdx.x < ICPB_NSUMS) {
             for (int q = 0; q < p2p.world; ++q) {
                 const uint32_t *r = prow + (size_t)q * P2P_ROW_WORDS + 2 * threadIdx.x;
-                const unsigned long long bits = (unsigned long long)__ldcv(r) | ((unsigned long long)__ldcv(r + 1) << 32);
+                const unsigned long long bits = (unsigned long long)__ldcg(r) | ((unsigned long long)__ldcg(r + 1) << 32);
                 t += __longlong_as_double((long long)bits);
             }
         }
@@ -1432,20 +1520,15 @@ __global__ void __launch_bounds__(SEL_THREADS, 2)
         // read it (above).
         const unsigned target = lin_target;
         if (blockIdx.x == 0) {
-            for (int b = threadIdx.x; b < LIN_BINS; b += SEL_THREADS) xscratch[b] = __ldcg(lhist + b * LIN_STRIDE);
-            if (threadIdx.x == 0) xscratch[LIN_BINS] = (uint32_t)st->found;
-            __threadfence();
-            __syncthreads();
-            const uint32_t *rows = p2p_exchange(p2p, st, xscratch, LIN_BINS + 1);
-            for (int b = threadIdx.x; b < LIN_BINS; b += SEL_THREADS) {
-                uint32_t v = 0;
-                for (int q = 0; q < p2p.world; ++q) v += __ldcv(rows + (size_t)q * P2P_ROW_WORDS + b);
-                lsum[b] = v;
-            }
-            if (threadIdx.x == 0) {
+            {
+                uint32_t h8[8], a8[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) h8[j] = __ldcg(lhist + (threadIdx.x * 8 + j) * LIN_STRIDE);
                 unsigned long long f = 0;
-                for (int q = 0; q < p2p.world; ++q) f += __ldcv(rows + (size_t)q * P2P_ROW_WORDS + LIN_BINS);
-                st->found = f;
+                p2p_allreduce_hist(p2p, st, h8, (uint32_t)found_in, a8, f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) lsum[threadIdx.x * 8 + j] = a8[j];
+                if (threadIdx.x == 0) st->found = f;
             }
             __threadfence();
             __syncthreads();
