@@ -632,28 +632,45 @@ __device__ const uint32_t *p2p_exchange(const P2PView &v, IcpState *st, const ui
     uint32_t *recv = v.peer[v.rank] + P2P_LL_WORDS;
     const unsigned long long *mine = p2p_ll_rows(v.peer[v.rank], par);
     bool dead = false;
-    for (int q = 0; q < v.world; ++q) {
-        const unsigned long long *row = mine + (size_t)q * P2P_ROW_WORDS;
-        int len = nwords;
-        if (var_stride > 0) {
-            const uint32_t c = p2p_poll(row, seq, st, dead);
-            len = 1 + (c <= (uint32_t)var_cap ? var_stride * (int)c : 0);
-        }
-        for (int base = 0; base < len; base += 8 * (int)blockDim.x) {
-            unsigned long long e[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int i = base + u * (int)blockDim.x + (int)threadIdx.x;
-                e[u] = i < len ? *reinterpret_cast<const volatile unsigned long long *>(row + i) : tag;
+    // the rows of all ranks as one index space (off[q]: words of the rows before q), so that a trip's eight loads are
+    // in flight whatever row they belong to
+    __shared__ int off[P2P_MAX_RANKS + 1];
+    if (threadIdx.x == 0) {
+        unsigned long long e0[P2P_MAX_RANKS];
+        if (var_stride > 0)
+            for (int q = 0; q < v.world; ++q) e0[q] = *reinterpret_cast<const volatile unsigned long long *>(mine + (size_t)q * P2P_ROW_WORDS);
+        int run = 0;
+        for (int q = 0; q < v.world; ++q) {
+            int len = nwords;
+            if (var_stride > 0) {
+                const uint32_t c = (uint32_t)(e0[q] >> 32) == seq ? (uint32_t)e0[q] : p2p_poll(mine + (size_t)q * P2P_ROW_WORDS, seq, st, dead);
+                len = 1 + (c <= (uint32_t)var_cap ? var_stride * (int)c : 0);
             }
+            off[q] = run;
+            run += len;
+        }
+        off[v.world] = run;
+    }
+    __syncthreads();
+    const int total = off[v.world];
+    for (int base = 0; base < total; base += 8 * (int)blockDim.x) {
+        unsigned long long e[8];
+        int at[8]; // position of the word inside its rank's buffers, -1: none
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int i = base + u * (int)blockDim.x + (int)threadIdx.x;
-                if (i >= len) continue;
-                const uint32_t d = (uint32_t)(e[u] >> 32) == seq ? (uint32_t)e[u] : p2p_poll(row + i, seq, st, dead);
-                recv[(size_t)q * P2P_ROW_WORDS + i] = d;
+        for (int u = 0; u < 8; ++u) {
+            const int f = base + u * (int)blockDim.x + (int)threadIdx.x;
+            at[u] = -1;
+            e[u] = tag;
+            if (f < total) {
+                int q = 0;
+                while (q + 1 < v.world && f >= off[q + 1]) ++q;
+                at[u] = q * P2P_ROW_WORDS + (f - off[q]);
+                e[u] = *reinterpret_cast<const volatile unsigned long long *>(mine + at[u]);
             }
         }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (at[u] >= 0) recv[at[u]] = (uint32_t)(e[u] >> 32) == seq ? (uint32_t)e[u] : p2p_poll(mine + at[u], seq, st, dead);
     }
     __syncthreads();
     if (threadIdx.x == 0) st->comm_seq = seq;
@@ -681,15 +698,24 @@ __device__ void p2p_allreduce_hist(const P2PView &v, IcpState *st, const uint32_
 #pragma unroll
     for (int j = 0; j < 8; ++j) sum[j] = 0u;
     extra_sum = 0ull;
-    for (int q = 0; q < v.world; ++q) { // rank order: the same sums on every rank
-        const unsigned long long *row = rows + (size_t)q * P2P_ROW_WORDS;
-        unsigned long long e[8];
+    for (int q0 = 0; q0 < v.world; q0 += 4) { // rank order: the same sums on every rank; four ranks' loads in flight
+        unsigned long long e[4][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) e[j] = *reinterpret_cast<const volatile unsigned long long *>(row + threadIdx.x * 8 + j);
+        for (int dq = 0; dq < 4; ++dq) {
+            const unsigned long long *row = rows + (size_t)(q0 + dq) * P2P_ROW_WORDS;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            sum[j] += (uint32_t)(e[j] >> 32) == seq ? (uint32_t)e[j] : p2p_poll(row + threadIdx.x * 8 + j, seq, st, dead);
-        if (threadIdx.x == 0) extra_sum += p2p_poll(row + 8 * blockDim.x, seq, st, dead);
+            for (int j = 0; j < 8; ++j)
+                e[dq][j] = q0 + dq < v.world ? *reinterpret_cast<const volatile unsigned long long *>(row + threadIdx.x * 8 + j) : tag;
+        }
+#pragma unroll
+        for (int dq = 0; dq < 4; ++dq) {
+            if (q0 + dq >= v.world) continue;
+            const unsigned long long *row = rows + (size_t)(q0 + dq) * P2P_ROW_WORDS;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                sum[j] += (uint32_t)(e[dq][j] >> 32) == seq ? (uint32_t)e[dq][j] : p2p_poll(row + threadIdx.x * 8 + j, seq, st, dead);
+            if (threadIdx.x == 0) extra_sum += p2p_poll(row + 8 * blockDim.x, seq, st, dead);
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) st->comm_seq = seq;
@@ -1101,6 +1127,27 @@ __device__ __forceinline__ unsigned lin_key_bit(unsigned long long hi, unsigned 
     return pass < 63 ? (unsigned)(hi >> (62 - pass)) & 1u : (unsigned)(lo >> (97 - pass)) & 1u;
 }
 
+// The candidates of all ranks (rows of exchange #2: count, then (key lo, key hi, pair index) each) as one list; a thread
+// loads eight of them per trip, all loads in flight before the first use.  off[q]: candidates of the ranks before q.
+__device__ __forceinline__ void union_load8(const uint32_t *crow, const unsigned *off, int world, unsigned base,
+                                            unsigned long long (&key)[8], uint32_t (&pidx)[8], uint32_t (&rnk)[8], bool (&ok)[8])
+{
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const unsigned f = base + (unsigned)u * blockDim.x + threadIdx.x;
+        ok[u] = f < off[world];
+        key[u] = 0ull, pidx[u] = 0u, rnk[u] = 0u;
+        if (ok[u]) {
+            int q = 0;
+            while (q + 1 < world && f >= off[q + 1]) ++q;
+            const uint32_t *r = crow + (size_t)q * P2P_ROW_WORDS + 1 + 3 * (size_t)(f - off[q]);
+            key[u] = (unsigned long long)__ldcg(r) | ((unsigned long long)__ldcg(r + 1) << 32);
+            pidx[u] = __ldcg(r + 2);
+            rnk[u] = (uint32_t)q;
+        }
+    }
+}
+
 __device__ void trim_linear_finish_multi(const double *__restrict__ nn_d, const uint32_t *__restrict__ perm, IcpState *st,
                                          const unsigned long long *cand_key, const uint32_t *cand_idx, unsigned cnt, unsigned bin,
                                          unsigned long long krem, const P2PView &p2p, uint32_t *xb, uint32_t *fhist,
@@ -1111,37 +1158,60 @@ __device__ void trim_linear_finish_multi(const double *__restrict__ nn_d, const 
     __shared__ uint32_t f_rank[LIN_FINAL_CAP];
     const double scale = lin_scale(st->d_box);
     const bool fits = cnt <= (unsigned)P2P_LIN_CAP;
+    __shared__ unsigned u_off[P2P_MAX_RANKS + 1];
     if (threadIdx.x == 0) xb[0] = cnt;
     if (fits)
-        for (unsigned j = threadIdx.x; j < cnt; j += blockDim.x) {
-            const unsigned long long key = __ldcg(cand_key + j);
-            xb[1 + 3 * j] = (uint32_t)key;
-            xb[2 + 3 * j] = (uint32_t)(key >> 32);
-            xb[3 + 3 * j] = perm[__ldcg(cand_idx + j)];
+        for (unsigned j0 = 0; j0 < cnt; j0 += 4u * blockDim.x) { // four per trip: loads, dependent loads, then stores
+            unsigned long long k4[4];
+            uint32_t i4[4], p4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned j = j0 + (unsigned)u * blockDim.x + threadIdx.x;
+                k4[u] = j < cnt ? __ldcg(cand_key + j) : 0ull;
+                i4[u] = j < cnt ? __ldcg(cand_idx + j) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) p4[u] = perm[i4[u]];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned j = j0 + (unsigned)u * blockDim.x + threadIdx.x;
+                if (j < cnt) {
+                    xb[1 + 3 * j] = (uint32_t)k4[u];
+                    xb[2 + 3 * j] = (uint32_t)(k4[u] >> 32);
+                    xb[3 + 3 * j] = p4[u];
+                }
+            }
         }
     __threadfence();
     __syncthreads();
     const uint32_t *crow = p2p_exchange(p2p, st, xb, fits ? 1 + 3 * (int)cnt : 1, 3, P2P_LIN_CAP);
     if (threadIdx.x == 0) {
-        unsigned ok = 1;
-        for (int q = 0; q < p2p.world; ++q)
-            if (__ldcg(crow + (size_t)q * P2P_ROW_WORDS) > (uint32_t)P2P_LIN_CAP) ok = 0;
+        unsigned ok = 1, run = 0;
+        for (int q = 0; q < p2p.world; ++q) {
+            const uint32_t cq = __ldcg(crow + (size_t)q * P2P_ROW_WORDS);
+            if (cq > (uint32_t)P2P_LIN_CAP) ok = 0;
+            u_off[q] = run;
+            run += cq <= (uint32_t)P2P_LIN_CAP ? cq : 0u;
+        }
+        u_off[p2p.world] = run;
         m_allfit = ok;
         m_cnt = 0u;
         m_sub = ICPB_NONE;
     }
     __syncthreads();
+    const unsigned u_total = u_off[p2p.world];
     unsigned long long w_key = 0, w_lo = 0; // the selected pair: distance bits, (rank << 32 | pair index)
     bool have = false;
     if (m_allfit) {
         // sub-bin split over the union
-        for (int q = 0; q < p2p.world; ++q) {
-            const uint32_t *r = crow + (size_t)q * P2P_ROW_WORDS;
-            const unsigned cq = __ldcg(r);
-            for (unsigned j = threadIdx.x; j < cq; j += blockDim.x) {
-                const unsigned long long key = (unsigned long long)__ldcg(r + 1 + 3 * j) | ((unsigned long long)__ldcg(r + 2 + 3 * j) << 32);
-                atomicAdd(&fhist[lin_sub_bin(__longlong_as_double((long long)key), scale, bin)], 1u);
-            }
+        for (unsigned base = 0; base < u_total; base += 8u * blockDim.x) {
+            unsigned long long k8[8];
+            uint32_t p8[8], r8[8];
+            bool ok8[8];
+            union_load8(crow, u_off, p2p.world, base, k8, p8, r8, ok8);
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (ok8[u]) atomicAdd(&fhist[lin_sub_bin(__longlong_as_double((long long)k8[u]), scale, bin)], 1u);
         }
         __syncthreads();
         uint32_t c2[8], local2 = 0;
@@ -1166,17 +1236,19 @@ __device__ void trim_linear_finish_multi(const double *__restrict__ nn_d, const 
         __syncthreads();
         for (int b = threadIdx.x; b < SEL_MAX_BINS; b += SEL_THREADS) fhist[b] = 0u;
         const unsigned sub = m_sub;
-        for (int q = 0; q < p2p.world && sub != ICPB_NONE; ++q) {
-            const uint32_t *r = crow + (size_t)q * P2P_ROW_WORDS;
-            const unsigned cq = __ldcg(r);
-            for (unsigned j = threadIdx.x; j < cq; j += blockDim.x) {
-                const unsigned long long key = (unsigned long long)__ldcg(r + 1 + 3 * j) | ((unsigned long long)__ldcg(r + 2 + 3 * j) << 32);
-                if (lin_sub_bin(__longlong_as_double((long long)key), scale, bin) != sub) continue;
+        for (unsigned base = 0; base < u_total && sub != ICPB_NONE; base += 8u * blockDim.x) {
+            unsigned long long k8[8];
+            uint32_t p8[8], r8[8];
+            bool ok8[8];
+            union_load8(crow, u_off, p2p.world, base, k8, p8, r8, ok8);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (!ok8[u] || lin_sub_bin(__longlong_as_double((long long)k8[u]), scale, bin) != sub) continue;
                 const unsigned at = atomicAdd(&m_cnt, 1u);
                 if (at < LIN_FINAL_CAP) {
-                    f_key[at] = key;
-                    f_rank[at] = (uint32_t)q;
-                    f_perm[at] = __ldcg(r + 3 + 3 * j);
+                    f_key[at] = k8[u];
+                    f_rank[at] = r8[u];
+                    f_perm[at] = p8[u];
                 }
             }
         }
@@ -1217,13 +1289,15 @@ __device__ void trim_linear_finish_multi(const double *__restrict__ nn_d, const 
             const unsigned long long phi = m_phi, plo = m_plo;
             unsigned zeros = 0;
             if (uni) {
-                for (int q = 0; q < p2p.world; ++q) {
-                    const uint32_t *r = crow + (size_t)q * P2P_ROW_WORDS;
-                    const unsigned cq = __ldcg(r);
-                    for (unsigned j = threadIdx.x; j < cq; j += blockDim.x) {
-                        const unsigned long long hi = (unsigned long long)__ldcg(r + 1 + 3 * j) | ((unsigned long long)__ldcg(r + 2 + 3 * j) << 32);
-                        const unsigned long long lo = ((unsigned long long)q << 32) | __ldcg(r + 3 + 3 * j);
-                        if (lin_key_matches(hi, lo, phi, plo, pass) && lin_key_bit(hi, lo, pass) == 0u) ++zeros;
+                for (unsigned base = 0; base < u_total; base += 8u * blockDim.x) {
+                    unsigned long long k8[8];
+                    uint32_t p8[8], r8[8];
+                    bool ok8[8];
+                    union_load8(crow, u_off, p2p.world, base, k8, p8, r8, ok8);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const unsigned long long lo = ((unsigned long long)r8[u] << 32) | p8[u];
+                        if (ok8[u] && lin_key_matches(k8[u], lo, phi, plo, pass) && lin_key_bit(k8[u], lo, pass) == 0u) ++zeros;
                     }
                 }
             } else {
