@@ -80,7 +80,8 @@ const char *icpb_version(void);
  *       `floor` cell edges more, so that its bound is useful; results never depend on these),
  *       "block_levels" (-1/0/1, default 1: searches whose ball spans at most 2 (0) / 3 (1) cells per axis scan that
  *       cell block flat instead of walking the pyramid),
- *       "sort_source" (0/1), "graph" (0/1, default 1: the whole _align loop is ONE CUDA-graph launch whose WHILE
+ *       "sort_source" (0/1: order the source spatially at upload), "hilbert" (0/1, default 1: along a Hilbert curve
+ *       instead of a Morton curve), "morton_bits" (cells per axis of that curve, 2^bits, default 10), "graph" (0/1, default 1: the whole _align loop is ONE CUDA-graph launch whose WHILE
  *       node is driven by the device-side loop condition), "profile" (0/1, default 0: 1 enqueues the loop kernel by
  *       kernel on the stream with CUDA events around every phase -- icpb_last_timing / icpb_iteration_times --
  *       and the host peeking at a pinned flag at most "run_ahead" iterations behind),

@@ -211,7 +211,7 @@ struct icpb_ctx {
     std::string err;
     // options
     double opt_cell_size = 0.0, opt_target = 12.0, opt_max_cells = 64.0 * 1024 * 1024, opt_run_ahead = 2.0,
-           opt_warm = 1.0, opt_skip = 1.0, opt_skip_reach = 0.25, opt_skip_floor = 0.05, opt_lazy = 1.0, opt_lazy_margin = 0.05, opt_fail_build = 0.0, opt_linear_trim = 1.0, opt_fuse_moments = -1.0, opt_block_levels = 1.0, opt_profile = 0.0, opt_sort = 1.0, opt_margin = 0.0, opt_merge = 1.0, opt_graph = 1.0, opt_trim_bpsm = 2.0, opt_mom_bpsm = 2.0;
+           opt_warm = 1.0, opt_skip = 1.0, opt_skip_reach = 0.25, opt_skip_floor = 0.05, opt_lazy = 1.0, opt_lazy_margin = 0.05, opt_fail_build = 0.0, opt_linear_trim = 1.0, opt_fuse_moments = -1.0, opt_morton_bits = 10.0, opt_hilbert = 1.0, opt_block_levels = 1.0, opt_profile = 0.0, opt_sort = 1.0, opt_margin = 0.0, opt_merge = 1.0, opt_graph = 1.0, opt_trim_bpsm = 2.0, opt_mom_bpsm = 2.0;
     // model
     DevBuf<double> model_raw, model_nrm;
     DevBuf<uint8_t> model_edge;
@@ -485,6 +485,8 @@ static double *opt_slot(icpb_ctx *ctx, const char *key)
     if (!strcmp(key, "lazy_margin")) return &ctx->opt_lazy_margin;
     if (!strcmp(key, "linear_trim")) return &ctx->opt_linear_trim;
     if (!strcmp(key, "fuse_moments")) return &ctx->opt_fuse_moments;
+    if (!strcmp(key, "morton_bits")) return &ctx->opt_morton_bits;
+    if (!strcmp(key, "hilbert")) return &ctx->opt_hilbert;
     if (!strcmp(key, "test_fail_next_build")) return &ctx->opt_fail_build;
     if (!strcmp(key, "profile")) return &ctx->opt_profile;
     if (!strcmp(key, "sort_source")) return &ctx->opt_sort;
@@ -1057,10 +1059,12 @@ static int upload_points(icpb_ctx *ctx, size_t m, bool wait)
             CK(ctx->sort_scratch.ensure(rs_scratch_elems(m)));
             double *bb = ctx->bbox_part.p + (size_t)nbb * 6;
             bbox_kernel<<<nbb, 256, 0, s>>>(ctx->stage.p, m, ctx->bbox_part.p);
-            bbox_final_kernel<<<1, 256, 0, s>>>(ctx->bbox_part.p, nbb, bb);
-            morton_keys_kernel<<<grid_for(m, 256), 256, 0, s>>>(ctx->stage.p, (uint32_t)m, bb, ctx->keys0.p, ctx->vals0.p);
+            const int mbits = (int)std::max(4.0, std::min(ctx->opt_morton_bits, 10.0)); // Morton cells per axis: 2^mbits
+            bbox_final_kernel<<<1, 256, 0, s>>>(ctx->bbox_part.p, nbb, bb, (double)(1 << mbits));
+            morton_keys_kernel<<<grid_for(m, 256), 256, 0, s>>>(ctx->stage.p, (uint32_t)m, bb, ctx->keys0.p, ctx->vals0.p,
+                                                               ctx->opt_hilbert != 0.0 ? mbits : 0);
             CKL();
-            const int w = radix_sort<uint32_t, true>(ctx->keys0.p, ctx->vals0.p, ctx->keys1.p, ctx->vals1.p, m, 30,
+            const int w = radix_sort<uint32_t, true>(ctx->keys0.p, ctx->vals0.p, ctx->keys1.p, ctx->vals1.p, m, 3 * mbits,
                                                      ctx->sort_scratch.p, s, &ctx->launches);
             CKL();
             CK(cudaMemcpyAsync(ctx->src_perm.p, w ? ctx->vals1.p : ctx->vals0.p, m * sizeof(uint32_t),
