@@ -15,7 +15,8 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ok = True
 cases = [("cfg1", 0.2, 1.0, {}), ("cfg2", 0.05, 1.0, dict(max_iter=15)), ("cfg1", 0.1, 0.37, dict(max_iter=10, overlap=0.6)),
-         ("ties", 24, 1.0, {}), ("ties", 72, 1.0, {}), ("ties", 150, 1.0, {})]
+         ("ties", 24, 1.0, {}), ("ties", 72, 1.0, {}), ("ties", 150, 1.0, {}),
+         ("tiny", 5, 1.0, {}), ("tiny", 1, 1.0, {})]  # fewer source points than ranks: some ranks hold no point at all
 mode = os.environ.get("ICPB_COMM", "p2p")
 icp = pkg.Icp(local)
 sharding.init_comm(icp, dist, torch.device("cuda", local), mode=mode)
@@ -29,6 +30,10 @@ for name, scale, density, over in cases:
         m = np.concatenate([m, np.zeros((len(m), 1))], 1)
         s = m + [0.3, 0.2, 0.0]
         prm = dict(max_iter=6, min_mse=1e-12, min_mse_diff=1e-14, overlap=0.55)
+    elif name == "tiny":
+        m, s0, T, prm = synth.config("cfg1", 0.05)
+        s = s0[:scale]
+        prm = dict(prm, max_iter=5, overlap=1.0)
     else:
         m, s, T, prm = synth.config(name, scale)
         prm = dict(prm, **over)
@@ -40,7 +45,7 @@ for name, scale, density, over in cases:
     r = icp.align_resident(**prm)
     r1 = single.align(s, density=density, **prm)
     same = (r.iter == r1.iter and r.pairs == r1.pairs and np.abs(r.matrix() - r1.matrix()).max() < 1e-9
-            and abs(r.mse - r1.mse) <= 1e-9 * abs(r1.mse) + 1e-20)
+            and (abs(r.mse - r1.mse) <= 1e-9 * abs(r1.mse) + 1e-20 or (np.isinf(r.mse) and np.isinf(r1.mse))))
     tr, tr1 = icp.trace(), single.trace()
     same = same and len(tr) == len(tr1) and all(a["kept"] == b["kept"] and a["found"] == b["found"] for a, b in zip(tr, tr1))
     # getPairsDistance after a sharded align: every rank returns ITS kept distances (ascending); together they are the
@@ -55,7 +60,7 @@ for name, scale, density, over in cases:
     dist.all_gather(parts, padded)
     allpd = np.sort(np.concatenate([p.cpu().numpy()[:int(n.item())] for p, n in zip(parts, sizes)]))
     pd1 = single.pairs_distance()
-    same_pd = len(allpd) == len(pd1) == r1.pairs and np.allclose(allpd, pd1, rtol=1e-9, atol=1e-12) and bool(np.all(np.diff(pd.cpu().numpy()) >= 0))
+    same_pd = len(allpd) == len(pd1) and (len(pd1) == r1.pairs or r1.pairs < 3) and np.allclose(allpd, pd1, rtol=1e-9, atol=1e-12) and bool(np.all(np.diff(pd.cpu().numpy()) >= 0))
     if not same_pd and rank == 0:
         print("  pairs_distance differs: gathered", len(allpd), "single", len(pd1), "pairs", r1.pairs)
     same = same and same_pd
