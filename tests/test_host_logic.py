@@ -209,6 +209,21 @@ def test_c_abi_exports_every_declared_symbol(pkg):
     assert L.icpb_version().startswith(b"icp_b200")
 
 
+def test_create_multi_rejects_bad_device_lists(pkg):
+    """icpb_create_multi: argument errors are reported before any device is touched (runs without a GPU)."""
+    import ctypes as C
+    L = pkg.load_library()
+    L.icpb_create_multi.restype = C.c_int
+    h = C.c_void_p()
+    for ids in ([0, 0], [1, 2, 1], []):
+        arr = (C.c_int * max(len(ids), 1))(*ids)
+        assert L.icpb_create_multi(C.byref(h), arr, len(ids)) == pkg.ERR_ARG
+        assert not h.value
+    arr = (C.c_int * 9)(*range(9))
+    assert L.icpb_create_multi(C.byref(h), arr, 9) == pkg.ERR_ARG  # more than 8 ranks: the exchange rows are sized for 8
+    assert L.icpb_create_multi(None, arr, 2) == pkg.ERR_ARG
+
+
 def test_no_cpu_fallback(pkg):
     """Without a CUDA device the product must fail loudly, not fall back to a CPU path."""
     import torch
