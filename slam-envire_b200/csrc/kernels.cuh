@@ -632,45 +632,27 @@ __device__ const uint32_t *p2p_exchange(const P2PView &v, IcpState *st, const ui
     uint32_t *recv = v.peer[v.rank] + P2P_LL_WORDS;
     const unsigned long long *mine = p2p_ll_rows(v.peer[v.rank], par);
     bool dead = false;
-    // the rows of all ranks as one index space (off[q]: words of the rows before q), so that a trip's eight loads are
-    // in flight whatever row they belong to
-    __shared__ int off[P2P_MAX_RANKS + 1];
-    if (threadIdx.x == 0) {
-        unsigned long long e0[P2P_MAX_RANKS];
-        if (var_stride > 0)
-            for (int q = 0; q < v.world; ++q) e0[q] = *reinterpret_cast<const volatile unsigned long long *>(mine + (size_t)q * P2P_ROW_WORDS);
-        int run = 0;
-        for (int q = 0; q < v.world; ++q) {
-            int len = nwords;
-            if (var_stride > 0) {
-                const uint32_t c = (uint32_t)(e0[q] >> 32) == seq ? (uint32_t)e0[q] : p2p_poll(mine + (size_t)q * P2P_ROW_WORDS, seq, st, dead);
-                len = 1 + (c <= (uint32_t)var_cap ? var_stride * (int)c : 0);
-            }
-            off[q] = run;
-            run += len;
+    for (int q = 0; q < v.world; ++q) { // row by row, eight words per thread and trip
+        const unsigned long long *row = mine + (size_t)q * P2P_ROW_WORDS;
+        int len = nwords;
+        if (var_stride > 0) {
+            const uint32_t c = p2p_poll(row, seq, st, dead);
+            len = 1 + (c <= (uint32_t)var_cap ? var_stride * (int)c : 0);
         }
-        off[v.world] = run;
-    }
-    __syncthreads();
-    const int total = off[v.world];
-    for (int base = 0; base < total; base += 8 * (int)blockDim.x) {
-        unsigned long long e[8];
-        int at[8]; // position of the word inside its rank's buffers, -1: none
+        for (int base = 0; base < len; base += 8 * (int)blockDim.x) {
+            unsigned long long e[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int f = base + u * (int)blockDim.x + (int)threadIdx.x;
-            at[u] = -1;
-            e[u] = tag;
-            if (f < total) {
-                int q = 0;
-                while (q + 1 < v.world && f >= off[q + 1]) ++q;
-                at[u] = q * P2P_ROW_WORDS + (f - off[q]);
-                e[u] = *reinterpret_cast<const volatile unsigned long long *>(mine + at[u]);
+            for (int u = 0; u < 8; ++u) {
+                const int i = base + u * (int)blockDim.x + (int)threadIdx.x;
+                e[u] = i < len ? *reinterpret_cast<const volatile unsigned long long *>(row + i) : tag;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = base + u * (int)blockDim.x + (int)threadIdx.x;
+                if (i >= len) continue;
+                recv[(size_t)q * P2P_ROW_WORDS + i] = (uint32_t)(e[u] >> 32) == seq ? (uint32_t)e[u] : p2p_poll(row + i, seq, st, dead);
             }
         }
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-            if (at[u] >= 0) recv[at[u]] = (uint32_t)(e[u] >> 32) == seq ? (uint32_t)e[u] : p2p_poll(mine + at[u], seq, st, dead);
     }
     __syncthreads();
     if (threadIdx.x == 0) st->comm_seq = seq;
