@@ -259,7 +259,7 @@ struct icpb_ctx {
         size_t timed_iters = 0;
     } run;
     unsigned tm_blocks = 0; // co-resident blocks of trim_moments_kernel (0: not queried yet)
-    uint32_t *d_lhist = nullptr; // linear histogram of the pair distances (search epilogue -> trim_linear_kernel)
+    uint32_t *d_lhist = nullptr; // linear histogram of the pair distances (search epilogue -> trim_moments_kernel)
     unsigned long long *d_counter = nullptr;
     DevBuf<double> partials;
     DevBuf<double> trace;

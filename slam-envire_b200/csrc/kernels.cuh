@@ -176,17 +176,6 @@ __global__ void pad_tail_kernel(MPoint *__restrict__ pts, FPoint *__restrict__ p
     ptsf[n + threadIdx.x] = f;
 }
 
-// number of distinct keys in a sorted key array (occupied cells)
-__global__ void __launch_bounds__(256) count_unique_kernel(const uint32_t *__restrict__ keys, uint32_t n,
-                                                           unsigned long long *__restrict__ counter)
-{
-    unsigned c = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        c += (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(counter, (unsigned long long)c);
-}
-
 // Tight boxes without a pass per cell: every level-0 cell owns 48 bits (cell_bits[]), one per sixteenth of the cell edge
 // and axis (bits 0-15 x, 16-31 y, 32-47 z); a point ORs in the three sixteenths it lies in.  The box of the cell is
 // lowest / highest set bit per axis -- and a cloud appended later only ORs its own points in (the growing model).
@@ -373,7 +362,7 @@ __global__ void node_levelN_kernel(const uint32_t *__restrict__ below, int nx, i
 // ---------------------------------------------------------------------------
 // K2 + K3: transform the source vertex and find its exact nearest model point
 // ---------------------------------------------------------------------------
-// linear binning of the pair distances over [0, d_box] (fused first step of the trim, see trim_linear_kernel)
+// linear binning of the pair distances over [0, d_box] (fused first step of the trim, see trim_moments_kernel)
 constexpr int LIN_BINS = 2048;
 #ifndef ICPB_LIN_STRIDE
 #define ICPB_LIN_STRIDE 8
@@ -505,7 +494,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, ICPB_SEARCH_MIN_BLOCKS)
             found = search_finish<EAN>(i, s.bpos, s.bd2, icpb_nn_lower_bound(g, s), true, d_box, M, ean, nn_pos, nn_d, nn_lb, dq);
         }
     }
-    // K4's first step, fused: the linear histogram of the pair distances over [0, d_box] (trim_linear_kernel); one atomic
+    // K4's first step, fused: the linear histogram of the pair distances over [0, d_box] (trim_moments_kernel); one atomic
     // per distinct bin and warp.  Not in the first loop body (d_box = inf), which is trimmed by the radix passes.
     if (lhist && d_box_h < icpb_inf()) {
         const unsigned bin = dq < icpb_inf() ? lin_bin(dq, lin_scale(d_box_h)) : ICPB_NONE;
@@ -1086,7 +1075,7 @@ __global__ void __launch_bounds__(SEL_THREADS)
     }
 }
 
-// Exact selection across ranks (last block of trim_linear_kernel, source sharded over several GPUs): the s_krem-th
+// Exact selection across ranks (selecting block of trim_moments_kernel, source sharded over several GPUs): the s_krem-th
 // smallest of ALL ranks' pairs of the chosen bin in the order (distance, rank, pair index) -- "lower ranks first, then
 // local position", the global pair order of a contiguous sharding.  Exchange #2 of the loop body carries every rank's
 // candidates (key lo, key hi, pair index) to every rank, so all of them finish on the union with identical arithmetic:
