@@ -266,6 +266,35 @@ def test_fused_trim_moments_matches_separate(icp, oracle, synth):
     assert np.allclose(got[1, 1][0].matrix(), got[0, 1][0].matrix(), rtol=0, atol=1e-12)
 
 
+def test_align_lattice_mass_ties_in_the_linear_trim(icp, oracle):
+    """A lattice against its shifted copy: after the first loop body thousands of pairs have EXACTLY the same distance,
+    all in one bin and one sub-bin of the linear trim -- the selecting block of trim_moments_kernel gathers > 1024
+    candidates from the warps' segments, falls back to the radix digits and breaks the tie on the pair index (the lowest
+    indices are kept, like the oracle's stable order).  Fused and separate moments, graph and stream loop."""
+    g = np.arange(0, 120, dtype=np.float64)
+    m = np.stack(np.meshgrid(g, g, indexing="ij"), -1).reshape(-1, 2)
+    m = np.concatenate([m, np.zeros((len(m), 1))], 1)
+    s = m + [0.3, 0.2, 0.0]
+    prm = dict(max_iter=5, min_mse=1e-12, min_mse_diff=1e-14, overlap=0.55)
+    for fuse in (1, 0):
+        icp.set_option("fuse_moments", fuse)
+        for graph in (1, 0):
+            icp.set_option("graph", graph)
+            r, r_ref, run = _align_both(icp, oracle, m, s, **prm)
+            # (the clouds end up exactly aligned: the final mse is rounding noise on both sides, so no relative test on it)
+            assert r.iter == r_ref.iter and r.pairs == r_ref.pairs == int(len(s) * 0.55)
+            assert_transform_close(r.matrix(), r_ref.matrix(), 120.0)
+            tr, tr_ref = icp.trace(), run.trace()
+            assert [(a["found"], a["kept"]) for a in tr] == [(b["found"], b["kept"]) for b in tr_ref]
+            assert abs(tr[0]["tau"] - tr_ref[0]["tau"]) <= 1e-12 and abs(tr[1]["tau"] - tr_ref[1]["tau"]) <= 1e-9
+            pd, pd_ref = icp.pairs_distance(), run.pairs_distance()
+            assert len(pd) == len(pd_ref) == r.pairs and np.all(np.diff(pd) >= 0) and np.allclose(pd, pd_ref, rtol=0, atol=1e-9)
+            i_gpu, d_gpu, kept = icp.debug_pairs()
+            assert kept.sum() == r.pairs
+    icp.set_option("graph", 1)
+    icp.set_option("fuse_moments", -1)
+
+
 def test_align_cfg2_scaled_noise_and_source_frame(icp, oracle, synth):
     """1M-vs-1M config at 1/20 scale, Gaussian noise, overlap 0.8; the source cloud sits in its own frame."""
     m, s, T, prm = synth.config("cfg2", scale=0.05)
