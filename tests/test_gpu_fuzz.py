@@ -1,6 +1,8 @@
 """Randomised parity sweep: many small, oddly shaped problems through the C ABI against the oracle.  Covers what the
 fixed cases do not: degenerate clouds (planes, lines, duplicates, lattices with massive ties), queries far outside
 the grid, forced cell sizes (different pyramid depths), tiny and empty inputs, random d_box / overlap / density."""
+import os
+
 import numpy as np
 import pytest
 
@@ -33,9 +35,10 @@ def _cloud(rng, kind, n):
 
 
 KINDS = ["volume", "plane", "line", "lattice", "clusters", "duplicates"]
+EXTRA = int(os.environ.get("ICPB_FUZZ_EXTRA", "0"))  # soak runs: that many more seeds per test
 
 
-@pytest.mark.parametrize("seed", range(60))
+@pytest.mark.parametrize("seed", range(60 + EXTRA))
 def test_find_pairs_fuzz(pkg, oracle, seed):
     rng = np.random.default_rng(1000 + seed)
     kind = KINDS[seed % len(KINDS)]
@@ -63,7 +66,7 @@ def test_find_pairs_fuzz(pkg, oracle, seed):
     icp.close()
 
 
-@pytest.mark.parametrize("seed", range(30))
+@pytest.mark.parametrize("seed", range(30 + EXTRA))
 def test_align_fuzz(pkg, oracle, synth, seed):
     rng = np.random.default_rng(5000 + seed)
     kind = ["volume", "plane", "clusters", "lattice"][seed % 4]
@@ -99,13 +102,42 @@ def test_align_fuzz(pkg, oracle, synth, seed):
     idx_ref, _ = run.last_pairs() if tr_ref else (np.zeros(0, np.uint32), None)
     distinct = len(np.unique(idx_ref[idx_ref != 0xFFFFFFFF])) if len(idx_ref) else 0
     sv = np.linalg.svd(m - m.mean(0), compute_uv=False) if len(m) > 3 else np.zeros(3)
-    well_posed = distinct >= 12 and r_ref.pairs >= 12 and sv[1] > 1e-3 * sv[0]
+    # ... and the same for the FIRST body: a source blob a few units off a tight cluster pairs all its points with the one
+    # or two model points facing it -- the cross-covariance is rounding noise and the reference's rotation arbitrary
+    from oracle import oracle as O
+    vis0 = s[O.density_indices(len(s), density)]
+    if T_src is not None:
+        vis0 = vis0 @ T_src[:3, :3].T + T_src[:3, 3]
+    distinct0 = 0
+    if len(vis0):
+        idx0, d0 = M.find_pairs(vis0)
+        kept0, _ = O.trim(np.where(idx0 == 0xFFFFFFFF, np.inf, d0), int(int(len(s) * density) * prm["overlap"]))
+        distinct0 = len(np.unique(idx0[kept0]))  # distinct model points among the pairs the first trim keeps
+    well_posed = distinct >= 12 and distinct0 >= 12 and r_ref.pairs >= 12 and sv[1] > 1e-3 * sv[0]
     if well_posed:
-        assert r.iter == r_ref.iter and r.pairs == r_ref.pairs, (kind, n, ns, prm)
-        assert [t["kept"] for t in tr] == [t["kept"] for t in tr_ref]
-        assert [t["found"] for t in tr] == [t["found"] for t in tr_ref]
-        assert_transform_close(r.matrix(), r_ref.matrix(), max(span, 1.0), rot_tol=1e-5, trans_tol_rel=1e-6)
-        if np.isfinite(r_ref.mse) and r_ref.mse > 1e-20:
-            assert abs(r.mse - r_ref.mse) <= 1e-5 * r_ref.mse
-        assert len(icp.pairs_distance()) == len(run.pairs_distance())
+        def agrees(a_res, a_tr, n_pd):
+            try:
+                assert a_res.iter == r_ref.iter and a_res.pairs == r_ref.pairs, (kind, n, ns, prm)
+                assert [t["kept"] for t in a_tr] == [t["kept"] for t in tr_ref]
+                assert [t["found"] for t in a_tr] == [t["found"] for t in tr_ref]
+                assert_transform_close(a_res.matrix(), r_ref.matrix(), max(span, 1.0), rot_tol=1e-5, trans_tol_rel=1e-6)
+                if np.isfinite(r_ref.mse) and r_ref.mse > 1e-20:
+                    assert abs(a_res.mse - r_ref.mse) <= 1e-5 * r_ref.mse
+                assert n_pd == len(run.pairs_distance())
+            except AssertionError as e:
+                return e
+            return None
+        err = agrees(r, tr, len(icp.pairs_distance()))
+        if err is not None:
+            # Is the REFERENCE itself stable here?  Its sums run in visiting order; the device sums in its own order.  If
+            # the oracle, fed the same visited vertices in reverse order, does not reproduce its own result within the
+            # tolerances, the case is ill-conditioned (e.g. all kept pairs inside one tight cluster) and proves nothing.
+            from oracle import oracle as O
+            visited = s[O.density_indices(len(s), density)]
+            run2 = oracle.Run()
+            r2 = M.align(visited[::-1].copy(), T=T_src, density=1.0, run=run2, **prm)
+            # (lattices: reversing the order also changes which of the equidistant pairs the stable trim keeps, so there a
+            # disagreement is never excused)
+            if kind == "lattice" or agrees(r2, run2.trace(), len(run2.pairs_distance())) is None:
+                raise err
     icp.close()
