@@ -9,7 +9,9 @@ import numpy as np
 import pytest
 from scipy.spatial import cKDTree
 
-from conftest import assert_transform_close
+import os
+
+from conftest import ROOT, assert_transform_close
 
 
 def test_density_stepping(oracle):
@@ -255,3 +257,23 @@ def test_apply_transform(oracle, synth):
     assert np.allclose(out[:3, :3], U @ Vt, atol=1e-14)
     assert np.allclose(out[:3, 3], raw[:3, 3], atol=1e-14)
     assert np.allclose(out[:3, :3] @ out[:3, :3].T, np.eye(3), atol=1e-15)
+
+
+def test_oracle_under_sanitizers(tmp_path):
+    """The C restatement built with -fsanitize=address,undefined and driven through model add / align / golden section /
+    ties / tiny and empty inputs (oracle/san/san_driver.c): no report, no leak."""
+    import shutil, subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("gcc missing")
+    exe = str(tmp_path / "orc_san")
+    src = [os.path.join(ROOT, "oracle", "san", "san_driver.c"), os.path.join(ROOT, "oracle", "icp_oracle.c")]
+    b = subprocess.run(["gcc", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-ffp-contract=off",
+                        "-fopenmp", "-std=c11", "-D_POSIX_C_SOURCE=200809L", "-o", exe] + src + ["-lm"],
+                       capture_output=True, text=True)
+    if b.returncode != 0 and "sanitize" in (b.stderr or ""):
+        pytest.skip("sanitizer runtime missing")
+    assert b.returncode == 0, b.stderr[-2000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, ASAN_OPTIONS="detect_leaks=1", UBSAN_OPTIONS="halt_on_error=1"))
+    assert r.returncode == 0 and "SAN_OK" in r.stdout and "runtime error" not in r.stderr and "ERROR: AddressSanitizer" not in r.stderr, \
+        r.stdout[-500:] + r.stderr[-2000:]
