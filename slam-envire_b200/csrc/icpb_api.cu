@@ -6,6 +6,7 @@
 // flag so it never stalls the stream), and result read-back.
 // There is NO CPU fallback in this file: every compute step is a kernel.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
@@ -171,6 +172,14 @@ const T *density_gather_t(const T *v, size_t n, int width, double density, std::
     }
     return tmp.data();
 }
+// NVTX range over a host-side phase (model add / grid build / merge-append / source upload / align): shows up in
+// Nsight timelines; costs a few nanoseconds without a tool attached
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
 // ICPB_VERBOSE=1: wall-clock marks (with a stream sync each) through the build / append paths, printed to stderr
 struct PhaseMarks {
     bool on;
@@ -526,6 +535,7 @@ static int stage_visited(icpb_ctx *ctx, const double *xyz, size_t n, double dens
 // built grid or the batch does not fit inside the grid box.
 static int try_merge_append(icpb_ctx *ctx, size_t n_old, size_t k, bool *done)
 {
+    NvtxRange nvtx_range("icpb: merge-append (K1b)");
     *done = false;
     if (ctx->opt_merge == 0.0 || ctx->grid_dirty || n_old == 0 || ctx->gv.n != n_old || k == 0) return ICPB_OK;
     if (n_old + k >= 0xFFFFFFF0ull) return ICPB_OK;
@@ -622,6 +632,7 @@ static int try_merge_append(icpb_ctx *ctx, size_t n_old, size_t k, bool *done)
 static int model_add(icpb_ctx *ctx, const double *xyz, const double *normals, const int32_t *attrs, size_t n,
                      const double T[16], double density)
 {
+    NvtxRange nvtx_range("icpb: addToModel (K0)");
     if (!ctx || (!xyz && n) || !T || !(density > 0.0)) return ICPB_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     const bool ean = normals != nullptr;
@@ -777,6 +788,7 @@ static int update_masks(icpb_ctx *ctx, const uint32_t *keys, size_t k)
 
 static int build_grid(icpb_ctx *ctx)
 {
+    NvtxRange nvtx_range("icpb: grid build (K1)");
     const size_t n = ctx->model_n;
     cudaStream_t s = ctx->stream;
     memset(&ctx->ginfo, 0, sizeof(ctx->ginfo));
@@ -1092,6 +1104,7 @@ static int upload_points(icpb_ctx *ctx, size_t m, bool wait)
 
 static int source_upload(icpb_ctx *ctx, const double *xyz, size_t n, const double T[16], double density, bool wait)
 {
+    NvtxRange nvtx_range("icpb: source upload (K0 + Hilbert sort)");
     if (!ctx || (!xyz && n) || !T || !(density > 0.0)) return ICPB_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaEventRecord(ctx->ev_up0, ctx->stream));
@@ -1296,6 +1309,7 @@ static int launch_trim(icpb_ctx *ctx, uint32_t n, bool linear = false, bool *mom
 // back; icpb_multi_align_resident enqueues on every device first, so that the ranks' fused exchanges meet.
 static int align_enqueue(icpb_ctx *ctx, const icpb_params *prm, bool graph_only)
 {
+    NvtxRange nvtx_range("icpb: _align enqueue (K3-K6 loop)");
     if (!ctx || !prm) return ICPB_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     ctx->run.pending = false;
@@ -1555,6 +1569,7 @@ static int align_enqueue(icpb_ctx *ctx, const icpb_params *prm, bool graph_only)
 
 static int align_collect(icpb_ctx *ctx, icpb_result *out)
 {
+    NvtxRange nvtx_range("icpb: _align wait + result");
     if (!ctx || !out || !ctx->run.pending) return ICPB_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     ctx->run.pending = false;
