@@ -581,16 +581,17 @@ ICPB_HD void icpb_nn_block(const GridView &g, NNState &s, NNRun *runs, int strid
     }
     // one flattened loop over the runs: four candidates per trip, marks (icpb_scan_runs), exact evaluation at the end
     uint32_t p = 0, e = 0, base = 0, marks = 0;
-    int r = -1;
+    int r = -1, nm = 0;
     for (;;) {
         if (p >= e) {
-            // the marks of a run's last chunk wait in the run's own slot until every run is scanned: the exact
+            // the marks of a run's last chunk wait in a slot the scan is through with until every run is scanned: the exact
             // evaluations then happen where the lanes of the warp have come together again (cfg2: 16.0 vs 16.7 ms of
             // search per align against evaluating at the end of every run)
-            if (r >= 0) {
-                runs[r * stride].s = base;
-                runs[r * stride].e = marks;
+            if (marks) { // slots 0..r are free: this run's range has been read
+                runs[nm * stride].s = base;
+                runs[nm * stride].e = marks;
                 marks = 0;
+                ++nm;
             }
             ++r;
             if (r >= nr) break;
@@ -613,7 +614,7 @@ ICPB_HD void icpb_nn_block(const GridView &g, NNState &s, NNRun *runs, int strid
             base = p;
         }
     }
-    for (r = 0; r < nr; ++r) {
+    for (r = 0; r < nm; ++r) { // lanes that marked anything mostly did so in one run: their evaluations coincide at r == 0
         uint32_t mk = runs[r * stride].e;
         icpb_flush_marks(g, runs[r * stride].s, mk, s);
     }
