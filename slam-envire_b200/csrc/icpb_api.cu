@@ -275,6 +275,8 @@ struct icpb_ctx {
     int trace_cap = 0;
     int last_executed = 0;
     bool last_valid = false, last_early = false;
+    bool pd_valid = false; // nn_d / src_perm / the trim state of the last align are intact: its kept distances can still be listed
+                           // (a model change invalidates the winners' positions -- last_valid -- but not the distances)
     // K7 / debug scratch
     DevBuf<unsigned long long> kd0, kd1, cand_key, seg_key, cell_bits; // cell_bits: occupied sixteenths per level-0 cell and axis (tight boxes) // seg_*: per-warp candidate segments of trim_moments_kernel
     DevBuf<uint32_t> cand_idx, xscratch, seg_idx, seg_count, occ_bits; // occ_bits: one bit per cell while the build tunes the cell edge
@@ -1097,6 +1099,7 @@ static int upload_points(icpb_ctx *ctx, size_t m, bool wait)
     ctx->have_source = true;
     ctx->src_ean = false;
     ctx->last_valid = false;
+    ctx->pd_valid = false;
     ctx->upload_pending = true;
     if (wait) return upload_wait(ctx);
     return ICPB_OK;
@@ -1313,6 +1316,7 @@ static int align_enqueue(icpb_ctx *ctx, const icpb_params *prm, bool graph_only)
     if (!ctx || !prm) return ICPB_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     ctx->run.pending = false;
+    ctx->pd_valid = false;
     if (!ctx->have_source) return ICPB_ERR_NO_SOURCE;
     if (ctx->grid_dirty) {
         int rc = build_grid(ctx);
@@ -1573,6 +1577,7 @@ static int align_collect(icpb_ctx *ctx, icpb_result *out)
     if (!ctx || !out || !ctx->run.pending) return ICPB_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     ctx->run.pending = false;
+    ctx->pd_valid = false;
     cudaStream_t s = ctx->stream;
     const unsigned long long launches0 = ctx->run.launches0;
     const bool use_graph = ctx->run.use_graph, linear_ok = ctx->run.linear_ok;
@@ -1602,6 +1607,7 @@ static int align_collect(icpb_ctx *ctx, icpb_result *out)
     ctx->last_executed = hs.executed;
     ctx->last_early = hs.early != 0;
     ctx->last_valid = hs.executed > 0;
+    ctx->pd_valid = ctx->last_valid;
 
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end);
@@ -1673,7 +1679,8 @@ int icpb_pairs_distance(icpb_ctx *ctx, double *out, size_t capacity, size_t *n_o
     CK(cudaSetDevice(ctx->device));
     *n_out = 0;
     // _align returns before filling pairs_distance when pairs < MIN_PAIRS (icp/icp.hpp:475-476,500-504)
-    if (!ctx->last_valid || ctx->last_early) return ICPB_OK;
+    // (they outlive addToModel / clearModel: the reference keeps them in minResult until the next align)
+    if (!ctx->pd_valid || ctx->last_early) return ICPB_OK;
     cudaStream_t s = ctx->stream;
     const uint32_t n = (uint32_t)ctx->src_n;
     size_t kept = (size_t)ctx->h_state->pairs;
@@ -1781,6 +1788,7 @@ int icpb_find_pairs(icpb_ctx *ctx, const double *q, size_t n, double d_box, uint
     CK(cudaStreamSynchronize(s));
     ctx->have_source = false; // stage / scratch were reused
     ctx->last_valid = false;
+    ctx->pd_valid = false;
     return ICPB_OK;
 }
 
@@ -1824,6 +1832,7 @@ int icpb_trim(icpb_ctx *ctx, const double *dist, size_t n, size_t n_po, double *
     if (n_ties_kept) *n_ties_kept = (size_t)ctx->h_state->quota;
     ctx->have_source = false;
     ctx->last_valid = false;
+    ctx->pd_valid = false;
     return ICPB_OK;
 }
 
@@ -1897,6 +1906,7 @@ int icpb_pairs_transform(icpb_ctx *ctx, const double *x, const double *p, const 
     *kept = (size_t)hs.pairs;
     ctx->have_source = false;
     ctx->last_valid = false;
+    ctx->pd_valid = false;
     return hs.early ? ICPB_ERR_NOT_ENOUGH_PAIRS : ICPB_OK;
 }
 

@@ -294,7 +294,7 @@ public:
     }
     void addToModel(_Adapter model)
     {
-        fetchPairsDistance(minResult_); // the kept distances of the last align live in device scratch: secure them first
+        // (the kept distances of the last align stay listable after a model change: icpb_pairs_distance)
         double T[16];
         toColMajor(model.local2global(), T);
         if (multi_) check(icpb_multi_model_add(multi_, model.vertexData(), model.vertexCount(), T, model.density()));
@@ -302,7 +302,6 @@ public:
     }
     void clearModel()
     {
-        fetchPairsDistance(minResult_);
         check(multi_ ? icpb_multi_model_clear(multi_) : icpb_model_clear(ctx_));
     }
 

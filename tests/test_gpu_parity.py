@@ -295,6 +295,30 @@ def test_align_lattice_mass_ties_in_the_linear_trim(icp, oracle):
     icp.set_option("fuse_moments", -1)
 
 
+def test_pairs_distance_outlives_model_changes(icp, synth):
+    """Trimmed::getPairsDistance returns the kept distances of the LAST align until the next one (they live in minResult,
+    icp/icp.hpp:500-504) -- also after addToModel (a growing-map loop: align, add the scan, read the distances) and
+    clearModel.  On the device they are listed from the align's scratch, which a model change leaves intact."""
+    m, s, T, prm = synth.config("cfg1", 0.1)
+    icp.clear_model()
+    icp.add_to_model(m)
+    r = icp.align(s, **dict(prm, max_iter=6))
+    icp.add_to_model(s[:2000])          # merged into the built index
+    pd_after_add = icp.pairs_distance()
+    icp.set_option("cell_size", 0.3)    # forces a rebuild at the next use
+    icp.build()
+    pd_after_rebuild = icp.pairs_distance()
+    icp.clear_model()
+    pd_after_clear = icp.pairs_distance()
+    icp.set_option("cell_size", 0.0)
+    icp.add_to_model(m)
+    r2 = icp.align(s, **dict(prm, max_iter=6))
+    pd = icp.pairs_distance()
+    assert r2.pairs == r.pairs == len(pd) and np.all(np.diff(pd) >= 0)
+    for other in (pd_after_add, pd_after_rebuild, pd_after_clear):
+        assert np.array_equal(other, pd)
+
+
 def test_align_cfg2_scaled_noise_and_source_frame(icp, oracle, synth):
     """1M-vs-1M config at 1/20 scale, Gaussian noise, overlap 0.8; the source cloud sits in its own frame."""
     m, s, T, prm = synth.config("cfg2", scale=0.05)
