@@ -640,6 +640,7 @@ static int model_add(icpb_ctx *ctx, const double *xyz, const double *normals, co
     const bool ean = normals != nullptr;
     if (ean && !attrs) return ICPB_ERR_ARG;
     if (ctx->model_n > 0 && ean != ctx->model_ean) return ICPB_ERR_ARG; // all plain or all edge-and-normal
+    PhaseMarks pm("addToModel", ctx->stream);
     size_t m = 0;
     {
         int rc = stage_visited(ctx, xyz, n, density, &m); // K0: the visited vertices, gathered on the device
@@ -647,13 +648,16 @@ static int model_add(icpb_ctx *ctx, const double *xyz, const double *normals, co
     }
     if (m == 0) return ICPB_OK;
     if (ctx->model_n + m >= 0xFFFFFFF0ull) return ICPB_ERR_ARG;
+    pm.mark("copy");
     CK(ctx->model_raw.ensure_keep(3 * (ctx->model_n + m), 3 * ctx->model_n, ctx->stream));
+    pm.mark("grow");
     Aff12 A;
     cm_to_aff12(T, A.a);
     transform_append_kernel<<<grid_for(m, 256), 256, 0, ctx->stream>>>(ctx->stage.p, m, A,
                                                                        ctx->model_raw.p + 3 * ctx->model_n);
     CKL();
     CK(cudaStreamSynchronize(ctx->stream)); // the caller's buffer may go away
+    pm.mark("transform");
     if (ean) {
         std::vector<double> tn;
         std::vector<int32_t> ta;
