@@ -136,7 +136,8 @@ int icpb_align(icpb_ctx *, const double *xyz_aos, size_t n_vertices, const doubl
                double density, const icpb_params *, icpb_result *out);
 
 /* Replaces: Trimmed::getPairsDistance (icp/icp.hpp:439, filled at :500-504):
- * kept distances of the last executed iteration, ascending.  With
+ * kept distances of the last executed iteration, ascending; available until the next align / source upload (model
+ * changes in between do not disturb them).  With
  * out == NULL only *n_out is written (the count of all ranks' kept pairs).  After a sharded (multi-GPU) align every
  * rank returns the kept distances of ITS shard (*n_out = their number): concatenate and merge for the full list. */
 int icpb_pairs_distance(icpb_ctx *, double *out_sorted, size_t capacity, size_t *n_out);
